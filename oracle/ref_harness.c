@@ -1,0 +1,403 @@
+/* oracle/ref_harness.c -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * Flat, ctypes-friendly entry points around the UNMODIFIED reference rtlib
+ * (compiled from /root/reference by oracle/Makefile into oracle/_ref/libace_ref.so).
+ * Every function here only marshals raw int64 limb buffers into the reference's
+ * POLYNOMIAL / CIPHERTEXT structs and calls the reference's own API:
+ *   Prepare_context            fhe-cmplr/rtlib/ant/src/rtlib/context.c:29
+ *   Hw_modadd/modmul/rotate    fhe-cmplr/rtlib/ant/src/poly/poly_arith.c:14-56
+ *   Decomp_modup/Mod_down/Rescale  fhe-cmplr/rtlib/ant/src/poly/poly_eval.c:28-49
+ *   Ftt_fwd / Ftt_inv          fhe-cmplr/rtlib/ant/src/util/ntt.c:163-187
+ *   Rotate_ciph/Mul_ciph/...   fhe-cmplr/rtlib/ant/src/ckks/cipher_eval.c:292-364
+ *
+ * Determinism: keygen/encrypt draw from (i) the BLAKE2 PRNG global `Prng`
+ * (prng.c:13,56-70) which we pre-seed, and (ii) libc rand() re-seeded with
+ * srand(time) before every triangle sample (random_sample.c:20-24) which we
+ * neutralise by defining a no-op srand() in this shared object (linked with
+ * -Bsymbolic) and seeding once through srandom().
+ */
+#define _GNU_SOURCE
+#include <complex.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common/rt_api.h"
+#include "rt_ant/rt_ant.h"
+#include "util/ckks_bootstrap_context.h"
+#include "util/ckks_decryptor.h"
+#include "util/ckks_encoder.h"
+#include "util/ckks_encryptor.h"
+#include "util/ckks_evaluator.h"
+#include "util/ckks_key_generator.h"
+#include "util/ckks_parameters.h"
+#include "util/crt.h"
+#include "util/ntt.h"
+#include "util/prng.h"
+
+/* ---- pinned randomness ------------------------------------------------- */
+void srand(unsigned seed) { (void)seed; } /* swallow srand(time) */
+
+extern BLAKE2_PRNG* Prng;
+BLAKE2_PRNG*        Alloc_blake2_prng();
+
+static void Pin_random(void) {
+  srandom(12345u);
+  if (Prng == NULL) Prng = Alloc_blake2_prng();
+  for (uint32_t i = 0; i < SEED_CNT; i++) {
+    Set_ui32_value(Prng->_seed, i, 0x9e3779b9u * (i + 1));
+  }
+  Prng->_counter    = 0;
+  Prng->_buffer_idx = 0;
+}
+
+/* ---- callbacks the runtime expects from the emitted translation unit ---- */
+static CKKS_PARAMS* Harness_params = NULL;
+CKKS_PARAMS*        Get_context_params() { return Harness_params; }
+RT_DATA_INFO*       Get_rt_data_info() { return NULL; }
+int                 Get_input_count() { return 0; }
+int                 Get_output_count() { return 0; }
+DATA_SCHEME*        Get_encode_scheme(int idx) { (void)idx; return NULL; }
+DATA_SCHEME*        Get_decode_scheme(int idx) { (void)idx; return NULL; }
+bool                Main_graph() { return true; }
+
+/* ---- context ------------------------------------------------------------ */
+int ref_init(uint32_t degree, size_t mul_depth, size_t first_mod_size,
+             size_t scaling_mod_size, size_t num_q_parts, size_t hamming_weight,
+             const int32_t* rot_idxs, size_t num_rot_idx, int with_bootstrap) {
+  if (Context != NULL) return -1;
+  Pin_random();
+  size_t sz      = sizeof(CKKS_PARAMS) + sizeof(int32_t) * (num_rot_idx + 1);
+  Harness_params = (CKKS_PARAMS*)calloc(1, sz);
+  Harness_params->_provider         = LIB_ANT;
+  Harness_params->_poly_degree      = degree;
+  Harness_params->_sec_level        = 0;
+  Harness_params->_mul_depth        = mul_depth;
+  Harness_params->_first_mod_size   = first_mod_size;
+  Harness_params->_scaling_mod_size = scaling_mod_size;
+  Harness_params->_num_q_parts      = num_q_parts;
+  Harness_params->_hamming_weight   = hamming_weight;
+  Harness_params->_num_rot_idx      = num_rot_idx;
+  for (size_t i = 0; i < num_rot_idx; i++) {
+    Harness_params->_rot_idxs[i] = rot_idxs[i];
+  }
+  if (with_bootstrap) {
+    Prepare_context(); /* includes Bootstrap_precom(N/2) when the depth allows it */
+    return 0;
+  }
+  /* Same object graph as Prepare_context (context.c:29-86) minus Bootstrap_precom and the
+   * weight file, for primitive-level runs where bootstrap keys would cost minutes. */
+  Io_init();
+  CKKS_PARAMETER* params = Alloc_ckks_parameter();
+  Set_num_q_parts(params, num_q_parts);
+  Init_ckks_parameters_with_prime_size(params, degree, Get_sec_level(0), mul_depth + 1,
+                                       first_mod_size, scaling_mod_size, hamming_weight);
+  CKKS_CONTEXT*       ctxt   = (CKKS_CONTEXT*)malloc(sizeof(CKKS_CONTEXT));
+  CKKS_KEY_GENERATOR* keygen =
+      Alloc_ckks_key_generator(params, Harness_params->_rot_idxs, num_rot_idx);
+  CKKS_ENCODER*   encoder = Alloc_ckks_encoder(params);
+  CKKS_ENCRYPTOR* encryptor =
+      Alloc_ckks_encryptor(params, keygen->_public_key, keygen->_secret_key);
+  CKKS_DECRYPTOR* decryptor = Alloc_ckks_decryptor(params, keygen->_secret_key);
+  ctxt->_params        = (PTR_TY)params;
+  ctxt->_key_generator = (PTR_TY)keygen;
+  ctxt->_encoder       = (PTR_TY)encoder;
+  ctxt->_encryptor     = (PTR_TY)encryptor;
+  ctxt->_decryptor     = (PTR_TY)decryptor;
+  ctxt->_evaluator = (PTR_TY)Alloc_ckks_evaluator(params, encoder, decryptor, keygen);
+  Context          = ctxt;
+  return 0;
+}
+
+void ref_fini(void) {
+  if (Context) Finalize_context();
+  free(Harness_params);
+  Harness_params = NULL;
+}
+
+static CRT_CONTEXT* Crt(void) { return Get_crt_context(); }
+uint32_t ref_degree(void) { return Degree(); }
+size_t   ref_num_q(void) { return Get_primes_cnt(Get_q(Crt())); }
+size_t   ref_num_p(void) { return Get_primes_cnt(Get_p(Crt())); }
+size_t   ref_num_parts(void) { return Get_num_parts(Get_qpart(Crt())); }
+size_t   ref_part_size(void) { return Get_per_part_size(Get_qpart(Crt())); }
+double   ref_default_scale(void) { return Get_default_sc(); }
+
+void ref_get_primes(int64_t* q, int64_t* p) {
+  MODULUS* m = Q_modulus();
+  for (size_t i = 0; i < ref_num_q(); i++) q[i] = Get_mod_val(m + i);
+  m = P_modulus();
+  for (size_t i = 0; i < ref_num_p(); i++) p[i] = Get_mod_val(m + i);
+}
+
+/* is_p: 0 -> i-th Q prime, 1 -> i-th P prime */
+static CRT_PRIME* Prime_at(int is_p, size_t idx) {
+  return Get_prime_at(is_p ? Get_p(Crt()) : Get_q(Crt()), idx);
+}
+
+/* root of unity actually used by the NTT tables: rou[bitrev(1)] = rou[N/2] */
+int64_t ref_psi(int is_p, size_t idx) {
+  NTT_CONTEXT* ntt = Get_ntt(Prime_at(is_p, idx));
+  return Get_i64_value_at(ntt->_rou, ntt->_degree >> 1);
+}
+
+void ref_ntt(int is_p, size_t idx, int64_t* data) {
+  VALUE_LIST vl;
+  Init_i64_value_list_no_copy(&vl, Degree(), data);
+  Ftt_fwd(&vl, Get_ntt(Prime_at(is_p, idx)), &vl);
+}
+
+void ref_intt(int is_p, size_t idx, int64_t* data) {
+  VALUE_LIST vl;
+  Init_i64_value_list_no_copy(&vl, Degree(), data);
+  Ftt_inv(&vl, Get_ntt(Prime_at(is_p, idx)), &vl);
+}
+
+/* ---- per-limb "hardware" ops (boundary a4) -------------------------------- */
+static MODULUS* Mod_at(int is_p, size_t idx) {
+  return (is_p ? P_modulus() : Q_modulus()) + idx;
+}
+void ref_hw_modadd(int64_t* r, int64_t* a, int64_t* b, int is_p, size_t idx) {
+  Hw_modadd(r, a, b, Mod_at(is_p, idx), Degree());
+}
+void ref_hw_modmul(int64_t* r, int64_t* a, int64_t* b, int is_p, size_t idx) {
+  Hw_modmul(r, a, b, Mod_at(is_p, idx), Degree());
+}
+void ref_hw_rotate(int64_t* r, int64_t* a, int64_t* order, int is_p, size_t idx) {
+  Hw_rotate(r, a, order, Mod_at(is_p, idx), Degree());
+}
+
+int ref_auto_order(int32_t rot_idx, int64_t* out) {
+  memcpy(out, Auto_order(rot_idx), sizeof(int64_t) * Degree());
+  return (int)Auto_idx(rot_idx);
+}
+
+/* ---- polynomial-level ops (a5, a6, a8) ------------------------------------- */
+static void Wrap_poly(POLYNOMIAL* p, int64_t* data, size_t num_q, size_t num_p,
+                      bool is_ntt) {
+  memset(p, 0, sizeof(*p));
+  Init_poly_data(p, Degree(), num_q, num_p, data);
+  Set_is_ntt(p, is_ntt);
+}
+
+/* in: num_q limbs (NTT form). out: (num_q + K) limbs. */
+void ref_decomp_modup(int64_t* out, int64_t* in, size_t num_q, uint32_t part) {
+  POLYNOMIAL res, poly;
+  Wrap_poly(&poly, in, num_q, 0, true);
+  Wrap_poly(&res, out, num_q, ref_num_p(), true);
+  Decomp_modup(&res, &poly, part);
+}
+
+/* unfused pair Decomp + Mod_up (poly_eval.c:11-26) */
+void ref_decomp_then_modup(int64_t* out, int64_t* in, size_t num_q, uint32_t part) {
+  POLYNOMIAL res, poly, dec;
+  Wrap_poly(&poly, in, num_q, 0, true);
+  Wrap_poly(&res, out, num_q, ref_num_p(), true);
+  memset(&dec, 0, sizeof(dec));
+  Alloc_poly_data(&dec, Degree(), ref_part_size(), 0);
+  Decomp(&dec, &poly, part);
+  Mod_up(&res, &dec, part);
+  Free_poly_data(&dec);
+}
+
+/* in: (num_q + K) limbs NTT form. out: num_q limbs. NOTE: clobbers the P part of `in`
+ * exactly like the reference (in-place INTT, polynomial.c:941-945). */
+void ref_mod_down(int64_t* out, int64_t* in, size_t num_q) {
+  POLYNOMIAL res, poly;
+  Wrap_poly(&poly, in, num_q, ref_num_p(), true);
+  Wrap_poly(&res, out, num_q, 0, true);
+  Mod_down(&res, &poly);
+}
+
+/* in: num_q limbs NTT form. out: buffer of num_q limbs, first num_q-1 are valid. */
+void ref_rescale(int64_t* out, int64_t* in, size_t num_q) {
+  POLYNOMIAL res, poly;
+  Wrap_poly(&poly, in, num_q, 0, true);
+  Wrap_poly(&res, out, num_q, 0, true);
+  Rescale(&res, &poly);
+}
+
+/* ---- keys ------------------------------------------------------------------- */
+/* copies one key polynomial: (num_q_total + K) limbs, Q limbs first then P limbs */
+int ref_swk_export(int is_rot, int32_t rot_idx, uint32_t part, int which,
+                   int64_t* out) {
+  SW_KEY swk = Swk(is_rot, rot_idx);
+  if (part >= Get_swk_size(swk)) return -1;
+  POLY p = which ? Pk1_at(swk, part) : Pk0_at(swk, part);
+  memcpy(out, Get_poly_coeffs(p), Get_poly_mem_size(p));
+  return (int)Get_num_alloc_primes(p);
+}
+
+/* secret key in NTT form over Q then P */
+void ref_sk_export(int64_t* out) {
+  CKKS_KEY_GENERATOR* kg = (CKKS_KEY_GENERATOR*)Get_key_gen(Context);
+  POLYNOMIAL*         sk = Get_ntt_sk(kg->_secret_key);
+  memcpy(out, Get_poly_coeffs(sk), Get_poly_mem_size(sk));
+}
+
+void ref_pk_export(int64_t* pk0, int64_t* pk1) {
+  CKKS_KEY_GENERATOR* kg = (CKKS_KEY_GENERATOR*)Get_key_gen(Context);
+  memcpy(pk0, Get_poly_coeffs(Get_pk0(kg->_public_key)),
+         Get_poly_mem_size(Get_pk0(kg->_public_key)));
+  memcpy(pk1, Get_poly_coeffs(Get_pk1(kg->_public_key)),
+         Get_poly_mem_size(Get_pk1(kg->_public_key)));
+}
+
+/* ---- ciphertext-level ops ----------------------------------------------------- */
+typedef struct {
+  int64_t* c0;
+  int64_t* c1;
+  uint32_t level;
+  uint32_t slots;
+  uint32_t sf_degree;
+  double   scale;
+} REF_CT;
+
+static void Wrap_ct(CIPHERTEXT* ct, const REF_CT* r) {
+  memset(ct, 0, sizeof(*ct));
+  Wrap_poly(Get_c0(ct), r->c0, r->level, 0, true);
+  Wrap_poly(Get_c1(ct), r->c1, r->level, 0, true);
+  ct->_slots          = r->slots;
+  ct->_scaling_factor = r->scale;
+  ct->_sf_degree      = r->sf_degree;
+}
+
+static void Unwrap_ct(REF_CT* r, CIPHERTEXT* ct) {
+  size_t n = sizeof(int64_t) * Degree() * Get_ciph_level(ct);
+  memcpy(r->c0, Get_poly_coeffs(Get_c0(ct)), n);
+  memcpy(r->c1, Get_poly_coeffs(Get_c1(ct)), n);
+  r->level     = Get_ciph_level(ct);
+  r->slots     = Get_ciph_slots(ct);
+  r->sf_degree = Get_ciph_sf_degree(ct);
+  r->scale     = Get_ciph_sfactor(ct);
+}
+
+/* encode `len` real values into `slots` slots at `level`, sf_degree; out = level limbs */
+void ref_encode(int64_t* out, const double* vals, size_t len, uint32_t level,
+                uint32_t slots, uint32_t sf_degree, double* scale_out) {
+  VALUE_LIST* vec = Alloc_value_list(DCMPLX_TYPE, len);
+  for (size_t i = 0; i < len; i++) DCMPLX_VALUE_AT(vec, i) = vals[i];
+  PLAINTEXT* plain = Alloc_plaintext();
+  Encode_at_level_with_sf(plain, (CKKS_ENCODER*)Context->_encoder, vec, level,
+                          slots, sf_degree);
+  memcpy(out, Get_poly_coeffs(Get_plain_poly(plain)),
+         sizeof(int64_t) * Degree() * level);
+  if (scale_out) *scale_out = Get_plain_scaling_factor(plain);
+  Free_plaintext(plain);
+  Free_value_list(vec);
+}
+
+/* the run-time weight path: Encode_plain_from_float (plain_eval.c:25-42) */
+void ref_encode_float(int64_t* out, float* vals, size_t len, uint32_t sc_degree,
+                      uint32_t level, double* scale_out, uint32_t* slots_out) {
+  PLAINTEXT* plain = Alloc_plaintext();
+  Encode_plain_from_float(plain, vals, len, sc_degree, level);
+  memcpy(out, Get_poly_coeffs(Get_plain_poly(plain)),
+         sizeof(int64_t) * Degree() * Get_poly_level(Get_plain_poly(plain)));
+  if (scale_out) *scale_out = Get_plain_scaling_factor(plain);
+  if (slots_out) *slots_out = Get_plain_slots(plain);
+  Free_plaintext(plain);
+}
+
+void ref_encode_double(int64_t* out, double* vals, size_t len, uint32_t sc_degree,
+                       uint32_t level, double* scale_out, uint32_t* slots_out) {
+  PLAINTEXT* plain = Alloc_plaintext();
+  Encode_plain_from_double(plain, vals, len, sc_degree, level);
+  memcpy(out, Get_poly_coeffs(Get_plain_poly(plain)),
+         sizeof(int64_t) * Degree() * Get_poly_level(Get_plain_poly(plain)));
+  if (scale_out) *scale_out = Get_plain_scaling_factor(plain);
+  if (slots_out) *slots_out = Get_plain_slots(plain);
+  Free_plaintext(plain);
+}
+
+/* encode + pk-encrypt; r->c0/c1 must hold `level` limbs */
+void ref_encrypt(REF_CT* r, const double* vals, size_t len, uint32_t level,
+                 uint32_t slots) {
+  VALUE_LIST* vec = Alloc_value_list(DCMPLX_TYPE, len);
+  for (size_t i = 0; i < len; i++) DCMPLX_VALUE_AT(vec, i) = vals[i];
+  PLAINTEXT* plain = Alloc_plaintext();
+  Encode_at_level_with_sf(plain, (CKKS_ENCODER*)Context->_encoder, vec, level,
+                          slots, 1);
+  CIPHERTEXT* ct = Alloc_ciphertext();
+  Encrypt_msg(ct, (CKKS_ENCRYPTOR*)Context->_encryptor, plain);
+  Unwrap_ct(r, ct);
+  Free_ciphertext(ct);
+  Free_plaintext(plain);
+  Free_value_list(vec);
+}
+
+/* decrypt + decode; out must hold r->slots doubles (real parts) */
+void ref_decrypt(double* out, const REF_CT* r) {
+  CIPHERTEXT ct;
+  Wrap_ct(&ct, r);
+  double* msg = Get_msg(&ct);
+  memcpy(out, msg, sizeof(double) * r->slots);
+  free(msg);
+}
+
+void ref_ct_add(REF_CT* res, const REF_CT* a, const REF_CT* b) {
+  CIPHERTEXT  x, y;
+  CIPHERTEXT* z = Alloc_ciphertext();
+  Wrap_ct(&x, a);
+  Wrap_ct(&y, b);
+  Add_ciph(z, &x, &y);
+  Unwrap_ct(res, z);
+  Free_ciphertext(z);
+}
+
+/* tensor product + relinearisation (no rescale) */
+void ref_ct_mul(REF_CT* res, const REF_CT* a, const REF_CT* b) {
+  CIPHERTEXT  x, y;
+  CIPHERTEXT* z = Alloc_ciphertext();
+  Wrap_ct(&x, a);
+  Wrap_ct(&y, b);
+  Mul_ciph(z, &x, &y);
+  Unwrap_ct(res, z);
+  Free_ciphertext(z);
+}
+
+void ref_ct_rescale(REF_CT* res, const REF_CT* a) {
+  CIPHERTEXT  x;
+  CIPHERTEXT* z = Alloc_ciphertext();
+  Wrap_ct(&x, a);
+  Rescale_ciph(z, &x);
+  Unwrap_ct(res, z);
+  Free_ciphertext(z);
+}
+
+void ref_ct_rotate(REF_CT* res, const REF_CT* a, int32_t rot) {
+  CIPHERTEXT  x;
+  CIPHERTEXT* z = Alloc_ciphertext();
+  Wrap_ct(&x, a);
+  Rotate_ciph(z, &x, rot);
+  Unwrap_ct(res, z);
+  Free_ciphertext(z);
+}
+
+/* plaintext (already encoded, `level` limbs, NTT form) times ciphertext */
+void ref_ct_mul_plain(REF_CT* res, const REF_CT* a, int64_t* pt, double pt_scale,
+                      uint32_t pt_sf_degree) {
+  CIPHERTEXT  x;
+  CIPHERTEXT* z = Alloc_ciphertext();
+  PLAINTEXT   p;
+  memset(&p, 0, sizeof(p));
+  Wrap_ct(&x, a);
+  Wrap_poly(Get_plain_poly(&p), pt, a->level, 0, true);
+  p._slots          = a->slots;
+  p._scaling_factor = pt_scale;
+  p._sf_degree      = pt_sf_degree;
+  Mul_plain(z, &x, &p);
+  Unwrap_ct(res, z);
+  Free_ciphertext(z);
+}
+
+/* bootstrap (a11); res buffers must hold level_after_bts(+) limbs: use num_q limbs */
+void ref_ct_bootstrap(REF_CT* res, const REF_CT* a, uint32_t level_after_bts) {
+  CIPHERTEXT  x;
+  CIPHERTEXT* z = Alloc_ciphertext();
+  Wrap_ct(&x, a);
+  Bootstrap(z, &x, level_after_bts);
+  Unwrap_ct(res, z);
+  Free_ciphertext(z);
+}
