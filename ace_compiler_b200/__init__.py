@@ -1,0 +1,249 @@
+"""ace_compiler_b200 -- B200-native CKKS evaluation runtime for ACE-generated programs.
+
+Python is only a thin ctypes veneer over the C ABI in include/ace_b200.h
+(libace_b200.so: hand-written sm_100a CUDA kernels + C++ host runtime).  There is no CPU
+fallback: creating a context without a CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libace_b200.so")
+
+vp, u32, i32, sz = C.c_void_p, C.c_uint32, C.c_int32, C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/ace_b200.h declares
+SIGNATURES = {
+    "ace_ctx_create": (C.c_int, [C.POINTER(vp), u32, sz, sz, sz, sz, sz, C.c_int]),
+    "ace_ctx_destroy": (None, [vp]),
+    "ace_last_error": (C.c_char_p, []),
+    "ace_degree": (u32, [vp]),
+    "ace_num_q": (sz, [vp]),
+    "ace_num_p": (sz, [vp]),
+    "ace_num_q_parts": (sz, [vp]),
+    "ace_part_size": (sz, [vp]),
+    "ace_get_primes": (C.c_int, [vp, vp, vp]),
+    "ace_psi": (C.c_int64, [vp, u32]),
+    "ace_num_decomp": (sz, [vp, sz]),
+    "ace_launch_count": (C.c_uint64, [vp]),
+    "ace_alloc_limbs": (vp, [vp, sz, C.c_int]),
+    "ace_free_limbs": (C.c_int, [vp, vp]),
+    "ace_upload": (C.c_int, [vp, vp, vp, sz]),
+    "ace_download": (C.c_int, [vp, vp, vp, sz]),
+    "ace_copy_limbs": (C.c_int, [vp, vp, vp, sz]),
+    "ace_zero_limbs": (C.c_int, [vp, vp, sz]),
+    "ace_sync": (C.c_int, [vp]),
+    "ace_hw_modadd": (C.c_int, [vp, vp, vp, vp, u32, u32]),
+    "ace_hw_modsub": (C.c_int, [vp, vp, vp, vp, u32, u32]),
+    "ace_hw_modmul": (C.c_int, [vp, vp, vp, vp, u32, u32]),
+    "ace_hw_rotate": (C.c_int, [vp, vp, vp, vp, u32, u32]),
+    "ace_ntt": (C.c_int, [vp, vp, u32, u32]),
+    "ace_intt": (C.c_int, [vp, vp, u32, u32]),
+    "ace_decomp_modup": (C.c_int, [vp, vp, vp, u32, u32]),
+    "ace_mod_down": (C.c_int, [vp, vp, vp, u32]),
+    "ace_rescale": (C.c_int, [vp, vp, vp, u32]),
+    "ace_auto_index": (u32, [vp, i32]),
+    "ace_auto_order": (vp, [vp, i32]),
+    "ace_swk_import": (C.c_int, [vp, C.c_int, i32, u32, C.c_int, vp]),
+    "ace_swk_poly": (vp, [vp, C.c_int, i32, u32, C.c_int]),
+    "ace_key_switch": (C.c_int, [vp, vp, vp, vp, u32, C.c_int, i32]),
+    "ace_ct_rotate": (C.c_int, [vp, vp, vp, vp, vp, u32, i32]),
+    "ace_ct_mul_relin": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, u32]),
+    "ace_ct_rescale": (C.c_int, [vp, vp, vp, vp, vp, u32]),
+    "ace_timer_start": (C.c_int, [vp]),
+    "ace_timer_stop_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
+}
+
+_lib = None
+
+
+def load_library():
+    """dlopen libace_b200.so (building it first if sources are newer) and bind signatures."""
+    global _lib
+    if _lib is None:
+        _build.build()
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export it
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+class AceError(RuntimeError):
+    pass
+
+
+def _hp(a):
+    return a.ctypes.data_as(vp)
+
+
+class DevPoly:
+    """n_limbs x N device-resident limbs (owned)."""
+
+    def __init__(self, ctx, n_limbs, zero=False):
+        self.ctx, self.n_limbs = ctx, n_limbs
+        self.ptr = ctx.lib.ace_alloc_limbs(ctx.h, n_limbs, int(zero))
+        if not self.ptr:
+            raise AceError(ctx.lib.ace_last_error().decode())
+
+    def limb(self, i):
+        return self.ptr + i * self.ctx.N * 8
+
+    def get(self):
+        out = np.empty((self.n_limbs, self.ctx.N), np.int64)
+        self.ctx._ck(self.ctx.lib.ace_download(self.ctx.h, _hp(out), self.ptr, self.n_limbs))
+        return out
+
+    def free(self):
+        if self.ptr:
+            self.ctx.lib.ace_free_limbs(self.ctx.h, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """Evaluation context on one B200 (mirrors Prepare_context's parameter part,
+    fhe-cmplr/rtlib/ant/src/rtlib/context.c:29-47)."""
+
+    def __init__(self, degree, mul_depth, first_mod_size, scaling_mod_size, num_q_parts,
+                 hamming_weight=192, device=0):
+        self.lib = load_library()
+        h = vp()
+        rc = self.lib.ace_ctx_create(C.byref(h), degree, mul_depth, first_mod_size,
+                                     scaling_mod_size, num_q_parts, hamming_weight, device)
+        if rc != 0:
+            raise AceError(self.lib.ace_last_error().decode())
+        self.h = h
+        self.N = self.lib.ace_degree(h)
+        self.L, self.K = self.lib.ace_num_q(h), self.lib.ace_num_p(h)
+        self.parts, self.part_size = self.lib.ace_num_q_parts(h), self.lib.ace_part_size(h)
+        q, p = np.zeros(self.L, np.int64), np.zeros(self.K, np.int64)
+        self.lib.ace_get_primes(h, _hp(q), _hp(p))
+        self.q, self.p = q, p
+
+    def close(self):
+        if self.h:
+            self.lib.ace_ctx_destroy(self.h)
+            self.h = None
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise AceError(self.lib.ace_last_error().decode())
+
+    # ---- data movement
+    def put(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.int64).reshape(-1, self.N)
+        d = DevPoly(self, arr.shape[0])
+        self._ck(self.lib.ace_upload(self.h, d.ptr, _hp(arr), arr.shape[0]))
+        self.sync()  # the host array may be a temporary
+        return d
+
+    def empty(self, n_limbs, zero=False):
+        return DevPoly(self, n_limbs, zero)
+
+    def sync(self):
+        self._ck(self.lib.ace_sync(self.h))
+
+    def psi(self, g):
+        return self.lib.ace_psi(self.h, g)
+
+    def num_decomp(self, num_q):
+        return self.lib.ace_num_decomp(self.h, num_q)
+
+    def launch_count(self):
+        return self.lib.ace_launch_count(self.h)
+
+    # ---- per-limb ops on host arrays (convenience for tests)
+    def hw(self, op, g, a, b, n_limbs=1):
+        da, db = self.put(a), self.put(b)
+        r = self.empty(n_limbs)
+        self._ck(getattr(self.lib, "ace_hw_" + op)(self.h, r.ptr, da.ptr, db.ptr, g, n_limbs))
+        return r.get()
+
+    def ntt(self, g, a, n_limbs=1, inverse=False):
+        d = self.put(a)
+        f = self.lib.ace_intt if inverse else self.lib.ace_ntt
+        self._ck(f(self.h, d.ptr, g, n_limbs))
+        return d.get()
+
+    def auto_index(self, rot):
+        return self.lib.ace_auto_index(self.h, rot)
+
+    def auto_order(self, rot):
+        p = self.lib.ace_auto_order(self.h, rot)
+        if not p:
+            raise AceError(self.lib.ace_last_error().decode())
+        return p
+
+    def rotate_limbs(self, g, a, rot, n_limbs=1):
+        d, r = self.put(a), self.empty(n_limbs)
+        self._ck(self.lib.ace_hw_rotate(self.h, r.ptr, d.ptr, self.auto_order(rot), g, n_limbs))
+        return r.get()
+
+    # ---- polynomial-level ops
+    def decomp_modup(self, a, part):
+        a = np.ascontiguousarray(a)
+        nq = a.shape[0]
+        d, out = self.put(a), self.empty(nq + self.K, zero=True)
+        self._ck(self.lib.ace_decomp_modup(self.h, out.ptr, d.ptr, nq, part))
+        return out.get()
+
+    def mod_down(self, a):
+        a = np.ascontiguousarray(a)
+        nq = a.shape[0] - self.K
+        d, out = self.put(a), self.empty(nq)
+        self._ck(self.lib.ace_mod_down(self.h, out.ptr, d.ptr, nq))
+        return out.get()
+
+    def rescale(self, a):
+        a = np.ascontiguousarray(a)
+        nq = a.shape[0]
+        d, out = self.put(a), self.empty(nq - 1)
+        self._ck(self.lib.ace_rescale(self.h, out.ptr, d.ptr, nq))
+        return out.get()
+
+    # ---- keys
+    def import_switch_key(self, is_rot, rot, k0, k1):
+        """k0/k1: (parts, L+K, N) host arrays as exported by the key generator"""
+        for part in range(k0.shape[0]):
+            a0 = np.ascontiguousarray(k0[part], dtype=np.int64)
+            a1 = np.ascontiguousarray(k1[part], dtype=np.int64)
+            self._ck(self.lib.ace_swk_import(self.h, int(is_rot), rot, part, 0, _hp(a0)))
+            self._ck(self.lib.ace_swk_import(self.h, int(is_rot), rot, part, 1, _hp(a1)))
+
+    # ---- fused ciphertext-level ops (host in / host out, for tests)
+    def key_switch(self, d, is_rot, rot):
+        nq = d.shape[0]
+        dd, o0, o1 = self.put(d), self.empty(nq), self.empty(nq)
+        self._ck(self.lib.ace_key_switch(self.h, o0.ptr, o1.ptr, dd.ptr, nq, int(is_rot), rot))
+        return o0.get(), o1.get()
+
+    def ct_rotate(self, c0, c1, rot):
+        nq = c0.shape[0]
+        d0, d1, r0, r1 = self.put(c0), self.put(c1), self.empty(nq), self.empty(nq)
+        self._ck(self.lib.ace_ct_rotate(self.h, r0.ptr, r1.ptr, d0.ptr, d1.ptr, nq, rot))
+        return r0.get(), r1.get()
+
+    def ct_mul_relin(self, a0, a1, b0, b1):
+        nq = a0.shape[0]
+        da0, da1, db0, db1 = self.put(a0), self.put(a1), self.put(b0), self.put(b1)
+        r0, r1 = self.empty(nq), self.empty(nq)
+        self._ck(self.lib.ace_ct_mul_relin(self.h, r0.ptr, r1.ptr, da0.ptr, da1.ptr, db0.ptr,
+                                           db1.ptr, nq))
+        return r0.get(), r1.get()
+
+    def ct_rescale(self, c0, c1):
+        nq = c0.shape[0]
+        d0, d1, r0, r1 = self.put(c0), self.put(c1), self.empty(nq - 1), self.empty(nq - 1)
+        self._ck(self.lib.ace_ct_rescale(self.h, r0.ptr, r1.ptr, d0.ptr, d1.ptr, nq))
+        return r0.get(), r1.get()

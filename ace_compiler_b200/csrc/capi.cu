@@ -1,0 +1,204 @@
+// capi.cu -- extern "C" boundary (include/ace_b200.h) over ace::Context.
+// No torch types, no exceptions across the boundary: errors become negative return codes
+// plus a thread-local message.
+#include <cstring>
+#include <string>
+
+#include "../../include/ace_b200.h"
+#include "context.h"
+
+using namespace ace;
+
+struct ace_ctx {
+  Context*    c;
+  cudaEvent_t ev0, ev1;
+};
+
+static thread_local std::string g_err;
+
+#define ACE_TRY(body)                     \
+  try {                                   \
+    if (!ctx) { g_err = "null context"; return -1; } \
+    cudaSetDevice(ctx->c->device);        \
+    body;                                 \
+    return 0;                             \
+  } catch (const std::exception& e) {     \
+    g_err = e.what();                     \
+    return -1;                            \
+  }
+
+static inline u64*       U(int64_t* p) { return reinterpret_cast<u64*>(p); }
+static inline const u64* U(const int64_t* p) { return reinterpret_cast<const u64*>(p); }
+
+extern "C" {
+
+const char* ace_last_error(void) { return g_err.c_str(); }
+
+int ace_ctx_create(ace_ctx** out, uint32_t poly_degree, size_t mul_depth, size_t first_mod_size,
+                   size_t scaling_mod_size, size_t num_q_parts, size_t hamming_weight,
+                   int device) {
+  try {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+      g_err = "no CUDA device: libace_b200 has no CPU fallback";
+      return -2;
+    }
+    Params p{poly_degree, mul_depth, first_mod_size, scaling_mod_size, num_q_parts,
+             hamming_weight};
+    ace_ctx* h = new ace_ctx;
+    h->c       = new Context(p, device);
+    cudaEventCreate(&h->ev0);
+    cudaEventCreate(&h->ev1);
+    *out = h;
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+void ace_ctx_destroy(ace_ctx* ctx) {
+  if (!ctx) return;
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  delete ctx->c;
+  delete ctx;
+}
+
+uint32_t ace_degree(const ace_ctx* ctx) { return ctx->c->N; }
+size_t   ace_num_q(const ace_ctx* ctx) { return ctx->c->L; }
+size_t   ace_num_p(const ace_ctx* ctx) { return ctx->c->K; }
+size_t   ace_num_q_parts(const ace_ctx* ctx) { return ctx->c->dnum; }
+size_t   ace_part_size(const ace_ctx* ctx) { return ctx->c->part_size; }
+int      ace_get_primes(const ace_ctx* ctx, int64_t* q, int64_t* p) {
+  for (size_t i = 0; i < ctx->c->L; i++) q[i] = (int64_t)ctx->c->mod[i];
+  for (size_t i = 0; i < ctx->c->K; i++) p[i] = (int64_t)ctx->c->mod[ctx->c->L + i];
+  return 0;
+}
+int64_t  ace_psi(const ace_ctx* ctx, uint32_t g) { return (int64_t)ctx->c->psi[g]; }
+size_t   ace_num_decomp(const ace_ctx* ctx, size_t num_q) { return ctx->c->num_decomp(num_q); }
+uint64_t ace_launch_count(const ace_ctx* ctx) { return ctx->c->launches; }
+
+int64_t* ace_alloc_limbs(ace_ctx* ctx, size_t n_limbs, int zero) {
+  try {
+    cudaSetDevice(ctx->c->device);
+    return reinterpret_cast<int64_t*>(ctx->c->alloc_limbs(n_limbs, zero != 0));
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+int ace_free_limbs(ace_ctx* ctx, int64_t* dev) { ACE_TRY(ctx->c->free_limbs(U(dev))) }
+int ace_upload(ace_ctx* ctx, int64_t* d, const int64_t* s, size_t n) {
+  ACE_TRY(ctx->c->upload(U(d), U(s), n))
+}
+int ace_download(ace_ctx* ctx, int64_t* d, const int64_t* s, size_t n) {
+  ACE_TRY(ctx->c->download(U(d), U(s), n))
+}
+int ace_copy_limbs(ace_ctx* ctx, int64_t* d, const int64_t* s, size_t n) {
+  ACE_TRY(ACE_CUDA(cudaMemcpyAsync(d, s, n * ctx->c->N * sizeof(u64), cudaMemcpyDeviceToDevice,
+                                   ctx->c->stream)))
+}
+int ace_zero_limbs(ace_ctx* ctx, int64_t* d, size_t n) {
+  ACE_TRY(ACE_CUDA(cudaMemsetAsync(d, 0, n * ctx->c->N * sizeof(u64), ctx->c->stream)))
+}
+int ace_sync(ace_ctx* ctx) { ACE_TRY(ctx->c->sync()) }
+
+static void check_g(Context* c, uint32_t g0, uint32_t n) {
+  if ((size_t)g0 + n > c->G) throw std::runtime_error("modulus index out of range");
+}
+
+int ace_hw_modadd(ace_ctx* ctx, int64_t* r, const int64_t* a, const int64_t* b, uint32_t g0,
+                  uint32_t n) {
+  ACE_TRY(check_g(ctx->c, g0, n); launch_ew(ctx->c->T, EW_ADD, U(r), U(a), U(b), g0, n, ctx->c->stream); ctx->c->launches++)
+}
+int ace_hw_modsub(ace_ctx* ctx, int64_t* r, const int64_t* a, const int64_t* b, uint32_t g0,
+                  uint32_t n) {
+  ACE_TRY(check_g(ctx->c, g0, n); launch_ew(ctx->c->T, EW_SUB, U(r), U(a), U(b), g0, n, ctx->c->stream); ctx->c->launches++)
+}
+int ace_hw_modmul(ace_ctx* ctx, int64_t* r, const int64_t* a, const int64_t* b, uint32_t g0,
+                  uint32_t n) {
+  ACE_TRY(check_g(ctx->c, g0, n); launch_ew(ctx->c->T, EW_MUL, U(r), U(a), U(b), g0, n, ctx->c->stream); ctx->c->launches++)
+}
+int ace_hw_rotate(ace_ctx* ctx, int64_t* r, const int64_t* a, const int64_t* order, uint32_t g0,
+                  uint32_t n) {
+  ACE_TRY(check_g(ctx->c, g0, n); launch_gather(ctx->c->T, U(r), U(a), order, g0, n, ctx->c->stream); ctx->c->launches++)
+}
+int ace_ntt(ace_ctx* ctx, int64_t* d, uint32_t g0, uint32_t n) {
+  ACE_TRY(check_g(ctx->c, g0, n); ctx->c->ntt(U(d), g0, n))
+}
+int ace_intt(ace_ctx* ctx, int64_t* d, uint32_t g0, uint32_t n) {
+  ACE_TRY(check_g(ctx->c, g0, n); ctx->c->intt(U(d), g0, n))
+}
+
+static void check_level(Context* c, uint32_t num_q) {
+  if (num_q == 0 || num_q > c->L) throw std::runtime_error("num_q out of range");
+}
+int ace_decomp_modup(ace_ctx* ctx, int64_t* out, const int64_t* in, uint32_t num_q,
+                     uint32_t part) {
+  ACE_TRY(check_level(ctx->c, num_q);
+          if (part >= ctx->c->num_decomp(num_q)) throw std::runtime_error("q_part_idx out of range");
+          ctx->c->decomp_modup(U(out), U(in), num_q, part))
+}
+int ace_mod_down(ace_ctx* ctx, int64_t* out, const int64_t* in, uint32_t num_q) {
+  ACE_TRY(check_level(ctx->c, num_q); ctx->c->mod_down(U(out), U(in), num_q))
+}
+int ace_rescale(ace_ctx* ctx, int64_t* out, const int64_t* in, uint32_t num_q) {
+  ACE_TRY(check_level(ctx->c, num_q); ctx->c->rescale(U(out), U(in), num_q))
+}
+
+uint32_t ace_auto_index(const ace_ctx* ctx, int32_t rot) { return ctx->c->auto_index(rot); }
+const int64_t* ace_auto_order(ace_ctx* ctx, int32_t rot) {
+  try {
+    cudaSetDevice(ctx->c->device);
+    return ctx->c->auto_order(ctx->c->auto_index(rot));
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+static SwitchKey& key_of(Context* c, int is_rot, int32_t rot) {
+  return is_rot ? c->rot_key(c->auto_index(rot)) : c->relin_key;
+}
+int ace_swk_import(ace_ctx* ctx, int is_rot, int32_t rot, uint32_t part, int which,
+                   const int64_t* host) {
+  ACE_TRY(ctx->c->import_key_limbs(key_of(ctx->c, is_rot, rot), part, which, U(host)))
+}
+const int64_t* ace_swk_poly(ace_ctx* ctx, int is_rot, int32_t rot, uint32_t part, int which) {
+  Context* c = ctx->c;
+  if (is_rot && !c->has_rot_key(c->auto_index(rot))) return nullptr;
+  SwitchKey& k = key_of(c, is_rot, rot);
+  u64* base = which ? k.k1 : k.k0;
+  if (!base || part >= c->dnum) return nullptr;
+  return reinterpret_cast<const int64_t*>(base + (size_t)part * c->G * c->N);
+}
+
+int ace_key_switch(ace_ctx* ctx, int64_t* o0, int64_t* o1, const int64_t* d, uint32_t num_q,
+                   int is_rot, int32_t rot) {
+  ACE_TRY(check_level(ctx->c, num_q);
+          if (is_rot && !ctx->c->has_rot_key(ctx->c->auto_index(rot))) throw std::runtime_error("rotation key not loaded");
+          ctx->c->key_switch(U(o0), U(o1), U(d), num_q, key_of(ctx->c, is_rot, rot), nullptr))
+}
+int ace_ct_rotate(ace_ctx* ctx, int64_t* r0, int64_t* r1, const int64_t* c0, const int64_t* c1,
+                  uint32_t num_q, int32_t rot) {
+  ACE_TRY(check_level(ctx->c, num_q); ctx->c->ct_rotate(U(r0), U(r1), U(c0), U(c1), num_q, rot))
+}
+int ace_ct_mul_relin(ace_ctx* ctx, int64_t* r0, int64_t* r1, const int64_t* a0,
+                     const int64_t* a1, const int64_t* b0, const int64_t* b1, uint32_t num_q) {
+  ACE_TRY(check_level(ctx->c, num_q);
+          ctx->c->ct_mul_relin(U(r0), U(r1), U(a0), U(a1), U(b0), U(b1), num_q))
+}
+int ace_ct_rescale(ace_ctx* ctx, int64_t* r0, int64_t* r1, const int64_t* c0, const int64_t* c1,
+                   uint32_t num_q) {
+  ACE_TRY(check_level(ctx->c, num_q); ctx->c->rescale(U(r0), U(c0), num_q);
+          ctx->c->rescale(U(r1), U(c1), num_q))
+}
+
+int ace_timer_start(ace_ctx* ctx) { ACE_TRY(ACE_CUDA(cudaEventRecord(ctx->ev0, ctx->c->stream))) }
+int ace_timer_stop_ms(ace_ctx* ctx, float* ms) {
+  ACE_TRY(ACE_CUDA(cudaEventRecord(ctx->ev1, ctx->c->stream));
+          ACE_CUDA(cudaEventSynchronize(ctx->ev1));
+          ACE_CUDA(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1)))
+}
+
+}  // extern "C"

@@ -1,0 +1,470 @@
+// context.cu -- host-side setup (primes, roots, CRT constants -> HBM tables) and the
+// polynomial / ciphertext level operations built from the kernels in kernels.cu.
+//
+// Reference routines restated here (paths under fhe-cmplr/rtlib/ant/):
+//   parameter set         src/util/ckks_parameters.c:60-97, src/util/crt.c:574-585
+//   Q / P primes          src/util/crt.c:46-125, 353-396
+//   NTT tables            src/util/ntt.c:80-127
+//   base-conversion and rescale constants  src/util/crt.c:206-533
+//   Decompose_modup / Reduce_rns_base / Rescale_poly  src/util/polynomial.c:1241-1335, 928-967, 1097-1161
+//   emitted Rotate()/Relinearize()  dataset/resnet20_cifar10_pre.onnx.inc:6972-7146
+#include "context.h"
+
+#include <cstring>
+
+#include "host_math.h"
+
+namespace ace {
+
+static const size_t kAuxBits = 60;  // AUXBITS, include/util/fhe_types.h:27-29
+
+template <typename Tp>
+Tp* Context::to_device(const std::vector<Tp>& v) {
+  Tp* d = nullptr;
+  ACE_CUDA(cudaMalloc(&d, v.size() * sizeof(Tp) + 16));
+  ACE_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(Tp), cudaMemcpyHostToDevice));
+  owned_.push_back(d);
+  return d;
+}
+
+Context::Context(const Params& p, int dev) : params(p), device(dev) {
+  if (p.degree < 16 || (p.degree & (p.degree - 1)) || p.degree > (1u << 17))
+    throw std::runtime_error("degree must be a power of two in [16, 2^17]");
+  if (p.num_q_parts == 0) throw std::runtime_error("num_q_parts must be > 0");
+  N    = p.degree;
+  logN = 0;
+  while ((1u << logN) < N) logN++;
+  L         = p.mul_depth + 1;
+  dnum      = p.num_q_parts;
+  part_size = (L + dnum - 1) / dnum;  // ceil(L / dnum), crt.c:356
+  if (L <= part_size * (dnum - 1)) throw std::runtime_error("invalid number of q parts");
+
+  // ---- primes
+  std::vector<u64> q = hm::q_chain(L, p.first_mod_size, p.scaling_mod_size, N);
+  size_t max_bits = 0;
+  for (size_t j = 0; j < dnum; j++) {
+    size_t lo = j * part_size, hi = std::min(L, lo + part_size);
+    max_bits  = std::max(max_bits, hm::product_bit_length(q.data() + lo, hi - lo));
+  }
+  K = (max_bits + kAuxBits - 1) / kAuxBits;  // crt.c:396
+  G = L + K;
+  if (G > 64 || part_size > 48 || K > 48) throw std::runtime_error("parameter set too large");
+  mod = q;
+  u64 prev = hm::first_prime(N, kAuxBits);  // crt.c:56-75
+  for (size_t i = 0; i < K; i++) {
+    u64 cand;
+    bool dup;
+    do {
+      cand = hm::previous_prime(prev, 2 * (u64)N);
+      dup  = false;
+      for (size_t j = 0; j < L; j++) dup |= (cand == q[j]);
+      prev = cand;
+    } while (dup);
+    mod.push_back(cand);
+  }
+
+  ACE_CUDA(cudaSetDevice(device));
+  ACE_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  {  // keep freed limbs cached in the pool instead of returning them to the driver
+    cudaMemPool_t pool;
+    ACE_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    ACE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  }
+
+  // ---- per-modulus constants + NTT tables
+  std::vector<Modulus> mods(G);
+  std::vector<u64>     tw(G * (size_t)N), tw_sh(G * (size_t)N), itw(G * (size_t)N),
+      itw_sh(G * (size_t)N), n_inv(G), n_inv_sh(G);
+  psi.resize(G);
+  for (size_t g = 0; g < G; g++) {
+    const u64 m = mod[g];
+    Modulus&  M = mods[g];
+    M.q         = m;
+    // floor(2^128 / m) = floor((2^128 - 1) / m) because m is odd and > 1
+    u128 mu = ~(u128)0 / m;
+    M.mu_hi = (u64)(mu >> 64);
+    M.mu_lo = (u64)mu;
+    u32 nbits = 64 - (u32)__builtin_clzll(m);
+    M.shift   = nbits - 2;
+    M.mu64    = (u64)((((u128)1) << (62 + nbits)) / m);
+    M.pad     = 0;
+    // psi = g^((q-1)/2N) with g the smallest generator (number_theory.c:132-157)
+    psi[g] = hm::powmod(hm::smallest_generator(m), (m - 1) / (2 * (u64)N), m);
+    u64 psi_inv = hm::invmod_prime(psi[g], m), pw = 1, ipw = 1;
+    u64* t  = tw.data() + g * (size_t)N;
+    u64* ts = tw_sh.data() + g * (size_t)N;
+    u64* it = itw.data() + g * (size_t)N;
+    u64* is = itw_sh.data() + g * (size_t)N;
+    for (u32 i = 0; i < N; i++) {
+      u32 r = hm::bit_reverse(i, logN);
+      t[r]  = pw;
+      it[r] = ipw;
+      pw    = hm::mulmod(pw, psi[g], m);
+      ipw   = hm::mulmod(ipw, psi_inv, m);
+    }
+    for (u32 i = 0; i < N; i++) {
+      ts[i] = hm::shoup(t[i], m);
+      is[i] = hm::shoup(it[i], m);
+    }
+    n_inv[g]    = hm::invmod_prime(N % m, m);
+    n_inv_sh[g] = hm::shoup(n_inv[g], m);
+  }
+  T.N = N; T.logN = logN; T.G = (u32)G;
+  T.mod    = to_device(mods);
+  T.tw     = to_device(tw);
+  T.tw_sh  = to_device(tw_sh);
+  T.itw    = to_device(itw);
+  T.itw_sh = to_device(itw_sh);
+  T.n_inv    = to_device(n_inv);
+  T.n_inv_sh = to_device(n_inv_sh);
+
+  // ---- ModDown constants (crt.c Precompute_primes(p) + Precompute_new_base(p, q))
+  std::vector<u64> phi(K), phi_sh(K), phm(L * K), pinv(L), pinv_sh(L);
+  for (size_t i = 0; i < K; i++) {
+    u64 pi = mod[L + i], hat = 1;
+    for (size_t k = 0; k < K; k++)
+      if (k != i) hat = hm::mulmod(hat, mod[L + k] % pi, pi);
+    phi[i]    = hm::invmod_prime(hat, pi);
+    phi_sh[i] = hm::shoup(phi[i], pi);
+  }
+  for (size_t j = 0; j < L; j++) {
+    u64 qj = mod[j], prod = 1;
+    for (size_t i = 0; i < K; i++) {
+      u64 hat = 1;
+      for (size_t k = 0; k < K; k++)
+        if (k != i) hat = hm::mulmod(hat, mod[L + k] % qj, qj);
+      phm[j * K + i] = hat;
+      prod           = hm::mulmod(prod, mod[L + i] % qj, qj);
+    }
+    pinv[j]    = hm::invmod_prime(prod, qj);
+    pinv_sh[j] = hm::shoup(pinv[j], qj);
+  }
+  phat_inv_      = to_device(phi);
+  phat_inv_sh_   = to_device(phi_sh);
+  phat_mod_q_    = to_device(phm);
+  pinv_mod_q_    = to_device(pinv);
+  pinv_mod_q_sh_ = to_device(pinv_sh);
+
+  // ---- Rescale constants (crt.c:270-330).  _ql_ql_inv_mod_ql_div_ql_mod_qi equals
+  // -q_l^-1 mod q_i: (Q/q_l)*[(Q/q_l)^-1]_{q_l} = 1 + k*q_l and is 0 mod q_i, so the stored
+  // floor quotient k satisfies k*q_l = -1 (mod q_i).
+  std::vector<u64> qi(L * L, 0), qi_sh(L * L, 0), nq(L * L, 0), nq_sh(L * L, 0);
+  for (size_t l = 1; l < L; l++) {
+    for (size_t i = 0; i < l; i++) {
+      u64 m = mod[i], inv = hm::invmod_prime(mod[l] % m, m);
+      qi[l * L + i]    = inv;
+      qi_sh[l * L + i] = hm::shoup(inv, m);
+      nq[l * L + i]    = m - inv;
+      nq_sh[l * L + i] = hm::shoup(m - inv, m);
+    }
+  }
+  qlinv_       = to_device(qi);
+  qlinv_sh_    = to_device(qi_sh);
+  negqlinv_    = to_device(nq);
+  negqlinv_sh_ = to_device(nq_sh);
+}
+
+Context::~Context() {
+  cudaSetDevice(device);
+  cudaStreamSynchronize(stream);
+  for (auto& kv : rot_keys_) { cudaFree(kv.second.k0); cudaFree(kv.second.k1); }
+  cudaFree(relin_key.k0);
+  cudaFree(relin_key.k1);
+  for (auto& kv : auto_orders_) cudaFree(kv.second);
+  for (void* p : owned_) cudaFree(p);
+  cudaStreamDestroy(stream);
+}
+
+// ---------------------------------------------------------------------------- memory
+u64* Context::alloc_limbs(size_t n_limbs, bool zero) {
+  u64*   p     = nullptr;
+  size_t bytes = std::max<size_t>(n_limbs, 1) * N * sizeof(u64);
+  ACE_CUDA(cudaMallocAsync(&p, bytes, stream));
+  if (zero) ACE_CUDA(cudaMemsetAsync(p, 0, bytes, stream));
+  return p;
+}
+void Context::free_limbs(u64* p) {
+  if (p) ACE_CUDA(cudaFreeAsync(p, stream));
+}
+void Context::upload(u64* dst, const u64* src, size_t n_limbs) {
+  ACE_CUDA(cudaMemcpyAsync(dst, src, n_limbs * N * sizeof(u64), cudaMemcpyHostToDevice, stream));
+}
+void Context::download(u64* dst, const u64* src, size_t n_limbs) {
+  ACE_CUDA(cudaMemcpyAsync(dst, src, n_limbs * N * sizeof(u64), cudaMemcpyDeviceToHost, stream));
+  ACE_CUDA(cudaStreamSynchronize(stream));
+}
+void Context::sync() { ACE_CUDA(cudaStreamSynchronize(stream)); }
+
+static void copy_limbs(u64* dst, const u64* src, size_t n_limbs, u32 N, cudaStream_t s) {
+  ACE_CUDA(cudaMemcpyAsync(dst, src, n_limbs * N * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+}
+
+// ---------------------------------------------------------------------------- transforms
+void Context::ntt(u64* data, u32 g0, u32 n) {
+  for (u32 done = 0; done < n; done += kMaxBatch) {
+    LimbBatch b;
+    b.base = data;
+    b.n    = std::min<u32>(kMaxBatch, n - done);
+    for (u32 i = 0; i < b.n; i++) { b.slot[i] = (u16)(done + i); b.g[i] = (u16)(g0 + done + i); }
+    launch_ntt(T, b, stream);
+    launches += (logN > 12) ? 2 : 1;
+  }
+}
+void Context::intt(u64* data, u32 g0, u32 n) {
+  for (u32 done = 0; done < n; done += kMaxBatch) {
+    LimbBatch b;
+    b.base = data;
+    b.n    = std::min<u32>(kMaxBatch, n - done);
+    for (u32 i = 0; i < b.n; i++) { b.slot[i] = (u16)(done + i); b.g[i] = (u16)(g0 + done + i); }
+    launch_intt(T, b, stream);
+    launches += (logN > 12) ? 2 : 1;
+  }
+}
+
+// ---------------------------------------------------------------------------- ModUp
+// tables _l_hat_inv_modq[part][n_in-1] and _l_hat_modp[num_q-1][part] (crt.c:399-533)
+const Context::ModUpTab& Context::modup_tab(u32 num_q, u32 part) {
+  auto key = std::make_pair(num_q, part);
+  auto it  = modup_tabs_.find(key);
+  if (it != modup_tabs_.end()) return it->second;
+  ModUpTab t;
+  u32 beta = (u32)num_decomp(num_q);
+  t.start  = (u32)(part_size * part);
+  t.n_in   = (part == beta - 1) ? num_q - t.start : (u32)part_size;
+  std::vector<u64> hi(t.n_in), his(t.n_in);
+  for (u32 i = 0; i < t.n_in; i++) {
+    u64 qi = mod[t.start + i], hat = 1;
+    for (u32 k = 0; k < t.n_in; k++)
+      if (k != i) hat = hm::mulmod(hat, mod[t.start + k] % qi, qi);
+    hi[i]  = hm::invmod_prime(hat, qi);
+    his[i] = hm::shoup(hi[i], qi);
+    t.g_in.push_back((u16)(t.start + i));
+  }
+  for (u32 o = 0; o < num_q + K; o++) {
+    if (o >= t.start && o < t.start + t.n_in) continue;
+    t.g_out.push_back((u16)gidx(o, num_q));
+    t.out_slot.push_back((u16)o);
+  }
+  t.n_out = (u32)t.g_out.size();
+  std::vector<u64> hm_(std::max<size_t>(1, (size_t)t.n_out * t.n_in));
+  for (u32 o = 0; o < t.n_out; o++) {
+    u64 tm = mod[t.g_out[o]];
+    for (u32 i = 0; i < t.n_in; i++) {
+      u64 hat = 1;
+      for (u32 k = 0; k < t.n_in; k++)
+        if (k != i) hat = hm::mulmod(hat, mod[t.start + k] % tm, tm);
+      hm_[(size_t)o * t.n_in + i] = hat;
+    }
+  }
+  t.hatinv    = to_device(hi);
+  t.hatinv_sh = to_device(his);
+  t.hatmod    = to_device(hm_);
+  return modup_tabs_.emplace(key, std::move(t)).first->second;
+}
+
+void Context::fill_conv_desc(ConvDesc& d, const ModUpTab& t, const u64* x, u64* out) {
+  d.x = x; d.out = out;
+  d.hatinv = t.hatinv; d.hatinv_sh = t.hatinv_sh; d.hatmod = t.hatmod;
+  d.n_in = t.n_in; d.n_out = t.n_out;
+  for (u32 i = 0; i < t.n_in; i++) d.g_in[i] = t.g_in[i];
+  for (u32 o = 0; o < t.n_out; o++) { d.g_out[o] = t.g_out[o]; d.out_slot[o] = t.out_slot[o]; }
+}
+
+// Decomp_modup (poly_eval.c:28-34): out = num_q + K limbs
+void Context::decomp_modup(u64* out, const u64* in, u32 num_q, u32 part) {
+  const ModUpTab& t = modup_tab(num_q, part);
+  u64* coef = alloc_limbs(t.n_in, false);
+  copy_limbs(coef, in + (size_t)t.start * N, t.n_in, N, stream);
+  copy_limbs(out + (size_t)t.start * N, in + (size_t)t.start * N, t.n_in, N, stream);
+  intt(coef, t.start, t.n_in);
+  ConvDesc d;
+  fill_conv_desc(d, t, coef, out);
+  launch_base_conv(T, &d, 1, stream);
+  LimbBatch b;
+  b.base = out; b.n = t.n_out;
+  for (u32 o = 0; o < t.n_out; o++) { b.slot[o] = t.out_slot[o]; b.g[o] = t.g_out[o]; }
+  launch_ntt(T, b, stream);
+  launches += 1 + ((logN > 12) ? 2 : 1);
+  free_limbs(coef);
+}
+
+// Mod_down (poly_eval.c:36-41).  Unlike the reference the P part of `in` is left intact.
+void Context::mod_down(u64* out, const u64* in, u32 num_q) {
+  u64* pc   = alloc_limbs(K, false);
+  u64* conv = alloc_limbs(num_q, false);
+  copy_limbs(pc, in + (size_t)num_q * N, K, N, stream);
+  intt(pc, (u32)L, (u32)K);
+  ConvDesc d;
+  d.x = pc; d.out = conv;
+  d.hatinv = phat_inv_; d.hatinv_sh = phat_inv_sh_; d.hatmod = phat_mod_q_;
+  d.n_in = (u32)K; d.n_out = num_q;
+  for (u32 i = 0; i < K; i++) d.g_in[i] = (u16)(L + i);
+  for (u32 o = 0; o < num_q; o++) { d.g_out[o] = (u16)o; d.out_slot[o] = (u16)o; }
+  launch_base_conv(T, &d, 1, stream);
+  ntt(conv, 0, num_q);
+  launch_moddown_tail(T, out, in, conv, nullptr, pinv_mod_q_, pinv_mod_q_sh_, num_q, stream);
+  launches += 2;
+  free_limbs(pc);
+  free_limbs(conv);
+}
+
+// Rescale (poly_eval.c:43-49): out gets num_q - 1 limbs
+void Context::rescale(u64* out, const u64* in, u32 num_q) {
+  if (num_q < 2) throw std::runtime_error("Rescale: level not enough");
+  const u32 l = num_q - 1;
+  u64* last = alloc_limbs(1, false);
+  u64* tmp  = alloc_limbs(l, false);
+  copy_limbs(last, in + (size_t)l * N, 1, N, stream);
+  intt(last, l, 1);
+  launch_rescale_pre(T, tmp, last, l, negqlinv_ + (size_t)l * L, negqlinv_sh_ + (size_t)l * L,
+                     stream);
+  ntt(tmp, 0, l);
+  launch_rescale_post(T, out, in, tmp, qlinv_ + (size_t)l * L, qlinv_sh_ + (size_t)l * L, l,
+                      stream);
+  launches += 2;
+  free_limbs(last);
+  free_limbs(tmp);
+}
+
+// ---------------------------------------------------------------------------- keys
+u32 Context::auto_index(int32_t rot) const {  // number_theory.c:187-199 with modulus 2N
+  const u64 M = 2 * (u64)N;
+  if (rot == 0) return 1;
+  if (rot == (int32_t)(M - 1)) return (u32)rot;
+  u64 gen = 5;
+  if (rot < 0) gen = hm::powmod(5, N / 2 - 1, M);  // 5 has order N/2 in Z_2N^*
+  return (u32)hm::powmod(gen, (u64)(rot < 0 ? -(int64_t)rot : rot), M);
+}
+
+const int64_t* Context::auto_order(u32 k) {  // number_theory.c:201-214 (is_ntt = TRUE)
+  auto it = auto_orders_.find(k);
+  if (it != auto_orders_.end()) return it->second;
+  std::vector<int64_t> ord(N);
+  const u32 logm = logN + 1;
+  for (u64 j = 0; j < N; j++) {
+    u64 jt  = (j << 1) + 1;
+    u64 idx = ((jt * k) - (((jt * k) >> logm) << logm)) >> 1;
+    ord[hm::bit_reverse((u32)j, logN)] = (int64_t)hm::bit_reverse((u32)idx, logN);
+  }
+  int64_t* d = nullptr;
+  ACE_CUDA(cudaMalloc(&d, N * sizeof(int64_t)));
+  ACE_CUDA(cudaMemcpy(d, ord.data(), N * sizeof(int64_t), cudaMemcpyHostToDevice));
+  auto_orders_[k] = d;
+  return d;
+}
+
+void Context::import_key_limbs(SwitchKey& key, u32 part, int which, const u64* host) {
+  if (part >= dnum) throw std::runtime_error("key part out of range");
+  size_t per = G * (size_t)N;
+  u64**  dst = which ? &key.k1 : &key.k0;
+  if (*dst == nullptr) ACE_CUDA(cudaMalloc(dst, dnum * per * sizeof(u64)));
+  ACE_CUDA(cudaMemcpy(*dst + part * per, host, per * sizeof(u64), cudaMemcpyHostToDevice));
+}
+
+// ---------------------------------------------------------------------------- key switch
+// Same dataflow as the emitted Rotate()/Relinearize() bodies, but batched: one INTT launch
+// for all digits, one base-conversion launch (one descriptor per digit), one NTT launch for
+// all complement limbs, one inner-product launch that reads the key once, and one ModDown
+// for both output polynomials.
+void Context::key_switch(u64* out0, u64* out1, const u64* d, u32 num_q, const SwitchKey& key,
+                         const u64* add0) {
+  if (!key.k0 || !key.k1) throw std::runtime_error("switch key not loaded");
+  const u32 beta = (u32)num_decomp(num_q), W = num_q + (u32)K;
+  u64* coef = alloc_limbs(num_q, false);
+  u64* ext  = alloc_limbs((size_t)beta * W, false);
+  u64* acc  = alloc_limbs(2 * (size_t)W, false);
+  copy_limbs(coef, d, num_q, N, stream);
+  intt(coef, 0, num_q);
+  ConvDesc  descs[6];
+  LimbBatch nb;
+  nb.base = ext; nb.n = 0;
+  for (u32 j = 0; j < beta; j++) {
+    const ModUpTab& t = modup_tab(num_q, j);
+    u64* ext_j = ext + (size_t)j * W * N;
+    copy_limbs(ext_j + (size_t)t.start * N, d + (size_t)t.start * N, t.n_in, N, stream);
+    fill_conv_desc(descs[j % 6], t, coef + (size_t)t.start * N, ext_j);
+    if (j % 6 == 5 || j == beta - 1) {
+      launch_base_conv(T, descs, j % 6 + 1, stream);
+      launches++;
+    }
+    for (u32 o = 0; o < t.n_out; o++) {
+      if (nb.n == kMaxBatch) {
+        launch_ntt(T, nb, stream);
+        launches += (logN > 12) ? 2 : 1;
+        nb.n = 0;
+      }
+      nb.slot[nb.n] = (u16)(j * W + t.out_slot[o]);
+      nb.g[nb.n]    = t.g_out[o];
+      nb.n++;
+    }
+  }
+  launch_ntt(T, nb, stream);
+  launches += (logN > 12) ? 2 : 1;
+  u64 *acc0 = acc, *acc1 = acc + (size_t)W * N;
+  launch_ksw_inner(T, acc0, acc1, ext, key.k0, key.k1, beta, num_q, (u32)L, (u32)K, stream);
+  launches++;
+  // ModDown of both accumulators
+  u64* pc   = alloc_limbs(2 * K, false);
+  u64* conv = alloc_limbs(2 * (size_t)num_q, false);
+  copy_limbs(pc, acc0 + (size_t)num_q * N, K, N, stream);
+  copy_limbs(pc + K * (size_t)N, acc1 + (size_t)num_q * N, K, N, stream);
+  LimbBatch pb;
+  pb.base = pc; pb.n = 2 * (u32)K;
+  for (u32 i = 0; i < 2 * K; i++) { pb.slot[i] = (u16)i; pb.g[i] = (u16)(L + i % K); }
+  launch_intt(T, pb, stream);
+  ConvDesc md[2];
+  for (int h = 0; h < 2; h++) {
+    ConvDesc& c = md[h];
+    c.x = pc + (size_t)h * K * N; c.out = conv + (size_t)h * num_q * N;
+    c.hatinv = phat_inv_; c.hatinv_sh = phat_inv_sh_; c.hatmod = phat_mod_q_;
+    c.n_in = (u32)K; c.n_out = num_q;
+    for (u32 i = 0; i < K; i++) c.g_in[i] = (u16)(L + i);
+    for (u32 o = 0; o < num_q; o++) { c.g_out[o] = (u16)o; c.out_slot[o] = (u16)o; }
+  }
+  launch_base_conv(T, md, 2, stream);
+  LimbBatch cb;
+  cb.base = conv; cb.n = 2 * num_q;
+  for (u32 i = 0; i < 2 * num_q; i++) { cb.slot[i] = (u16)i; cb.g[i] = (u16)(i % num_q); }
+  launch_ntt(T, cb, stream);
+  launch_moddown_tail(T, out0, acc0, conv, add0, pinv_mod_q_, pinv_mod_q_sh_, num_q, stream);
+  launch_moddown_tail(T, out1, acc1, conv + (size_t)num_q * N, nullptr, pinv_mod_q_,
+                      pinv_mod_q_sh_, num_q, stream);
+  launches += 3 + 2 * ((logN > 12) ? 2 : 1);
+  free_limbs(coef); free_limbs(ext); free_limbs(acc); free_limbs(pc); free_limbs(conv);
+}
+
+// emitted Rotate(): key switch c1, add c0, apply the automorphism to both polynomials
+void Context::ct_rotate(u64* r0, u64* r1, const u64* c0, const u64* c1, u32 num_q,
+                        int32_t rot_idx) {
+  u32 k = auto_index(rot_idx);
+  if (!has_rot_key(k)) throw std::runtime_error("rotation key not loaded");
+  const int64_t* order = auto_order(k);
+  u64* s = alloc_limbs(2 * (size_t)num_q, false);
+  u64 *s0 = s, *s1 = s + (size_t)num_q * N;
+  key_switch(s0, s1, c1, num_q, rot_keys_[k], c0);
+  launch_gather(T, r0, s0, order, 0, num_q, stream);
+  launch_gather(T, r1, s1, order, 0, num_q, stream);
+  launches += 2;
+  free_limbs(s);
+}
+
+// tensor product + emitted Relinearize(): r0 = a0 b0 + ks0(a1 b1), r1 = a0 b1 + a1 b0 + ks1
+void Context::ct_mul_relin(u64* r0, u64* r1, const u64* a0, const u64* a1, const u64* b0,
+                           const u64* b1, u32 num_q) {
+  u64* t  = alloc_limbs(4 * (size_t)num_q, false);
+  u64 *d2 = t, *d1 = t + (size_t)num_q * N, *s0 = t + 2 * (size_t)num_q * N,
+      *s1 = t + 3 * (size_t)num_q * N;
+  launch_ew(T, EW_MUL, d2, a1, b1, 0, num_q, stream);
+  key_switch(s0, s1, d2, num_q, relin_key, nullptr);
+  launch_ew(T, EW_MUL, d1, a0, b1, 0, num_q, stream);
+  launch_ew(T, EW_MUL, d2, a1, b0, 0, num_q, stream);
+  launch_ew(T, EW_ADD, d1, d1, d2, 0, num_q, stream);
+  launch_ew(T, EW_ADD, r1, d1, s1, 0, num_q, stream);
+  launch_ew(T, EW_MUL, d2, a0, b0, 0, num_q, stream);
+  launch_ew(T, EW_ADD, r0, d2, s0, 0, num_q, stream);
+  launches += 7;
+  free_limbs(t);
+}
+
+}  // namespace ace

@@ -1,0 +1,122 @@
+// context.h -- B200-resident CKKS evaluation context: parameter set, RNS tables in HBM,
+// evaluation keys, a stream-ordered limb allocator and the polynomial / ciphertext ops
+// that the C-ABI (include/ace_b200.h) exposes.
+//
+// Plays the role of the reference's global CKKS_CONTEXT (fhe-cmplr/rtlib/ant/src/rtlib/
+// context.c:27-86) + CRT_CONTEXT (include/util/crt.h:873-878) for the evaluation path.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace ace {
+
+struct Params {
+  u32    degree;
+  size_t mul_depth;       // L = mul_depth + 1 Q primes
+  size_t first_mod_size;  // bits of q0
+  size_t scaling_mod_size;
+  size_t num_q_parts;     // dnum
+  size_t hamming_weight;
+};
+
+struct SwitchKey {
+  u64* k0 = nullptr;  // [dnum][L+K][N], b part (Pk0_at)
+  u64* k1 = nullptr;  // [dnum][L+K][N], a part (Pk1_at)
+};
+
+#define ACE_CUDA(x)                                                                       \
+  do {                                                                                    \
+    cudaError_t e_ = (x);                                                                 \
+    if (e_ != cudaSuccess)                                                                \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) +     \
+                               " at " __FILE__ ":" + std::to_string(__LINE__));           \
+  } while (0)
+
+class Context {
+ public:
+  Context(const Params& p, int device);
+  ~Context();
+
+  // ---- parameter set (host copies)
+  Params           params;
+  u32              N, logN;
+  size_t           L, K, G, dnum, part_size;
+  std::vector<u64> mod;  // [G] Q primes then P primes
+  std::vector<u64> psi;  // [G] 2N-th roots used for the NTT tables
+  int              device;
+  cudaStream_t     stream;
+  DeviceTables     T;
+
+  // ---- memory: limb arrays in HBM, stream-ordered
+  u64* alloc_limbs(size_t n_limbs, bool zero);
+  void free_limbs(u64* p);
+  void upload(u64* dst, const u64* src, size_t n_limbs);
+  void download(u64* dst, const u64* src, size_t n_limbs);
+  void sync();
+
+  size_t num_decomp(size_t num_q) const {
+    size_t n = (num_q + part_size - 1) / part_size;
+    return n > dnum ? dnum : n;
+  }
+  u32 gidx(u32 o, u32 num_q) const { return o < num_q ? o : (u32)L + (o - num_q); }
+
+  // ---- transforms on `n` consecutive limbs starting at modulus g0
+  void ntt(u64* data, u32 g0, u32 n);
+  void intt(u64* data, u32 g0, u32 n);
+
+  // ---- reference polynomial-level API (a5, a6, a8)
+  void decomp_modup(u64* out, const u64* in, u32 num_q, u32 part);
+  void mod_down(u64* out, const u64* in, u32 num_q);
+  void rescale(u64* out, const u64* in, u32 num_q);
+
+  // ---- keys and automorphisms
+  u32            auto_index(int32_t rot_idx) const;
+  const int64_t* auto_order(u32 auto_idx);  // device table, built on first use
+  SwitchKey&     rot_key(u32 auto_idx) { return rot_keys_[auto_idx]; }
+  bool           has_rot_key(u32 auto_idx) const { return rot_keys_.count(auto_idx) != 0; }
+  SwitchKey      relin_key;
+  void           import_key_limbs(SwitchKey& key, u32 part, int which, const u64* host);
+
+  // ---- fused ciphertext-level pipeline
+  // hybrid key switch of d (num_q limbs, NTT form); out0 += nothing, optional add0 is added
+  // to out0 after ModDown (the c0 of a rotation).
+  void key_switch(u64* out0, u64* out1, const u64* d, u32 num_q, const SwitchKey& key,
+                  const u64* add0);
+  void ct_rotate(u64* r0, u64* r1, const u64* c0, const u64* c1, u32 num_q, int32_t rot_idx);
+  void ct_mul_relin(u64* r0, u64* r1, const u64* a0, const u64* a1, const u64* b0,
+                    const u64* b1, u32 num_q);
+
+  size_t launches = 0;  // kernels launched so far (bench.py reports the delta)
+
+ private:
+  typedef uint16_t u16;
+  struct ModUpTab {
+    u32              n_in, n_out, start;
+    u64 *            hatinv, *hatinv_sh, *hatmod;  // device
+    std::vector<u16> g_in, g_out, out_slot;
+  };
+  const ModUpTab&  modup_tab(u32 num_q, u32 part);
+  void             fill_conv_desc(ConvDesc& d, const ModUpTab& t, const u64* x, u64* out);
+
+  std::map<std::pair<u32, u32>, ModUpTab>  modup_tabs_;
+  std::unordered_map<u32, int64_t*>        auto_orders_;
+  std::unordered_map<u32, SwitchKey>       rot_keys_;
+  std::vector<void*>                       owned_;  // device tables freed in the destructor
+  // ModDown tables
+  u64 *phat_inv_, *phat_inv_sh_, *phat_mod_q_;  // [K], [K], [L][K]
+  u64 *pinv_mod_q_, *pinv_mod_q_sh_;            // [L]
+  // Rescale tables, row l (dropping q_l), column i < l
+  u64 *qlinv_, *qlinv_sh_, *negqlinv_, *negqlinv_sh_;  // [L][L]
+
+  template <typename Tp>
+  Tp* to_device(const std::vector<Tp>& v);
+};
+
+}  // namespace ace

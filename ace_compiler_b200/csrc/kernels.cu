@@ -1,0 +1,450 @@
+// kernels.cu -- hand-written sm_100a kernels for the CKKS evaluation hot path.
+//
+// Reference CPU routines each kernel replaces (paths under fhe-cmplr/rtlib/ant/):
+//   ntt_*            Forward_transform / Inverse_transform      src/util/ntt.c:190-353
+//   ew_kernel        Hw_modadd / Hw_modmul                      src/poly/poly_arith.c:14-39
+//   gather_kernel    Hw_rotate                                  src/poly/poly_arith.c:41-56
+//   base_conv_kernel Fast_base_conv / Decompose_modup MAC loop  src/util/polynomial.c:755-807,1297-1320
+//   ksw_inner_kernel emitted key inner-product loops            dataset/resnet20_cifar10_pre.onnx.inc:7005-7032
+//   moddown_tail     Reduce_rns_base tail                       src/util/polynomial.c:953-965
+//   rescale_*        Rescale_poly (NTT branch)                  src/util/polynomial.c:1123-1161
+//
+// All of these are integer kernels: NTT and base conversion are bound by the INT32 multiply
+// pipe (IMAD), the rest by HBM bandwidth.  No tensor-core path is used.
+#include "kernels.cuh"
+
+namespace ace {
+
+// ------------------------------------------------------------------------------------
+// NTT.  N = 2^logN.  A transform is split into a "tile" phase working on contiguous tiles
+// of T = min(N, 4096) elements in shared memory (the min(logN,12) stages whose butterfly
+// stride fits in a tile) and, for N > 4096, a "strided" phase doing the remaining
+// logN-12 stages entirely in registers: a thread owns one column (R = N/4096 elements at
+// stride 4096), adjacent threads own adjacent columns, so every access is coalesced.
+// Forward (Cooley-Tukey, natural -> bit-reversed): strided phase first, then tiles.
+// Inverse (Gentleman-Sande, bit-reversed -> natural): tiles first, then strided phase,
+// which also folds in N^-1.
+// ------------------------------------------------------------------------------------
+constexpr int kTileLog   = 12;
+constexpr int kTile      = 1 << kTileLog;
+constexpr int kNttThreads = 512;
+
+// forward butterfly: (u, v) -> (u + w v, u - w v)
+__device__ __forceinline__ void ct_butterfly(u64& u, u64& v, u64 w, u64 wsh, u64 q) {
+  u64 t = mul_shoup(v, w, wsh, q);
+  u64 a = u + t;
+  a     = a >= q ? a - q : a;
+  v     = u >= t ? u - t : u + q - t;
+  u     = a;
+}
+// inverse butterfly: (u, v) -> (u + v, (u - v) w)
+__device__ __forceinline__ void gs_butterfly(u64& u, u64& v, u64 w, u64 wsh, u64 q) {
+  u64 d = u >= v ? u - v : u + q - v;
+  u64 a = u + v;
+  u     = a >= q ? a - q : a;
+  v     = mul_shoup(d, w, wsh, q);
+}
+
+// ---- strided phase, forward: stages 0 .. SA-1, R = 2^SA rows at stride N/R -------------
+template <int SA>
+__global__ void __launch_bounds__(256) ntt_fwd_strided(DeviceTables T, LimbBatch b) {
+  constexpr int R = 1 << SA;
+  const u32 limb  = blockIdx.y;
+  const u32 g     = b.g[limb];
+  const u64 q     = T.mod[g].q;
+  u64*      data  = b.base + (size_t)b.slot[limb] * T.N;
+  const u64* tw   = T.tw + (size_t)g * T.N;
+  const u64* twsh = T.tw_sh + (size_t)g * T.N;
+  const u32 stride = T.N >> SA;  // = 4096
+  const u32 col    = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= stride) return;
+  u64 x[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) x[r] = data[(size_t)r * stride + col];
+#pragma unroll
+  for (int s = 0; s < SA; s++) {
+    const int m  = 1 << s;
+    const int tr = R >> (s + 1);
+#pragma unroll
+    for (int p = 0; p < R / 2; p++) {
+      const int i  = p / tr;
+      const int lo = i * 2 * tr + (p % tr);
+      ct_butterfly(x[lo], x[lo + tr], tw[m + i], twsh[m + i], q);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; r++) data[(size_t)r * stride + col] = x[r];
+}
+
+// ---- strided phase, inverse: stages with t = N/R .. N/2, then * N^-1 --------------------
+template <int SA>
+__global__ void __launch_bounds__(256) ntt_inv_strided(DeviceTables T, LimbBatch b) {
+  constexpr int R = 1 << SA;
+  const u32 limb  = blockIdx.y;
+  const u32 g     = b.g[limb];
+  const u64 q     = T.mod[g].q;
+  u64*      data  = b.base + (size_t)b.slot[limb] * T.N;
+  const u64* tw   = T.itw + (size_t)g * T.N;
+  const u64* twsh = T.itw_sh + (size_t)g * T.N;
+  const u64 ninv = T.n_inv[g], ninv_sh = T.n_inv_sh[g];
+  const u32 stride = T.N >> SA;
+  const u32 col    = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= stride) return;
+  u64 x[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) x[r] = data[(size_t)r * stride + col];
+#pragma unroll
+  for (int s = SA - 1; s >= 0; s--) {  // m = 2^s groups, row stride tr
+    const int m  = 1 << s;
+    const int tr = R >> (s + 1);
+#pragma unroll
+    for (int p = 0; p < R / 2; p++) {
+      const int i  = p / tr;
+      const int lo = i * 2 * tr + (p % tr);
+      gs_butterfly(x[lo], x[lo + tr], tw[m + i], twsh[m + i], q);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; r++)
+    data[(size_t)r * stride + col] = mul_shoup(x[r], ninv, ninv_sh, q);
+}
+
+// ---- tile phase, forward: stages s0 .. logN-1 on a contiguous tile in shared memory ----
+__global__ void __launch_bounds__(kNttThreads) ntt_fwd_tile(DeviceTables T, LimbBatch b) {
+  extern __shared__ u64 sm[];
+  const u32 limb   = blockIdx.y;
+  const u32 g      = b.g[limb];
+  const u64 q      = T.mod[g].q;
+  const u32 tile   = T.N < (u32)kTile ? T.N : (u32)kTile;
+  const u32 tlog   = T.logN < (u32)kTileLog ? T.logN : (u32)kTileLog;
+  const u32 tbase  = blockIdx.x * tile;
+  u64*      data   = b.base + (size_t)b.slot[limb] * T.N + tbase;
+  const u64* tw    = T.tw + (size_t)g * T.N;
+  const u64* twsh  = T.tw_sh + (size_t)g * T.N;
+  for (u32 i = threadIdx.x; i < tile; i += blockDim.x) sm[i] = data[i];
+  __syncthreads();
+  const u32 s0 = T.logN - tlog;
+  for (u32 s = s0; s < T.logN; s++) {
+    const u32 lt = T.logN - 1 - s;  // log2 of butterfly stride t
+    const u32 t  = 1u << lt;
+    const u32 m  = 1u << s;
+    for (u32 p = threadIdx.x; p < tile / 2; p += blockDim.x) {
+      const u32 lo = ((p >> lt) << (lt + 1)) | (p & (t - 1));
+      const u32 i  = (tbase + lo) >> (lt + 1);
+      u64 u = sm[lo], v = sm[lo + t];
+      ct_butterfly(u, v, tw[m + i], twsh[m + i], q);
+      sm[lo]     = u;
+      sm[lo + t] = v;
+    }
+    __syncthreads();
+  }
+  for (u32 i = threadIdx.x; i < tile; i += blockDim.x) data[i] = sm[i];
+}
+
+// ---- tile phase, inverse: stages with t = 1 .. tile/2; folds N^-1 when it is the only phase
+__global__ void __launch_bounds__(kNttThreads) ntt_inv_tile(DeviceTables T, LimbBatch b) {
+  extern __shared__ u64 sm[];
+  const u32 limb   = blockIdx.y;
+  const u32 g      = b.g[limb];
+  const u64 q      = T.mod[g].q;
+  const u32 tile   = T.N < (u32)kTile ? T.N : (u32)kTile;
+  const u32 tlog   = T.logN < (u32)kTileLog ? T.logN : (u32)kTileLog;
+  const u32 tbase  = blockIdx.x * tile;
+  u64*      data   = b.base + (size_t)b.slot[limb] * T.N + tbase;
+  const u64* tw    = T.itw + (size_t)g * T.N;
+  const u64* twsh  = T.itw_sh + (size_t)g * T.N;
+  for (u32 i = threadIdx.x; i < tile; i += blockDim.x) sm[i] = data[i];
+  __syncthreads();
+  for (u32 lt = 0; lt < tlog; lt++) {
+    const u32 t = 1u << lt;
+    const u32 m = T.N >> (lt + 1);
+    for (u32 p = threadIdx.x; p < tile / 2; p += blockDim.x) {
+      const u32 lo = ((p >> lt) << (lt + 1)) | (p & (t - 1));
+      const u32 i  = (tbase + lo) >> (lt + 1);
+      u64 u = sm[lo], v = sm[lo + t];
+      gs_butterfly(u, v, tw[m + i], twsh[m + i], q);
+      sm[lo]     = u;
+      sm[lo + t] = v;
+    }
+    __syncthreads();
+  }
+  if (T.logN <= (u32)kTileLog) {
+    const u64 ninv = T.n_inv[g], ninv_sh = T.n_inv_sh[g];
+    for (u32 i = threadIdx.x; i < tile; i += blockDim.x)
+      data[i] = mul_shoup(sm[i], ninv, ninv_sh, q);
+  } else {
+    for (u32 i = threadIdx.x; i < tile; i += blockDim.x) data[i] = sm[i];
+  }
+}
+
+template <int SA>
+static void launch_strided(bool fwd, const DeviceTables& T, const LimbBatch& b,
+                           cudaStream_t s) {
+  dim3 grid((T.N >> SA) / 256, b.n);
+  if (fwd) {
+    ntt_fwd_strided<SA><<<grid, 256, 0, s>>>(T, b);
+  } else {
+    ntt_inv_strided<SA><<<grid, 256, 0, s>>>(T, b);
+  }
+}
+
+static void launch_strided_any(bool fwd, const DeviceTables& T, const LimbBatch& b,
+                               cudaStream_t s) {
+  switch (T.logN - kTileLog) {
+    case 1: launch_strided<1>(fwd, T, b, s); break;
+    case 2: launch_strided<2>(fwd, T, b, s); break;
+    case 3: launch_strided<3>(fwd, T, b, s); break;
+    case 4: launch_strided<4>(fwd, T, b, s); break;
+    case 5: launch_strided<5>(fwd, T, b, s); break;
+    default: break;
+  }
+}
+
+void launch_ntt(const DeviceTables& T, const LimbBatch& b, cudaStream_t s) {
+  if (b.n == 0) return;
+  const u32 tile = T.N < (u32)kTile ? T.N : (u32)kTile;
+  if (T.logN > (u32)kTileLog) launch_strided_any(true, T, b, s);
+  dim3 grid(T.N / tile, b.n);
+  u32  threads = tile / 2 < (u32)kNttThreads ? tile / 2 : (u32)kNttThreads;
+  ntt_fwd_tile<<<grid, threads, tile * sizeof(u64), s>>>(T, b);
+}
+
+void launch_intt(const DeviceTables& T, const LimbBatch& b, cudaStream_t s) {
+  if (b.n == 0) return;
+  const u32 tile = T.N < (u32)kTile ? T.N : (u32)kTile;
+  dim3 grid(T.N / tile, b.n);
+  u32  threads = tile / 2 < (u32)kNttThreads ? tile / 2 : (u32)kNttThreads;
+  ntt_inv_tile<<<grid, threads, tile * sizeof(u64), s>>>(T, b);
+  if (T.logN > (u32)kTileLog) launch_strided_any(false, T, b, s);
+}
+
+// ------------------------------------------------------------------------------------
+// Element-wise kernels (HBM-bound): one thread per coefficient, grid.y = limb.
+// ------------------------------------------------------------------------------------
+template <int OP>
+__global__ void __launch_bounds__(256) ew_kernel(DeviceTables T, u64* __restrict__ r,
+                                                 const u64* __restrict__ a,
+                                                 const u64* __restrict__ b, u32 g0) {
+  const Modulus m   = T.mod[g0 + blockIdx.y];
+  const size_t  off = (size_t)blockIdx.y * T.N;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
+    u64 x = a[off + i], y = b[off + i];
+    u64 z;
+    if (OP == EW_ADD) z = add_mod(x, y, m.q);
+    if (OP == EW_SUB) z = sub_mod(x, y, m.q);
+    if (OP == EW_MUL) z = mul_mod(x, y, m);
+    r[off + i] = z;
+  }
+}
+
+static inline dim3 ew_grid(const DeviceTables& T, u32 n_limbs) {
+  u32 bx = (T.N + 255) / 256;
+  return dim3(bx, n_limbs);
+}
+
+void launch_ew(const DeviceTables& T, EwOp op, u64* r, const u64* a, const u64* b, u32 g0,
+               u32 n_limbs, cudaStream_t s) {
+  if (n_limbs == 0) return;
+  dim3 grid = ew_grid(T, n_limbs);
+  switch (op) {
+    case EW_ADD: ew_kernel<EW_ADD><<<grid, 256, 0, s>>>(T, r, a, b, g0); break;
+    case EW_SUB: ew_kernel<EW_SUB><<<grid, 256, 0, s>>>(T, r, a, b, g0); break;
+    case EW_MUL: ew_kernel<EW_MUL><<<grid, 256, 0, s>>>(T, r, a, b, g0); break;
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_kernel(DeviceTables T, u64* __restrict__ r,
+                                                     const u64* __restrict__ a,
+                                                     const int64_t* __restrict__ order,
+                                                     u32 g0) {
+  const u64    q   = T.mod[g0 + blockIdx.y].q;
+  const size_t off = (size_t)blockIdx.y * T.N;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
+    int64_t k = order[i];
+    // negative entries only occur for coefficient-form tables (number_theory.c:215-224)
+    r[off + i] = k >= 0 ? a[off + k] : q - a[off - k];
+  }
+}
+
+void launch_gather(const DeviceTables& T, u64* r, const u64* a, const int64_t* order, u32 g0,
+                   u32 n_limbs, cudaStream_t s) {
+  if (n_limbs == 0) return;
+  gather_kernel<<<ew_grid(T, n_limbs), 256, 0, s>>>(T, r, a, order, g0);
+}
+
+__global__ void __launch_bounds__(256) mul_scalar_kernel(DeviceTables T, u64* __restrict__ r,
+                                                         const u64* __restrict__ a,
+                                                         const u64* __restrict__ sc,
+                                                         const u64* __restrict__ sc_sh,
+                                                         u32 g0) {
+  const u64    q   = T.mod[g0 + blockIdx.y].q;
+  const u64    w = sc[blockIdx.y], wsh = sc_sh[blockIdx.y];
+  const size_t off = (size_t)blockIdx.y * T.N;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x)
+    r[off + i] = mul_shoup(a[off + i], w, wsh, q);
+}
+
+void launch_mul_scalar(const DeviceTables& T, u64* r, const u64* a, const u64* sc,
+                       const u64* sc_sh, u32 g0, u32 n_limbs, cudaStream_t s) {
+  if (n_limbs == 0) return;
+  mul_scalar_kernel<<<ew_grid(T, n_limbs), 256, 0, s>>>(T, r, a, sc, sc_sh, g0);
+}
+
+// ------------------------------------------------------------------------------------
+// Fast base conversion.  One thread per coefficient; the n_in scaled inputs y_i stay in
+// registers and are re-used for every output limb, so HBM traffic is exactly
+// (n_in + n_out) limbs; the work is n_in*n_out 64x64->128 MACs per coefficient (INT-bound).
+// ------------------------------------------------------------------------------------
+struct ConvDescPack {
+  ConvDesc d[6];
+};
+
+template <int MAXIN>
+__global__ void __launch_bounds__(128) base_conv_kernel(DeviceTables T, ConvDescPack P) {
+  extern __shared__ u64 sh_hat[];  // [n_out][n_in]
+  const ConvDesc& D = P.d[blockIdx.y];
+  const u32 n_in = D.n_in, n_out = D.n_out;
+  for (u32 i = threadIdx.x; i < n_in * n_out; i += blockDim.x) sh_hat[i] = D.hatmod[i];
+  __syncthreads();
+  const u32 n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= T.N) return;
+  u64 y[MAXIN];
+#pragma unroll
+  for (int i = 0; i < MAXIN; i++) {
+    if (i < (int)n_in) {
+      const u64 q = T.mod[D.g_in[i]].q;
+      y[i] = mul_shoup(D.x[(size_t)i * T.N + n], D.hatinv[i], D.hatinv_sh[i], q);
+    }
+  }
+  for (u32 o = 0; o < n_out; o++) {
+    const Modulus m = T.mod[D.g_out[o]];
+    const u64*    h = sh_hat + o * n_in;
+    u64 lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < MAXIN; i++) {
+      if (i < (int)n_in) mac128(lo, hi, y[i], h[i]);
+    }
+    D.out[(size_t)D.out_slot[o] * T.N + n] = reduce128(lo, hi, m);
+  }
+}
+
+void launch_base_conv(const DeviceTables& T, const ConvDesc* descs, u32 n_desc,
+                      cudaStream_t s) {
+  if (n_desc == 0) return;
+  ConvDescPack P;
+  u32 max_in = 0, max_sh = 0;
+  for (u32 i = 0; i < n_desc; i++) {
+    P.d[i] = descs[i];
+    if (descs[i].n_in > max_in) max_in = descs[i].n_in;
+    u32 sh = descs[i].n_in * descs[i].n_out;
+    if (sh > max_sh) max_sh = sh;
+  }
+  dim3   grid((T.N + 127) / 128, n_desc);
+  size_t shm = max_sh * sizeof(u64);
+  if (max_in <= 4) {
+    base_conv_kernel<4><<<grid, 128, shm, s>>>(T, P);
+  } else if (max_in <= 12) {
+    base_conv_kernel<12><<<grid, 128, shm, s>>>(T, P);
+  } else if (max_in <= 16) {
+    base_conv_kernel<16><<<grid, 128, shm, s>>>(T, P);
+  } else {
+    base_conv_kernel<48><<<grid, 128, shm, s>>>(T, P);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Key-switch inner product.  Streams the evaluation key exactly once (2*beta*(num_q+K)
+// limbs) plus beta*(num_q+K) ext limbs; accumulates in 128 bits and reduces once.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ksw_inner_kernel(DeviceTables T, u64* __restrict__ acc0,
+                                                        u64* __restrict__ acc1,
+                                                        const u64* __restrict__ ext,
+                                                        const u64* __restrict__ key0,
+                                                        const u64* __restrict__ key1, u32 beta,
+                                                        u32 num_q, u32 L, u32 K) {
+  const u32     o = blockIdx.y;
+  const u32     g = o < num_q ? o : L + (o - num_q);
+  const u32     W = num_q + K;
+  const Modulus m = T.mod[g];
+  const u32     n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= T.N) return;
+  u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+  for (u32 j = 0; j < beta; j++) {
+    const u64 e  = ext[((size_t)j * W + o) * T.N + n];
+    const u64 k0 = key0[((size_t)j * (L + K) + g) * T.N + n];
+    const u64 k1 = key1[((size_t)j * (L + K) + g) * T.N + n];
+    mac128(lo0, hi0, e, k0);
+    mac128(lo1, hi1, e, k1);
+  }
+  acc0[(size_t)o * T.N + n] = reduce128(lo0, hi0, m);
+  acc1[(size_t)o * T.N + n] = reduce128(lo1, hi1, m);
+}
+
+void launch_ksw_inner(const DeviceTables& T, u64* acc0, u64* acc1, const u64* ext,
+                      const u64* key0, const u64* key1, u32 beta, u32 num_q, u32 L, u32 K,
+                      cudaStream_t s) {
+  dim3 grid((T.N + 255) / 256, num_q + K);
+  ksw_inner_kernel<<<grid, 256, 0, s>>>(T, acc0, acc1, ext, key0, key1, beta, num_q, L, K);
+}
+
+__global__ void __launch_bounds__(256) moddown_tail_kernel(
+    DeviceTables T, u64* __restrict__ out, const u64* __restrict__ old,
+    const u64* __restrict__ conv, const u64* __restrict__ add, const u64* __restrict__ pinv,
+    const u64* __restrict__ pinv_sh) {
+  const u32    l   = blockIdx.y;
+  const u64    q   = T.mod[l].q;
+  const u64    w = pinv[l], wsh = pinv_sh[l];
+  const size_t off = (size_t)l * T.N;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
+    u64 v = mul_shoup(sub_mod(old[off + i], conv[off + i], q), w, wsh, q);
+    if (add != nullptr) v = add_mod(v, add[off + i], q);
+    out[off + i] = v;
+  }
+}
+
+void launch_moddown_tail(const DeviceTables& T, u64* out, const u64* old, const u64* conv,
+                         const u64* add, const u64* pinv, const u64* pinv_sh, u32 n_limbs,
+                         cudaStream_t s) {
+  if (n_limbs == 0) return;
+  moddown_tail_kernel<<<ew_grid(T, n_limbs), 256, 0, s>>>(T, out, old, conv, add, pinv,
+                                                          pinv_sh);
+}
+
+__global__ void __launch_bounds__(256) rescale_pre_kernel(DeviceTables T, u64* __restrict__ tmp,
+                                                          const u64* __restrict__ last, u32 l,
+                                                          const u64* __restrict__ negqlinv,
+                                                          const u64* __restrict__ negqlinv_sh) {
+  const u32    i   = blockIdx.y;
+  const u64    qi  = T.mod[i].q, ql = T.mod[l].q;
+  const u64    w = negqlinv[i], wsh = negqlinv_sh[i];
+  const size_t off = (size_t)i * T.N;
+  for (u32 n = blockIdx.x * blockDim.x + threadIdx.x; n < T.N; n += gridDim.x * blockDim.x)
+    tmp[off + n] = mul_shoup(switch_modulus(last[n], ql, qi), w, wsh, qi);
+}
+
+void launch_rescale_pre(const DeviceTables& T, u64* tmp, const u64* last, u32 l,
+                        const u64* negqlinv, const u64* negqlinv_sh, cudaStream_t s) {
+  if (l == 0) return;
+  rescale_pre_kernel<<<ew_grid(T, l), 256, 0, s>>>(T, tmp, last, l, negqlinv, negqlinv_sh);
+}
+
+__global__ void __launch_bounds__(256) rescale_post_kernel(DeviceTables T, u64* __restrict__ out,
+                                                           const u64* __restrict__ c,
+                                                           const u64* __restrict__ tmp,
+                                                           const u64* __restrict__ qlinv,
+                                                           const u64* __restrict__ qlinv_sh) {
+  const u32    i   = blockIdx.y;
+  const u64    qi  = T.mod[i].q;
+  const u64    w = qlinv[i], wsh = qlinv_sh[i];
+  const size_t off = (size_t)i * T.N;
+  for (u32 n = blockIdx.x * blockDim.x + threadIdx.x; n < T.N; n += gridDim.x * blockDim.x)
+    out[off + n] = add_mod(mul_shoup(c[off + n], w, wsh, qi), tmp[off + n], qi);
+}
+
+void launch_rescale_post(const DeviceTables& T, u64* out, const u64* c, const u64* tmp,
+                         const u64* qlinv, const u64* qlinv_sh, u32 n_limbs, cudaStream_t s) {
+  if (n_limbs == 0) return;
+  rescale_post_kernel<<<ew_grid(T, n_limbs), 256, 0, s>>>(T, out, c, tmp, qlinv, qlinv_sh);
+}
+
+}  // namespace ace

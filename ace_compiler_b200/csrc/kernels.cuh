@@ -1,0 +1,88 @@
+// kernels.cuh -- launch wrappers of the hand-written sm_100a kernels (kernels.cu).
+// All kernels work on limb-major RNS polynomials: limb l of a polynomial is the contiguous
+// array data[l*N .. (l+1)*N) of canonical residues (int64 in the reference,
+// fhe-cmplr/rtlib/ant/include/util/polynomial.h:35-44; u64 here, same bits).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "modarith.cuh"
+
+namespace ace {
+
+constexpr int kMaxBatch = 192;  // limbs per batched launch (3 digits x 45 limbs fits)
+
+// A batch of limbs living at base + slot[i]*N, limb i reduced modulo modulus g[i].
+struct LimbBatch {
+  u64*     base;
+  u32      n;
+  uint16_t slot[kMaxBatch];
+  uint16_t g[kMaxBatch];
+};
+
+// Device-resident per-context tables.
+struct DeviceTables {
+  u32            N, logN;
+  u32            G;        // L + K
+  const Modulus* mod;      // [G]
+  const u64*     tw;       // [G][N] psi powers, bit-reversed order   (ntt.c:95-101)
+  const u64*     tw_sh;    // [G][N] Shoup companions                 (ntt.c:119-126)
+  const u64*     itw;      // [G][N] inverse psi powers
+  const u64*     itw_sh;
+  const u64*     n_inv;    // [G]
+  const u64*     n_inv_sh;
+};
+
+void launch_ntt(const DeviceTables& T, const LimbBatch& b, cudaStream_t s);
+void launch_intt(const DeviceTables& T, const LimbBatch& b, cudaStream_t s);
+
+enum EwOp { EW_ADD = 0, EW_SUB = 1, EW_MUL = 2 };
+// r[i] = a[i] op b[i] over n_limbs consecutive limbs, limb i uses modulus g0 + i
+void launch_ew(const DeviceTables& T, EwOp op, u64* r, const u64* a, const u64* b, u32 g0,
+               u32 n_limbs, cudaStream_t s);
+// r[l][i] = a[l][order[i]]  (Hw_rotate with a non-negative order table, poly_arith.c:41-56)
+void launch_gather(const DeviceTables& T, u64* r, const u64* a, const int64_t* order,
+                   u32 g0, u32 n_limbs, cudaStream_t s);
+// r = a * scalar[l] mod q_l, scalar given per limb with Shoup companion
+void launch_mul_scalar(const DeviceTables& T, u64* r, const u64* a, const u64* sc,
+                       const u64* sc_sh, u32 g0, u32 n_limbs, cudaStream_t s);
+
+// Approximate fast base conversion (no correction term):
+//   y_i   = x_i * hatinv_i mod b_i                     i < n_in
+//   out_o = (sum_i y_i * hatmod[o][i]) mod t_o         o < n_out
+// x: n_in limbs (coefficient form) at x + in_slot*N ..., moduli g_in[]; out limbs at
+// out + out_slot[o]*N with moduli g_out[o].   (polynomial.c:755-807, 1297-1320)
+struct ConvDesc {
+  const u64* x;        // first input limb
+  u64*       out;      // base of output polynomial
+  const u64* hatinv;   // [n_in]
+  const u64* hatinv_sh;
+  const u64* hatmod;   // [n_out][n_in]
+  u32        n_in, n_out;
+  uint16_t   g_in[48];
+  uint16_t   g_out[64];
+  uint16_t   out_slot[64];
+};
+void launch_base_conv(const DeviceTables& T, const ConvDesc* descs, u32 n_desc,
+                      cudaStream_t s);
+
+// key-switch inner product over digits (emitted loops, resnet20 .inc:7005-7032):
+//   acc0[o] = sum_j ext_j[o] * key0_j[g(o)],  acc1 likewise, o < W = num_q + K
+// ext: [beta][W][N]; key0/key1: [dnum][L+K][N]; g(o) = o < num_q ? o : L + o - num_q
+void launch_ksw_inner(const DeviceTables& T, u64* acc0, u64* acc1, const u64* ext,
+                      const u64* key0, const u64* key1, u32 beta, u32 num_q, u32 L, u32 K,
+                      cudaStream_t s);
+
+// ModDown tail: out[l] = (old[l] - conv[l]) * pinv[l] (+ add[l] if add != nullptr)
+void launch_moddown_tail(const DeviceTables& T, u64* out, const u64* old, const u64* conv,
+                         const u64* add, const u64* pinv, const u64* pinv_sh, u32 n_limbs,
+                         cudaStream_t s);
+
+// Rescale (polynomial.c:1097-1161):
+//  pre : tmp[i] = switch_modulus(last, q_l, q_i) * negqlinv[i]          (coefficient form)
+//  post: out[i] = c[i] * qlinv[i] + NTT(tmp)[i]
+void launch_rescale_pre(const DeviceTables& T, u64* tmp, const u64* last, u32 l,
+                        const u64* negqlinv, const u64* negqlinv_sh, cudaStream_t s);
+void launch_rescale_post(const DeviceTables& T, u64* out, const u64* c, const u64* tmp,
+                         const u64* qlinv, const u64* qlinv_sh, u32 n_limbs, cudaStream_t s);
+
+}  // namespace ace

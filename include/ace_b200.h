@@ -1,0 +1,101 @@
+/* ace_b200.h -- C ABI of the B200-native CKKS evaluation runtime (libace_b200.so).
+ *
+ * Drop-in boundary for the polynomial-level "rt_ant" API that ACE-generated C calls
+ * (reference: fhe-cmplr/rtlib/include/rt_ant/rt_ant.h:17-21 and the headers it pulls in).
+ * Plain pointers and sizes only.  Every `int64_t*` limb pointer below is a DEVICE pointer
+ * obtained from ace_alloc_limbs(); a "limb" is N int64 canonical residues, polynomials are
+ * limb-major exactly like POLYNOMIAL._data (ant/include/util/polynomial.h:35-44): the
+ * num_q Q-limbs first, then the K P-limbs.
+ *
+ * Modulus index `g`: 0..L-1 are the Q primes, L..L+K-1 the P primes -- the same order in
+ * which the reference lays out its contiguous MODULUS arrays (Q_modulus()+i, P_modulus()+i,
+ * ant/src/rtlib/context.c:156-160).
+ *
+ * All calls are asynchronous on the context's CUDA stream except ace_download/ace_sync.
+ * Return value: 0 on success, negative on error (message via ace_last_error()); the
+ * reference aborts on the same conditions (FMT_ASSERT, rtlib/include/common/error.h:23-29).
+ */
+#ifndef ACE_B200_H
+#define ACE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ace_ctx ace_ctx;
+
+/* ---- context: replaces Prepare_context's parameter/CRT/NTT-table part
+ *      (ant/src/rtlib/context.c:29-47, ant/src/util/ckks_parameters.c:60-97).
+ *      Arguments are the CKKS_PARAMS fields (rtlib/include/common/common.h:71-82). */
+int  ace_ctx_create(ace_ctx** out, uint32_t poly_degree, size_t mul_depth,
+                    size_t first_mod_size, size_t scaling_mod_size, size_t num_q_parts,
+                    size_t hamming_weight, int device);
+void ace_ctx_destroy(ace_ctx* ctx);          /* Finalize_context, context.c:88-138 */
+const char* ace_last_error(void);
+
+uint32_t ace_degree(const ace_ctx* ctx);     /* Degree(),      context.c:140-142 */
+size_t   ace_num_q(const ace_ctx* ctx);      /* Get_primes_cnt(Get_q(crt)) */
+size_t   ace_num_p(const ace_ctx* ctx);      /* Get_p_cnt(),   context.c:154 */
+size_t   ace_num_q_parts(const ace_ctx* ctx);/* Get_q_parts(), context.c:148-150 */
+size_t   ace_part_size(const ace_ctx* ctx);  /* Get_per_part_size(qpart) */
+int      ace_get_primes(const ace_ctx* ctx, int64_t* q, int64_t* p); /* Q_modulus()/P_modulus() values */
+int64_t  ace_psi(const ace_ctx* ctx, uint32_t g);   /* 2N-th root of unity behind NTT_CONTEXT._rou */
+size_t   ace_num_decomp(const ace_ctx* ctx, size_t num_q); /* Num_decomp(), poly_eval.h:108-113 */
+uint64_t ace_launch_count(const ace_ctx* ctx);      /* kernels launched so far */
+
+/* ---- memory: Alloc_poly/Free_poly_data (ant/include/poly/poly_eval.h:29-37,
+ *      ant/include/util/polynomial.h:54-77); zero != 0 reproduces the memset. */
+int64_t* ace_alloc_limbs(ace_ctx* ctx, size_t n_limbs, int zero);
+int      ace_free_limbs(ace_ctx* ctx, int64_t* dev);
+int      ace_upload(ace_ctx* ctx, int64_t* dev_dst, const int64_t* host_src, size_t n_limbs);
+int      ace_download(ace_ctx* ctx, int64_t* host_dst, const int64_t* dev_src, size_t n_limbs);
+int      ace_copy_limbs(ace_ctx* ctx, int64_t* dev_dst, const int64_t* dev_src, size_t n_limbs); /* Set_coeffs, poly_eval.h:74-79 */
+int      ace_zero_limbs(ace_ctx* ctx, int64_t* dev, size_t n_limbs);
+int      ace_sync(ace_ctx* ctx);
+
+/* ---- per-limb "hardware" ops (ant/src/poly/poly_arith.c:14-56).  n_limbs consecutive
+ *      limbs are processed in one launch, limb i with modulus g0+i (n_limbs = 1 is the
+ *      reference call). */
+int ace_hw_modadd(ace_ctx* ctx, int64_t* res, const int64_t* a, const int64_t* b, uint32_t g0, uint32_t n_limbs);
+int ace_hw_modsub(ace_ctx* ctx, int64_t* res, const int64_t* a, const int64_t* b, uint32_t g0, uint32_t n_limbs);
+int ace_hw_modmul(ace_ctx* ctx, int64_t* res, const int64_t* a, const int64_t* b, uint32_t g0, uint32_t n_limbs);
+int ace_hw_rotate(ace_ctx* ctx, int64_t* res, const int64_t* a, const int64_t* order_dev, uint32_t g0, uint32_t n_limbs);
+
+/* ---- negacyclic NTT / INTT in place (Ftt_fwd / Ftt_inv, ant/src/util/ntt.c:163-187) */
+int ace_ntt(ace_ctx* ctx, int64_t* data, uint32_t g0, uint32_t n_limbs);
+int ace_intt(ace_ctx* ctx, int64_t* data, uint32_t g0, uint32_t n_limbs);
+
+/* ---- polynomial-level ops (ant/src/poly/poly_eval.c:28-49).
+ *      decomp_modup: in = num_q limbs, out = num_q + K limbs.
+ *      mod_down:     in = num_q + K limbs, out = num_q limbs.
+ *      rescale:      in = num_q limbs, out = num_q - 1 limbs.            NTT form throughout. */
+int ace_decomp_modup(ace_ctx* ctx, int64_t* out, const int64_t* in, uint32_t num_q, uint32_t q_part_idx);
+int ace_mod_down(ace_ctx* ctx, int64_t* out, const int64_t* in, uint32_t num_q);
+int ace_rescale(ace_ctx* ctx, int64_t* out, const int64_t* in, uint32_t num_q);
+
+/* ---- keys and automorphism tables (ant/include/rtlib/key_gen.h:28-75).
+ *      A switch key is num_q_parts public keys; each polynomial has L+K limbs.
+ *      ace_swk_import copies one host polynomial (Pk0_at: which=0, Pk1_at: which=1). */
+uint32_t ace_auto_index(const ace_ctx* ctx, int32_t rot_idx);          /* Auto_idx   */
+const int64_t* ace_auto_order(ace_ctx* ctx, int32_t rot_idx);          /* Auto_order (device table) */
+int ace_swk_import(ace_ctx* ctx, int is_rot, int32_t rot_idx, uint32_t part, int which, const int64_t* host_poly);
+const int64_t* ace_swk_poly(ace_ctx* ctx, int is_rot, int32_t rot_idx, uint32_t part, int which); /* device pointer, Pk0_at/Pk1_at */
+
+/* ---- fused ciphertext-level entry points: same results as the emitted Rotate() /
+ *      Relinearize() bodies (dataset/resnet20_cifar10_pre.onnx.inc:6972-7146) with all
+ *      limbs and digits batched.  All pointers: num_q limbs. */
+int ace_key_switch(ace_ctx* ctx, int64_t* out0, int64_t* out1, const int64_t* d, uint32_t num_q, int is_rot, int32_t rot_idx);
+int ace_ct_rotate(ace_ctx* ctx, int64_t* r0, int64_t* r1, const int64_t* c0, const int64_t* c1, uint32_t num_q, int32_t rot_idx);
+int ace_ct_mul_relin(ace_ctx* ctx, int64_t* r0, int64_t* r1, const int64_t* a0, const int64_t* a1, const int64_t* b0, const int64_t* b1, uint32_t num_q);
+int ace_ct_rescale(ace_ctx* ctx, int64_t* r0, int64_t* r1, const int64_t* c0, const int64_t* c1, uint32_t num_q);
+
+/* ---- timing helpers for the benchmark: CUDA events on the context's stream */
+int ace_timer_start(ace_ctx* ctx);
+int ace_timer_stop_ms(ace_ctx* ctx, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACE_B200_H */
