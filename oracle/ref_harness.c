@@ -401,3 +401,62 @@ void ref_ct_bootstrap(REF_CT* res, const REF_CT* a, uint32_t level_after_bts) {
   Unwrap_ct(res, z);
   Free_ciphertext(z);
 }
+
+/* ---- CPU baseline: the chain HMult+relin -> rescale -> rotate on independent ciphertexts,
+ *      one per thread, sharing the (read-only) context like the reference's OpenMP image
+ *      loop does (ant/dataset/resnet_cifar.main.inc:81).  Returns wall seconds. ---------- */
+#include <pthread.h>
+#include <time.h>
+
+typedef struct {
+  CIPHERTEXT* ct;
+  int         iters;
+  int32_t     rot;
+} CHAIN_ARG;
+
+static void* Chain_worker(void* p) {
+  CHAIN_ARG* a = (CHAIN_ARG*)p;
+  for (int i = 0; i < a->iters; i++) {
+    CIPHERTEXT* m  = Alloc_ciphertext();
+    CIPHERTEXT* rs = Alloc_ciphertext();
+    CIPHERTEXT* r  = Alloc_ciphertext();
+    Mul_ciph(m, a->ct, a->ct);
+    Rescale_ciph(rs, m);
+    Rotate_ciph(r, rs, a->rot);
+    Free_ciphertext(m);
+    Free_ciphertext(rs);
+    Free_ciphertext(r);
+  }
+  return NULL;
+}
+
+double ref_bench_chain(int nthreads, int iters, uint32_t level, int32_t rot) {
+  if (nthreads < 1) nthreads = 1;
+  uint32_t    slots = Degree() / 2;
+  CIPHERTEXT** cts  = (CIPHERTEXT**)malloc(sizeof(CIPHERTEXT*) * nthreads);
+  VALUE_LIST* vec   = Alloc_value_list(DCMPLX_TYPE, slots);
+  for (uint32_t i = 0; i < slots; i++) {
+    DCMPLX_VALUE_AT(vec, i) = ((i * 2654435761u) % 1000) / 1000.0 - 0.5;
+  }
+  for (int t = 0; t < nthreads; t++) {
+    PLAINTEXT* plain = Alloc_plaintext();
+    Encode_at_level_with_sf(plain, (CKKS_ENCODER*)Context->_encoder, vec, level, slots, 1);
+    cts[t] = Alloc_ciphertext();
+    Encrypt_msg(cts[t], (CKKS_ENCRYPTOR*)Context->_encryptor, plain);
+    Free_plaintext(plain);
+  }
+  pthread_t* th   = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
+  CHAIN_ARG* args = (CHAIN_ARG*)malloc(sizeof(CHAIN_ARG) * nthreads);
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int t = 0; t < nthreads; t++) {
+    args[t].ct = cts[t]; args[t].iters = iters; args[t].rot = rot;
+    pthread_create(&th[t], NULL, Chain_worker, &args[t]);
+  }
+  for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  for (int t = 0; t < nthreads; t++) Free_ciphertext(cts[t]);
+  free(cts); free(th); free(args);
+  Free_value_list(vec);
+  return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
