@@ -204,7 +204,7 @@ static void copy_limbs(u64* dst, const u64* src, size_t n_limbs, u32 N, cudaStre
 void Context::ntt(u64* data, u32 g0, u32 n) {
   for (u32 done = 0; done < n; done += kMaxBatch) {
     LimbBatch b;
-    b.base = data;
+    b.base = data; b.src = nullptr;
     b.n    = std::min<u32>(kMaxBatch, n - done);
     for (u32 i = 0; i < b.n; i++) { b.slot[i] = (u16)(done + i); b.g[i] = (u16)(g0 + done + i); }
     launch_ntt(T, b, stream);
@@ -214,9 +214,24 @@ void Context::ntt(u64* data, u32 g0, u32 n) {
 void Context::intt(u64* data, u32 g0, u32 n) {
   for (u32 done = 0; done < n; done += kMaxBatch) {
     LimbBatch b;
-    b.base = data;
+    b.base = data; b.src = nullptr;
     b.n    = std::min<u32>(kMaxBatch, n - done);
     for (u32 i = 0; i < b.n; i++) { b.slot[i] = (u16)(done + i); b.g[i] = (u16)(g0 + done + i); }
+    launch_intt(T, b, stream);
+    launches += (logN > 12) ? 2 : 1;
+  }
+}
+
+// out-of-place inverse transform: dst[i] = INTT(src[i]) for n consecutive limbs
+void Context::intt_from(u64* dst, const u64* src, u32 g0, u32 n) {
+  for (u32 done = 0; done < n; done += kMaxBatch) {
+    LimbBatch b;
+    b.base = dst; b.src = src;
+    b.n    = std::min<u32>(kMaxBatch, n - done);
+    for (u32 i = 0; i < b.n; i++) {
+      b.slot[i] = b.src_slot[i] = (u16)(done + i);
+      b.g[i]    = (u16)(g0 + done + i);
+    }
     launch_intt(T, b, stream);
     launches += (logN > 12) ? 2 : 1;
   }
@@ -275,14 +290,13 @@ void Context::fill_conv_desc(ConvDesc& d, const ModUpTab& t, const u64* x, u64* 
 void Context::decomp_modup(u64* out, const u64* in, u32 num_q, u32 part) {
   const ModUpTab& t = modup_tab(num_q, part);
   u64* coef = alloc_limbs(t.n_in, false);
-  copy_limbs(coef, in + (size_t)t.start * N, t.n_in, N, stream);
   copy_limbs(out + (size_t)t.start * N, in + (size_t)t.start * N, t.n_in, N, stream);
-  intt(coef, t.start, t.n_in);
+  intt_from(coef, in + (size_t)t.start * N, t.start, t.n_in);
   ConvDesc d;
   fill_conv_desc(d, t, coef, out);
   launch_base_conv(T, &d, 1, stream);
   LimbBatch b;
-  b.base = out; b.n = t.n_out;
+  b.base = out; b.src = nullptr; b.n = t.n_out;
   for (u32 o = 0; o < t.n_out; o++) { b.slot[o] = t.out_slot[o]; b.g[o] = t.g_out[o]; }
   launch_ntt(T, b, stream);
   launches += 1 + ((logN > 12) ? 2 : 1);
@@ -293,8 +307,7 @@ void Context::decomp_modup(u64* out, const u64* in, u32 num_q, u32 part) {
 void Context::mod_down(u64* out, const u64* in, u32 num_q) {
   u64* pc   = alloc_limbs(K, false);
   u64* conv = alloc_limbs(num_q, false);
-  copy_limbs(pc, in + (size_t)num_q * N, K, N, stream);
-  intt(pc, (u32)L, (u32)K);
+  intt_from(pc, in + (size_t)num_q * N, (u32)L, (u32)K);
   ConvDesc d;
   d.x = pc; d.out = conv;
   d.hatinv = phat_inv_; d.hatinv_sh = phat_inv_sh_; d.hatmod = phat_mod_q_;
@@ -315,8 +328,7 @@ void Context::rescale(u64* out, const u64* in, u32 num_q) {
   const u32 l = num_q - 1;
   u64* last = alloc_limbs(1, false);
   u64* tmp  = alloc_limbs(l, false);
-  copy_limbs(last, in + (size_t)l * N, 1, N, stream);
-  intt(last, l, 1);
+  intt_from(last, in + (size_t)l * N, l, 1);
   launch_rescale_pre(T, tmp, last, l, negqlinv_ + (size_t)l * L, negqlinv_sh_ + (size_t)l * L,
                      stream);
   ntt(tmp, 0, l);
@@ -374,15 +386,13 @@ void Context::key_switch(u64* out0, u64* out1, const u64* d, u32 num_q, const Sw
   u64* coef = alloc_limbs(num_q, false);
   u64* ext  = alloc_limbs((size_t)beta * W, false);
   u64* acc  = alloc_limbs(2 * (size_t)W, false);
-  copy_limbs(coef, d, num_q, N, stream);
-  intt(coef, 0, num_q);
+  intt_from(coef, d, 0, num_q);
   ConvDesc  descs[6];
   LimbBatch nb;
-  nb.base = ext; nb.n = 0;
+  nb.base = ext; nb.src = nullptr; nb.n = 0;
   for (u32 j = 0; j < beta; j++) {
     const ModUpTab& t = modup_tab(num_q, j);
     u64* ext_j = ext + (size_t)j * W * N;
-    copy_limbs(ext_j + (size_t)t.start * N, d + (size_t)t.start * N, t.n_in, N, stream);
     fill_conv_desc(descs[j % 6], t, coef + (size_t)t.start * N, ext_j);
     if (j % 6 == 5 || j == beta - 1) {
       launch_base_conv(T, descs, j % 6 + 1, stream);
@@ -402,16 +412,19 @@ void Context::key_switch(u64* out0, u64* out1, const u64* d, u32 num_q, const Sw
   launch_ntt(T, nb, stream);
   launches += (logN > 12) ? 2 : 1;
   u64 *acc0 = acc, *acc1 = acc + (size_t)W * N;
-  launch_ksw_inner(T, acc0, acc1, ext, key.k0, key.k1, beta, num_q, (u32)L, (u32)K, stream);
+  launch_ksw_inner(T, acc0, acc1, ext, d, (u32)part_size, key.k0, key.k1, beta, num_q, (u32)L,
+                   (u32)K, stream);
   launches++;
   // ModDown of both accumulators
   u64* pc   = alloc_limbs(2 * K, false);
   u64* conv = alloc_limbs(2 * (size_t)num_q, false);
-  copy_limbs(pc, acc0 + (size_t)num_q * N, K, N, stream);
-  copy_limbs(pc + K * (size_t)N, acc1 + (size_t)num_q * N, K, N, stream);
   LimbBatch pb;
-  pb.base = pc; pb.n = 2 * (u32)K;
-  for (u32 i = 0; i < 2 * K; i++) { pb.slot[i] = (u16)i; pb.g[i] = (u16)(L + i % K); }
+  pb.base = pc; pb.src = acc; pb.n = 2 * (u32)K;
+  for (u32 i = 0; i < 2 * K; i++) {
+    pb.slot[i]     = (u16)i;
+    pb.src_slot[i] = (u16)((i / K) * W + num_q + i % K);
+    pb.g[i]        = (u16)(L + i % K);
+  }
   launch_intt(T, pb, stream);
   ConvDesc md[2];
   for (int h = 0; h < 2; h++) {
@@ -424,7 +437,7 @@ void Context::key_switch(u64* out0, u64* out1, const u64* d, u32 num_q, const Sw
   }
   launch_base_conv(T, md, 2, stream);
   LimbBatch cb;
-  cb.base = conv; cb.n = 2 * num_q;
+  cb.base = conv; cb.src = nullptr; cb.n = 2 * num_q;
   for (u32 i = 0; i < 2 * num_q; i++) { cb.slot[i] = (u16)i; cb.g[i] = (u16)(i % num_q); }
   launch_ntt(T, cb, stream);
   launch_moddown_tail(T, out0, acc0, conv, add0, pinv_mod_q_, pinv_mod_q_sh_, num_q, stream);

@@ -70,6 +70,7 @@ class Context {
   // ---- transforms on `n` consecutive limbs starting at modulus g0
   void ntt(u64* data, u32 g0, u32 n);
   void intt(u64* data, u32 g0, u32 n);
+  void intt_from(u64* dst, const u64* src, u32 g0, u32 n);
 
   // ---- reference polynomial-level API (a5, a6, a8)
   void decomp_modup(u64* out, const u64* in, u32 num_q, u32 part);

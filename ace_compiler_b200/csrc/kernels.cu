@@ -29,30 +29,37 @@ constexpr int kTileLog   = 12;
 constexpr int kTile      = 1 << kTileLog;
 constexpr int kNttThreads = 512;
 
-// forward butterfly: (u, v) -> (u + w v, u - w v)
+// Harvey-style lazy butterflies: values stay in [0, 4q) (forward) / [0, 2q) (inverse) between
+// stages, one conditional subtraction per butterfly; the final pass normalises to [0, q), so
+// the stored result is the same canonical residue the reference produces (ntt.c:206-263).
+__device__ __forceinline__ u64 csub(u64 a, u64 m) { return a >= m ? a - m : a; }
+
+// forward: (u, v) -> (u + w v, u - w v); in/out in [0, 4q)
 __device__ __forceinline__ void ct_butterfly(u64& u, u64& v, u64 w, u64 wsh, u64 q) {
-  u64 t = mul_shoup(v, w, wsh, q);
-  u64 a = u + t;
-  a     = a >= q ? a - q : a;
-  v     = u >= t ? u - t : u + q - t;
-  u     = a;
+  const u64 q2 = 2 * q;
+  u64 a = csub(u, q2);
+  u64 t = mul_shoup_lazy(v, w, wsh, q);
+  u     = a + t;
+  v     = a - t + q2;
 }
-// inverse butterfly: (u, v) -> (u + v, (u - v) w)
+// inverse: (u, v) -> (u + v, (u - v) w); in/out in [0, 2q)
 __device__ __forceinline__ void gs_butterfly(u64& u, u64& v, u64 w, u64 wsh, u64 q) {
-  u64 d = u >= v ? u - v : u + q - v;
-  u64 a = u + v;
-  u     = a >= q ? a - q : a;
-  v     = mul_shoup(d, w, wsh, q);
+  const u64 q2 = 2 * q;
+  u64 d = u - v + q2;
+  u     = csub(u + v, q2);
+  v     = mul_shoup_lazy(d, w, wsh, q);
 }
+__device__ __forceinline__ u64 normalize4(u64 a, u64 q) { return csub(csub(a, 2 * q), q); }
 
 // ---- strided phase, forward: stages 0 .. SA-1, R = 2^SA rows at stride N/R -------------
 template <int SA>
-__global__ void __launch_bounds__(256) ntt_fwd_strided(DeviceTables T, LimbBatch b) {
+__global__ void __launch_bounds__(128) ntt_fwd_strided(DeviceTables T, LimbBatch b) {
   constexpr int R = 1 << SA;
   const u32 limb  = blockIdx.y;
   const u32 g     = b.g[limb];
   const u64 q     = T.mod[g].q;
   u64*      data  = b.base + (size_t)b.slot[limb] * T.N;
+  const u64* in   = b.src ? b.src + (size_t)b.src_slot[limb] * T.N : data;
   const u64* tw   = T.tw + (size_t)g * T.N;
   const u64* twsh = T.tw_sh + (size_t)g * T.N;
   const u32 stride = T.N >> SA;  // = 4096
@@ -60,7 +67,7 @@ __global__ void __launch_bounds__(256) ntt_fwd_strided(DeviceTables T, LimbBatch
   if (col >= stride) return;
   u64 x[R];
 #pragma unroll
-  for (int r = 0; r < R; r++) x[r] = data[(size_t)r * stride + col];
+  for (int r = 0; r < R; r++) x[r] = in[(size_t)r * stride + col];
 #pragma unroll
   for (int s = 0; s < SA; s++) {
     const int m  = 1 << s;
@@ -78,7 +85,7 @@ __global__ void __launch_bounds__(256) ntt_fwd_strided(DeviceTables T, LimbBatch
 
 // ---- strided phase, inverse: stages with t = N/R .. N/2, then * N^-1 --------------------
 template <int SA>
-__global__ void __launch_bounds__(256) ntt_inv_strided(DeviceTables T, LimbBatch b) {
+__global__ void __launch_bounds__(128) ntt_inv_strided(DeviceTables T, LimbBatch b) {
   constexpr int R = 1 << SA;
   const u32 limb  = blockIdx.y;
   const u32 g     = b.g[limb];
@@ -121,7 +128,8 @@ __global__ void __launch_bounds__(kNttThreads) ntt_fwd_tile(DeviceTables T, Limb
   u64*      data   = b.base + (size_t)b.slot[limb] * T.N + tbase;
   const u64* tw    = T.tw + (size_t)g * T.N;
   const u64* twsh  = T.tw_sh + (size_t)g * T.N;
-  for (u32 i = threadIdx.x; i < tile; i += blockDim.x) sm[i] = data[i];
+  const u64* in    = b.src ? b.src + (size_t)b.src_slot[limb] * T.N + tbase : data;
+  for (u32 i = threadIdx.x; i < tile; i += blockDim.x) sm[i] = in[i];
   __syncthreads();
   const u32 s0 = T.logN - tlog;
   for (u32 s = s0; s < T.logN; s++) {
@@ -138,7 +146,7 @@ __global__ void __launch_bounds__(kNttThreads) ntt_fwd_tile(DeviceTables T, Limb
     }
     __syncthreads();
   }
-  for (u32 i = threadIdx.x; i < tile; i += blockDim.x) data[i] = sm[i];
+  for (u32 i = threadIdx.x; i < tile; i += blockDim.x) data[i] = normalize4(sm[i], q);
 }
 
 // ---- tile phase, inverse: stages with t = 1 .. tile/2; folds N^-1 when it is the only phase
@@ -153,7 +161,8 @@ __global__ void __launch_bounds__(kNttThreads) ntt_inv_tile(DeviceTables T, Limb
   u64*      data   = b.base + (size_t)b.slot[limb] * T.N + tbase;
   const u64* tw    = T.itw + (size_t)g * T.N;
   const u64* twsh  = T.itw_sh + (size_t)g * T.N;
-  for (u32 i = threadIdx.x; i < tile; i += blockDim.x) sm[i] = data[i];
+  const u64* in    = b.src ? b.src + (size_t)b.src_slot[limb] * T.N + tbase : data;
+  for (u32 i = threadIdx.x; i < tile; i += blockDim.x) sm[i] = in[i];
   __syncthreads();
   for (u32 lt = 0; lt < tlog; lt++) {
     const u32 t = 1u << lt;
@@ -177,14 +186,160 @@ __global__ void __launch_bounds__(kNttThreads) ntt_inv_tile(DeviceTables T, Limb
   }
 }
 
+// ---- tile phase for N >= 4096, register radix-8 version ---------------------------------
+// 512 threads x 8 elements = one 4096-element tile.  The 12 stages run as 4 passes of three
+// radix-2 stages held in registers; between passes the tile is transposed through shared
+// memory (two padded buffers used alternately -> one barrier per exchange).  Pass 0 of the
+// forward transform reads global memory directly in its register pattern (coalesced) and the
+// last pass leaves 8 consecutive coefficients per thread, written with 16-byte stores; the
+// inverse transform mirrors this.
+__host__ __device__ constexpr u32 kPad(u32 i) { return i + (i >> 3); }  // 1 pad per 8 elements
+constexpr int kTileSm = kTile + (kTile >> 3);
+
+// position of element k (0..7) of thread tid in a pass whose innermost stride is 2^ltq
+__device__ __forceinline__ u32 r8_base(u32 tid, u32 ltq) {
+  return ((tid >> ltq) << (ltq + 3)) | (tid & ((1u << ltq) - 1));
+}
+
+// three forward stages (strides 4tq, 2tq, tq) on x[0..7]; ia = (tile_base + base) >> (ltq+3)
+__device__ __forceinline__ void ct_radix8(u64 (&x)[8], const u64* __restrict__ tw,
+                                          const u64* __restrict__ twsh, u32 ma, u32 ia, u64 q) {
+  {
+    const u64 w = __ldg(tw + ma + ia), ws = __ldg(twsh + ma + ia);
+#pragma unroll
+    for (int k = 0; k < 4; k++) ct_butterfly(x[k], x[k + 4], w, ws, q);
+  }
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const u32 idx = 2 * ma + 2 * ia + h;
+    const u64 w = __ldg(tw + idx), ws = __ldg(twsh + idx);
+    ct_butterfly(x[4 * h + 0], x[4 * h + 2], w, ws, q);
+    ct_butterfly(x[4 * h + 1], x[4 * h + 3], w, ws, q);
+  }
+#pragma unroll
+  for (int h = 0; h < 4; h++) {
+    const u32 idx = 4 * ma + 4 * ia + h;
+    const u64 w = __ldg(tw + idx), ws = __ldg(twsh + idx);
+    ct_butterfly(x[2 * h], x[2 * h + 1], w, ws, q);
+  }
+}
+
+// three inverse stages (strides tq, 2tq, 4tq); mc = N / (8 tq) is the group count of the
+// widest stage, ic = (tile_base + base) >> (ltq+3)
+__device__ __forceinline__ void gs_radix8(u64 (&x)[8], const u64* __restrict__ tw,
+                                          const u64* __restrict__ twsh, u32 mc, u32 ic, u64 q) {
+#pragma unroll
+  for (int h = 0; h < 4; h++) {
+    const u32 idx = 4 * mc + 4 * ic + h;
+    const u64 w = __ldg(tw + idx), ws = __ldg(twsh + idx);
+    gs_butterfly(x[2 * h], x[2 * h + 1], w, ws, q);
+  }
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const u32 idx = 2 * mc + 2 * ic + h;
+    const u64 w = __ldg(tw + idx), ws = __ldg(twsh + idx);
+    gs_butterfly(x[4 * h + 0], x[4 * h + 2], w, ws, q);
+    gs_butterfly(x[4 * h + 1], x[4 * h + 3], w, ws, q);
+  }
+  {
+    const u64 w = __ldg(tw + mc + ic), ws = __ldg(twsh + mc + ic);
+#pragma unroll
+    for (int k = 0; k < 4; k++) gs_butterfly(x[k], x[k + 4], w, ws, q);
+  }
+}
+
+__global__ void __launch_bounds__(512, 2) ntt_fwd_tile8(DeviceTables T, LimbBatch b) {
+  extern __shared__ u64 sm[];
+  u64* buf[2] = {sm, sm + kTileSm};
+  const u32 limb  = blockIdx.y;
+  const u32 g     = b.g[limb];
+  const u64 q     = T.mod[g].q;
+  const u32 tbase = blockIdx.x * kTile;
+  u64*      data  = b.base + (size_t)b.slot[limb] * T.N + tbase;
+  const u64* tw   = T.tw + (size_t)g * T.N;
+  const u64* twsh = T.tw_sh + (size_t)g * T.N;
+  const u32 tid   = threadIdx.x;
+  const u32 m0    = T.N >> kTileLog;  // groups of the first tile stage (stride 2048)
+  // the strided phase (if any) already moved the limb to its destination
+  const u64* in = (b.src && T.logN == (u32)kTileLog)
+                      ? b.src + (size_t)b.src_slot[limb] * T.N + tbase : data;
+  u64 x[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) x[k] = in[tid + 512 * k];
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    const u32 ltq  = 9 - 3 * p;  // log2 of the innermost stride of this pass
+    const u32 base = r8_base(tid, ltq);
+    if (p > 0) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) x[k] = buf[(p - 1) & 1][kPad(base + (k << ltq))];
+    }
+    ct_radix8(x, tw, twsh, m0 << (3 * p), (tbase + base) >> (ltq + 3), q);
+    if (p < 3) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) buf[p & 1][kPad(base + (k << ltq))] = x[k];
+      __syncthreads();
+    }
+  }
+  ulonglong2* out = reinterpret_cast<ulonglong2*>(data + 8 * tid);
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    out[k] = make_ulonglong2(normalize4(x[2 * k], q), normalize4(x[2 * k + 1], q));
+}
+
+__global__ void __launch_bounds__(512, 2) ntt_inv_tile8(DeviceTables T, LimbBatch b) {
+  extern __shared__ u64 sm[];
+  u64* buf[2] = {sm, sm + kTileSm};
+  const u32 limb  = blockIdx.y;
+  const u32 g     = b.g[limb];
+  const u64 q     = T.mod[g].q;
+  const u32 tbase = blockIdx.x * kTile;
+  u64*      data  = b.base + (size_t)b.slot[limb] * T.N + tbase;
+  const u64* tw   = T.itw + (size_t)g * T.N;
+  const u64* twsh = T.itw_sh + (size_t)g * T.N;
+  const u32 tid   = threadIdx.x;
+  u64 x[8];
+  {
+    const u64* src = b.src ? b.src + (size_t)b.src_slot[limb] * T.N + tbase : data;
+    const ulonglong2* in = reinterpret_cast<const ulonglong2*>(src + 8 * tid);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      ulonglong2 v = in[k];
+      x[2 * k] = v.x; x[2 * k + 1] = v.y;
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    const u32 ltq  = 3 * p;
+    const u32 base = r8_base(tid, ltq);
+    if (p > 0) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) x[k] = buf[(p - 1) & 1][kPad(base + (k << ltq))];
+    }
+    gs_radix8(x, tw, twsh, T.N >> (ltq + 3), (tbase + base) >> (ltq + 3), q);
+    if (p < 3) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) buf[p & 1][kPad(base + (k << ltq))] = x[k];
+      __syncthreads();
+    }
+  }
+  if (T.logN == (u32)kTileLog) {  // single-phase transform: fold N^-1 here
+    const u64 ninv = T.n_inv[g], ninv_sh = T.n_inv_sh[g];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = mul_shoup(x[k], ninv, ninv_sh, q);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) data[tid + 512 * k] = x[k];
+}
+
 template <int SA>
 static void launch_strided(bool fwd, const DeviceTables& T, const LimbBatch& b,
                            cudaStream_t s) {
-  dim3 grid((T.N >> SA) / 256, b.n);
+  dim3 grid((T.N >> SA) / 128, b.n);
   if (fwd) {
-    ntt_fwd_strided<SA><<<grid, 256, 0, s>>>(T, b);
+    ntt_fwd_strided<SA><<<grid, 128, 0, s>>>(T, b);
   } else {
-    ntt_inv_strided<SA><<<grid, 256, 0, s>>>(T, b);
+    ntt_inv_strided<SA><<<grid, 128, 0, s>>>(T, b);
   }
 }
 
@@ -205,6 +360,16 @@ void launch_ntt(const DeviceTables& T, const LimbBatch& b, cudaStream_t s) {
   const u32 tile = T.N < (u32)kTile ? T.N : (u32)kTile;
   if (T.logN > (u32)kTileLog) launch_strided_any(true, T, b, s);
   dim3 grid(T.N / tile, b.n);
+  if (T.logN >= (u32)kTileLog) {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(ntt_fwd_tile8, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           2 * kTileSm * (int)sizeof(u64));
+      attr = true;
+    }
+    ntt_fwd_tile8<<<grid, 512, 2 * kTileSm * sizeof(u64), s>>>(T, b);
+    return;
+  }
   u32  threads = tile / 2 < (u32)kNttThreads ? tile / 2 : (u32)kNttThreads;
   ntt_fwd_tile<<<grid, threads, tile * sizeof(u64), s>>>(T, b);
 }
@@ -213,8 +378,18 @@ void launch_intt(const DeviceTables& T, const LimbBatch& b, cudaStream_t s) {
   if (b.n == 0) return;
   const u32 tile = T.N < (u32)kTile ? T.N : (u32)kTile;
   dim3 grid(T.N / tile, b.n);
-  u32  threads = tile / 2 < (u32)kNttThreads ? tile / 2 : (u32)kNttThreads;
-  ntt_inv_tile<<<grid, threads, tile * sizeof(u64), s>>>(T, b);
+  if (T.logN >= (u32)kTileLog) {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(ntt_inv_tile8, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           2 * kTileSm * (int)sizeof(u64));
+      attr = true;
+    }
+    ntt_inv_tile8<<<grid, 512, 2 * kTileSm * sizeof(u64), s>>>(T, b);
+  } else {
+    u32 threads = tile / 2 < (u32)kNttThreads ? tile / 2 : (u32)kNttThreads;
+    ntt_inv_tile<<<grid, threads, tile * sizeof(u64), s>>>(T, b);
+  }
   if (T.logN > (u32)kTileLog) launch_strided_any(false, T, b, s);
 }
 
@@ -359,6 +534,8 @@ void launch_base_conv(const DeviceTables& T, const ConvDesc* descs, u32 n_desc,
 __global__ void __launch_bounds__(256) ksw_inner_kernel(DeviceTables T, u64* __restrict__ acc0,
                                                         u64* __restrict__ acc1,
                                                         const u64* __restrict__ ext,
+                                                        const u64* __restrict__ own,
+                                                        u32 part_size,
                                                         const u64* __restrict__ key0,
                                                         const u64* __restrict__ key1, u32 beta,
                                                         u32 num_q, u32 L, u32 K) {
@@ -370,7 +547,8 @@ __global__ void __launch_bounds__(256) ksw_inner_kernel(DeviceTables T, u64* __r
   if (n >= T.N) return;
   u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
   for (u32 j = 0; j < beta; j++) {
-    const u64 e  = ext[((size_t)j * W + o) * T.N + n];
+    const bool mine = own != nullptr && o < num_q && o / part_size == j;
+    const u64 e = mine ? own[(size_t)o * T.N + n] : ext[((size_t)j * W + o) * T.N + n];
     const u64 k0 = key0[((size_t)j * (L + K) + g) * T.N + n];
     const u64 k1 = key1[((size_t)j * (L + K) + g) * T.N + n];
     mac128(lo0, hi0, e, k0);
@@ -381,10 +559,11 @@ __global__ void __launch_bounds__(256) ksw_inner_kernel(DeviceTables T, u64* __r
 }
 
 void launch_ksw_inner(const DeviceTables& T, u64* acc0, u64* acc1, const u64* ext,
-                      const u64* key0, const u64* key1, u32 beta, u32 num_q, u32 L, u32 K,
-                      cudaStream_t s) {
+                      const u64* own, u32 part_size, const u64* key0, const u64* key1,
+                      u32 beta, u32 num_q, u32 L, u32 K, cudaStream_t s) {
   dim3 grid((T.N + 255) / 256, num_q + K);
-  ksw_inner_kernel<<<grid, 256, 0, s>>>(T, acc0, acc1, ext, key0, key1, beta, num_q, L, K);
+  ksw_inner_kernel<<<grid, 256, 0, s>>>(T, acc0, acc1, ext, own, part_size, key0, key1, beta,
+                                        num_q, L, K);
 }
 
 __global__ void __launch_bounds__(256) moddown_tail_kernel(

@@ -11,12 +11,15 @@ namespace ace {
 
 constexpr int kMaxBatch = 192;  // limbs per batched launch (3 digits x 45 limbs fits)
 
-// A batch of limbs living at base + slot[i]*N, limb i reduced modulo modulus g[i].
+// A batch of limbs: limb i is read from src + src_slot[i]*N, transformed modulo modulus g[i]
+// and written to base + slot[i]*N.  src == nullptr means in place (src = base, same slots).
 struct LimbBatch {
-  u64*     base;
-  u32      n;
-  uint16_t slot[kMaxBatch];
-  uint16_t g[kMaxBatch];
+  u64*       base;
+  const u64* src;
+  u32        n;
+  uint16_t   slot[kMaxBatch];
+  uint16_t   src_slot[kMaxBatch];
+  uint16_t   g[kMaxBatch];
 };
 
 // Device-resident per-context tables.
@@ -68,9 +71,11 @@ void launch_base_conv(const DeviceTables& T, const ConvDesc* descs, u32 n_desc,
 // key-switch inner product over digits (emitted loops, resnet20 .inc:7005-7032):
 //   acc0[o] = sum_j ext_j[o] * key0_j[g(o)],  acc1 likewise, o < W = num_q + K
 // ext: [beta][W][N]; key0/key1: [dnum][L+K][N]; g(o) = o < num_q ? o : L + o - num_q
+// own != nullptr: the digit's own limbs (o in [j*part_size, (j+1)*part_size)) are read from
+// own[o] (the key-switched polynomial itself) instead of ext_j[o].
 void launch_ksw_inner(const DeviceTables& T, u64* acc0, u64* acc1, const u64* ext,
-                      const u64* key0, const u64* key1, u32 beta, u32 num_q, u32 L, u32 K,
-                      cudaStream_t s);
+                      const u64* own, u32 part_size, const u64* key0, const u64* key1,
+                      u32 beta, u32 num_q, u32 L, u32 K, cudaStream_t s);
 
 // ModDown tail: out[l] = (old[l] - conv[l]) * pinv[l] (+ add[l] if add != nullptr)
 void launch_moddown_tail(const DeviceTables& T, u64* out, const u64* old, const u64* conv,
