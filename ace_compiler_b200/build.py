@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libace_b200.so")
-SOURCES = ["kernels.cu", "context.cu", "capi.cu"]
+SOURCES = ["kernels.cu", "context.cu", "client.cu", "capi.cu", "rt_shim.cu"]
 
 
 def needs_build():
@@ -21,7 +21,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false",
            "-std=c++17", "-shared", "-Xcompiler", "-fPIC", 
            "-cudart", "shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:

@@ -1,0 +1,544 @@
+// client.cu -- key generation, encryption/decryption and CKKS encode/decode for the B200
+// runtime.  Arithmetic runs on the GPU with the kernels of kernels.cu; sampling uses a
+// counter-based generator (NOT the reference's BLAKE2/rand() streams: keys produced here are
+// valid but not bit-identical to the reference's -- parity runs import the oracle's keys).
+//
+// Reference routines followed (paths under fhe-cmplr/rtlib/ant/):
+//   keys       src/util/ckks_key_generator.c:69-336, src/util/polynomial.c:1349-1412
+//   encrypt    src/util/ckks_encryptor.c:20-95        decrypt  src/util/ckks_decryptor.c:19-65
+//   encode     src/util/ckks_encoder.c:199-299 (+464-528 for constants), src/util/ntt.c:713-753
+//   decode     src/util/ckks_encoder.c:649-703, src/util/polynomial.c:467-497, ntt.c:672-711
+#include <cmath>
+#include <complex>
+#include <cstring>
+#include <random>
+
+#include "context.h"
+#include "host_math.h"
+
+namespace ace {
+
+// ------------------------------------------------------------------------------ sampling
+__device__ __forceinline__ u64 mix64(u64 x) {  // splitmix64 finaliser
+  x += 0x9e3779b97f4a7c15ull;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+  return x ^ (x >> 31);
+}
+
+// uniform residues: limb l (modulus g[l]) gets floor(r * q / 2^64), r a 64-bit hash
+__global__ void uniform_kernel(DeviceTables T, LimbBatch b, u64 seed) {
+  const u32 limb = blockIdx.y;
+  const u64 q    = T.mod[b.g[limb]].q;
+  u64*      out  = b.base + (size_t)b.slot[limb] * T.N;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
+    u64 r  = mix64(mix64(seed + limb) ^ (u64)i);
+    out[i] = __umul64hi(r, q);
+  }
+}
+
+// "triangle" samples (random_sample.c:78-97): -1, +1 with probability 1/4 each, else 0;
+// the same small coefficient is written to every limb of the batch (Transform_values_to_rns)
+__global__ void triangle_kernel(DeviceTables T, LimbBatch b, u64 seed) {
+  const u32 limb = blockIdx.y;
+  const u64 q    = T.mod[b.g[limb]].q;
+  u64*      out  = b.base + (size_t)b.slot[limb] * T.N;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
+    u64 r  = mix64(seed ^ ((u64)i << 20)) & 3;
+    out[i] = r == 0 ? q - 1 : (r == 1 ? 1 : 0);
+  }
+}
+
+// small signed coefficients (host-sampled) -> residues
+__global__ void small_to_rns_kernel(DeviceTables T, LimbBatch b, const int64_t* __restrict__ v) {
+  const u32 limb = blockIdx.y;
+  const u64 q    = T.mod[b.g[limb]].q;
+  u64*      out  = b.base + (size_t)b.slot[limb] * T.N;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
+    int64_t x = v[i];
+    out[i]    = x < 0 ? q - (u64)(-x) % q : (u64)x % q;
+    if (out[i] == q) out[i] = 0;
+  }
+}
+
+// out = e + fac[l] * nk - a * old   on the limbs of the batch (fac = 0 outside the digit)
+__global__ void swk_b_kernel(DeviceTables T, LimbBatch b, const u64* __restrict__ a,
+                             const u64* __restrict__ e, const u64* __restrict__ nk,
+                             const u64* __restrict__ old, const u64* __restrict__ fac) {
+  const u32     limb = blockIdx.y;
+  const Modulus m    = T.mod[b.g[limb]];
+  const size_t  off  = (size_t)b.slot[limb] * T.N;
+  const u64     f    = fac[limb];
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
+    u64 v = e[off + i];
+    if (f) v = add_mod(v, mul_mod(nk[off + i], f, m), m.q);
+    b.base[off + i] = sub_mod(v, mul_mod(a[off + i], old[off + i], m), m.q);
+  }
+}
+
+static LimbBatch all_limbs(u64* base, u32 g0, u32 n) {
+  LimbBatch b;
+  b.base = base; b.src = nullptr; b.n = n;
+  for (u32 i = 0; i < n; i++) { b.slot[i] = (uint16_t)i; b.g[i] = (uint16_t)(g0 + i); }
+  return b;
+}
+
+static dim3 grid_for(u32 N, u32 n) { return dim3((N + 255) / 256, n); }
+
+void Context::gen_secret_key(u64 seed) {
+  std::mt19937_64 rng(seed);
+  std::vector<int64_t> s(N, 0);
+  size_t hw = params.hamming_weight;
+  if (hw == 0) {  // uniform ternary (random_sample.c:127-131)
+    for (auto& x : s) x = (int64_t)(rng() % 3) - 1;
+  } else {
+    if (hw > N) hw = N;
+    size_t placed = 0;
+    while (placed < hw) {
+      size_t idx = rng() % N;
+      if (s[idx] == 0) { s[idx] = (rng() & 1) ? 1 : -1; placed++; }
+    }
+  }
+  int64_t* dv = nullptr;
+  ACE_CUDA(cudaMalloc(&dv, N * sizeof(int64_t)));
+  ACE_CUDA(cudaMemcpy(dv, s.data(), N * sizeof(int64_t), cudaMemcpyHostToDevice));
+  if (!sk_ntt) ACE_CUDA(cudaMalloc(&sk_ntt, G * (size_t)N * sizeof(u64)));
+  LimbBatch b = all_limbs(sk_ntt, 0, (u32)G);
+  small_to_rns_kernel<<<grid_for(N, (u32)G), 256, 0, stream>>>(T, b, dv);
+  ntt(sk_ntt, 0, (u32)G);
+  sync();
+  cudaFree(dv);
+}
+
+void Context::import_secret_key(const u64* host_ntt_qp) {
+  if (!sk_ntt) ACE_CUDA(cudaMalloc(&sk_ntt, G * (size_t)N * sizeof(u64)));
+  ACE_CUDA(cudaMemcpy(sk_ntt, host_ntt_qp, G * (size_t)N * sizeof(u64), cudaMemcpyHostToDevice));
+}
+
+void Context::import_public_key(const u64* h0, const u64* h1) {
+  if (!pk0) ACE_CUDA(cudaMalloc(&pk0, L * (size_t)N * sizeof(u64)));
+  if (!pk1) ACE_CUDA(cudaMalloc(&pk1, L * (size_t)N * sizeof(u64)));
+  ACE_CUDA(cudaMemcpy(pk0, h0, L * (size_t)N * sizeof(u64), cudaMemcpyHostToDevice));
+  ACE_CUDA(cudaMemcpy(pk1, h1, L * (size_t)N * sizeof(u64), cudaMemcpyHostToDevice));
+}
+
+// pk = (-a s + e, a) over Q  (ckks_key_generator.c:84-125)
+void Context::gen_public_key(u64 seed) {
+  if (!sk_ntt) throw std::runtime_error("secret key missing");
+  if (!pk0) ACE_CUDA(cudaMalloc(&pk0, L * (size_t)N * sizeof(u64)));
+  if (!pk1) ACE_CUDA(cudaMalloc(&pk1, L * (size_t)N * sizeof(u64)));
+  u64* e = alloc_limbs(L, false);
+  LimbBatch ba = all_limbs(pk1, 0, (u32)L), be = all_limbs(e, 0, (u32)L);
+  uniform_kernel<<<grid_for(N, (u32)L), 256, 0, stream>>>(T, ba, seed * 3 + 1);
+  triangle_kernel<<<grid_for(N, (u32)L), 256, 0, stream>>>(T, be, seed * 3 + 2);
+  ntt(e, 0, (u32)L);
+  launch_ew(T, EW_MUL, pk0, pk1, sk_ntt, 0, (u32)L, stream);
+  launch_ew(T, EW_SUB, pk0, e, pk0, 0, (u32)L, stream);
+  free_limbs(e);
+  sync();
+}
+
+// Generate_switching_key (ckks_key_generator.c:127-200): for every digit j
+//   a_j uniform over Q u P,  b_j = e_j + [P]_q * new_key (digit limbs only) - a_j * old_key
+void Context::gen_switch_key(SwitchKey& key, const u64* new_key, const u64* old_key, u64 seed) {
+  const size_t per = G * (size_t)N;
+  if (!key.k0) ACE_CUDA(cudaMalloc(&key.k0, dnum * per * sizeof(u64)));
+  if (!key.k1) ACE_CUDA(cudaMalloc(&key.k1, dnum * per * sizeof(u64)));
+  u64* e = alloc_limbs(G, false);
+  std::vector<u64> fac(G);
+  u64* dfac = nullptr;
+  ACE_CUDA(cudaMalloc(&dfac, G * sizeof(u64)));
+  for (size_t j = 0; j < dnum; j++) {
+    u64* a = key.k1 + j * per;
+    u64* b = key.k0 + j * per;
+    LimbBatch ba = all_limbs(a, 0, (u32)G), be = all_limbs(e, 0, (u32)G),
+              bb = all_limbs(b, 0, (u32)G);
+    uniform_kernel<<<grid_for(N, (u32)G), 256, 0, stream>>>(T, ba, seed * 1000003 + 2 * j);
+    triangle_kernel<<<grid_for(N, (u32)G), 256, 0, stream>>>(T, be, seed * 1000003 + 2 * j + 1);
+    ntt(e, 0, (u32)G);
+    for (size_t g = 0; g < G; g++) {
+      fac[g] = 0;
+      if (g < L && g >= j * part_size && g < (j + 1) * part_size) {
+        u64 pm = 1;  // P mod q_g  (Get_pmodq)
+        for (size_t k = 0; k < K; k++) pm = hm::mulmod(pm, mod[L + k] % mod[g], mod[g]);
+        fac[g] = pm;
+      }
+    }
+    ACE_CUDA(cudaMemcpyAsync(dfac, fac.data(), G * sizeof(u64), cudaMemcpyHostToDevice, stream));
+    swk_b_kernel<<<grid_for(N, (u32)G), 256, 0, stream>>>(T, bb, a, e, new_key, old_key, dfac);
+    sync();
+  }
+  free_limbs(e);
+  sync();
+  cudaFree(dfac);
+}
+
+void Context::gen_relin_key(u64 seed) {  // new = s^2, old = s (ckks_key_generator.c:203-215)
+  u64* s2 = alloc_limbs(G, false);
+  launch_ew(T, EW_MUL, s2, sk_ntt, sk_ntt, 0, (u32)G, stream);
+  gen_switch_key(relin_key, s2, sk_ntt, seed);
+  free_limbs(s2);
+}
+
+static u64 inv_mod_pow2(u64 a, u64 M) {  // odd a, M a power of two
+  u64 x = 1;
+  for (int i = 0; i < 7; i++) x = x * (2 - a * x);
+  return x & (M - 1);
+}
+
+// "fast" rotation key for automorphism index k (ckks_key_generator.c:237-264):
+// old key = sigma_{k^-1}(s), new key = s, so that the automorphism is applied after the switch
+void Context::gen_auto_key(u32 k, u64 seed) {
+  const u64 M = 2 * (u64)N;
+  u32 kinv = (u32)inv_mod_pow2(k, M);
+  const int64_t* order = auto_order(kinv);
+  u64* rot = alloc_limbs(G, false);
+  launch_gather(T, rot, sk_ntt, order, 0, (u32)G, stream);
+  gen_switch_key(rot_keys_[k], sk_ntt, rot, seed);
+  free_limbs(rot);
+}
+
+void Context::keygen(u64 seed, const int32_t* rots, size_t n_rots) {
+  ACE_CUDA(cudaSetDevice(device));
+  gen_secret_key(seed);
+  gen_public_key(seed + 1);
+  gen_relin_key(seed + 2);
+  for (size_t i = 0; i < n_rots; i++) {
+    u32 k = auto_index(rots[i]);
+    if (!has_rot_key(k)) gen_auto_key(k, seed + 3 + i);
+  }
+}
+
+// Encrypt_msg (ckks_encryptor.c:20-95): c0 = pk0 u + e1 + m, c1 = pk1 u + e2
+void Context::encrypt(u64* c0, u64* c1, const u64* pt, u32 level, u64 seed) {
+  if (!pk0) throw std::runtime_error("public key missing");
+  u64* t = alloc_limbs(3 * (size_t)level, false);
+  u64 *u = t, *e1 = t + (size_t)level * N, *e2 = t + 2 * (size_t)level * N;
+  LimbBatch bu = all_limbs(u, 0, level), b1 = all_limbs(e1, 0, level),
+            b2 = all_limbs(e2, 0, level);
+  triangle_kernel<<<grid_for(N, level), 256, 0, stream>>>(T, bu, seed * 7 + 1);
+  triangle_kernel<<<grid_for(N, level), 256, 0, stream>>>(T, b1, seed * 7 + 2);
+  triangle_kernel<<<grid_for(N, level), 256, 0, stream>>>(T, b2, seed * 7 + 3);
+  ntt(t, 0, level);
+  ntt(e1, 0, level);
+  ntt(e2, 0, level);
+  launch_ew(T, EW_MUL, c0, pk0, u, 0, level, stream);
+  launch_ew(T, EW_ADD, c0, c0, e1, 0, level, stream);
+  launch_ew(T, EW_ADD, c0, c0, pt, 0, level, stream);
+  launch_ew(T, EW_MUL, c1, pk1, u, 0, level, stream);
+  launch_ew(T, EW_ADD, c1, c1, e2, 0, level, stream);
+  free_limbs(t);
+}
+
+// Decrypt (ckks_decryptor.c:19-65): m = c0 + c1 s
+void Context::decrypt(u64* pt, const u64* c0, const u64* c1, u32 level) {
+  if (!sk_ntt) throw std::runtime_error("secret key missing");
+  launch_ew(T, EW_MUL, pt, c1, sk_ntt, 0, level, stream);
+  launch_ew(T, EW_ADD, pt, pt, c0, 0, level, stream);
+}
+
+// ------------------------------------------------------------------------------ encode
+// FP64 arithmetic below must round exactly like the reference's x86-64 build (no FMA
+// contraction): every operation is an explicit _rn intrinsic.
+struct cplx { double re, im; };
+
+// one stage of Embedding_inv (ntt.c:725-747): (a, b) -> (a + b, (a - b) * w)
+__global__ void emb_inv_stage_kernel(cplx* __restrict__ v, const cplx* __restrict__ tw,
+                                     u32 slots, u32 logm) {
+  const u32 num2 = 1u << (logm - 1);
+  for (u32 p = blockIdx.x * blockDim.x + threadIdx.x; p < slots / 2;
+       p += gridDim.x * blockDim.x) {
+    const u32 i  = p & (num2 - 1);
+    const u32 lo = ((p >> (logm - 1)) << logm) | i;
+    const cplx a = v[lo], b = v[lo + num2], w = tw[num2 - 1 + i];
+    cplx s, d, r;
+    s.re = __dadd_rn(a.re, b.re);
+    s.im = __dadd_rn(a.im, b.im);
+    d.re = __dsub_rn(a.re, b.re);
+    d.im = __dsub_rn(a.im, b.im);
+    r.re = __dsub_rn(__dmul_rn(d.re, w.re), __dmul_rn(d.im, w.im));
+    r.im = __dadd_rn(__dmul_rn(d.re, w.im), __dmul_rn(d.im, w.re));
+    v[lo]        = s;
+    v[lo + num2] = r;
+  }
+}
+
+// bit-reverse, divide by slots, scale by Delta, round, spread with `gap`, reduce into every limb
+// (ckks_encoder.c:247-263 + polynomial.c:362-392); powp[l] = Delta^(sf_degree-1) mod q_l or 0
+__global__ void emb_round_rns_kernel(DeviceTables T, LimbBatch b, const cplx* __restrict__ v,
+                                     u32 slots, u32 logslots, double delta,
+                                     const u64* __restrict__ powp) {
+  const u32     limb = blockIdx.y;
+  const Modulus m    = T.mod[b.g[limb]];
+  u64*          out  = b.base + (size_t)b.slot[limb] * T.N;
+  const u32     gap  = T.N / (2 * slots);
+  const u64     pw   = powp ? powp[limb] : 0;
+  for (u32 n = blockIdx.x * blockDim.x + threadIdx.x; n < T.N; n += gridDim.x * blockDim.x) {
+    u64 res = 0;
+    if (n % gap == 0) {
+      const u32  k  = n / gap;           // < 2*slots
+      const u32  i  = k < slots ? k : k - slots;
+      const cplx c  = v[logslots ? (__brev(i) >> (32 - logslots)) : 0];
+      double     x  = k < slots ? c.re : c.im;
+      x             = __ddiv_rn(x, (double)slots);
+      x             = __dadd_rn(__dmul_rn(x, delta), 0.5);
+      long long  r  = llround(x);
+      // r mod q (Max_64bit_value detour of the reference is the identity for |r| < 2^62)
+      long long  q  = (long long)m.q;
+      long long  t  = r % q;
+      if (t < 0) t += q;
+      res = (u64)t;
+      if (pw) res = mul_mod(res, pw, m);
+    }
+    out[n] = res;
+  }
+}
+
+__global__ void fill_limb_kernel(DeviceTables T, LimbBatch b, const u64* __restrict__ val) {
+  const u32 limb = blockIdx.y;
+  u64*      out  = b.base + (size_t)b.slot[limb] * T.N;
+  const u64 v    = val[limb];
+  for (u32 n = blockIdx.x * blockDim.x + threadIdx.x; n < T.N; n += gridDim.x * blockDim.x)
+    out[n] = v;
+}
+
+void Context::init_encoder() {
+  if (enc_tw_) return;
+  // Precompute_fft (ntt.c:585-610) with fft_length = 2N, folded per stage:
+  //   tw[logm][i] = rou[(idx_mod - rot_group[i] % idx_mod) * gap]
+  const size_t M = 2 * (size_t)N, half = N / 2;
+  fft_rou_.resize(M);
+  for (size_t i = 0; i < M; i++) {
+    double angle = 2 * M_PI * i / M;
+    fft_rou_[i]  = std::complex<double>(cos(angle), sin(angle));
+  }
+  rot_group_.resize(half);
+  rot_group_[0] = 1;
+  for (size_t i = 1; i < half; i++) rot_group_[i] = (5 * rot_group_[i - 1]) % M;
+  // stage tables for every slot count share the same layout: entry (num2 - 1 + i)
+  std::vector<cplx> tw(half > 0 ? half : 1);
+  for (u32 logm = 1; (1u << logm) <= half; logm++) {
+    size_t idx_mod = (size_t)1 << (logm + 2), gap = M / idx_mod, num2 = (size_t)1 << (logm - 1);
+    for (size_t i = 0; i < num2; i++) {
+      auto w = fft_rou_[(idx_mod - (rot_group_[i] % idx_mod)) * gap];
+      tw[num2 - 1 + i] = cplx{w.real(), w.imag()};
+    }
+  }
+  cplx* d = nullptr;
+  ACE_CUDA(cudaMalloc(&d, tw.size() * sizeof(cplx)));
+  ACE_CUDA(cudaMemcpy(d, tw.data(), tw.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+  enc_tw_ = d;
+  ACE_CUDA(cudaMalloc(&enc_buf_, half * sizeof(cplx)));
+  ACE_CUDA(cudaMalloc(&enc_pow_, G * sizeof(u64)));
+  ACE_CUDA(cudaMallocHost(&enc_host_, half * sizeof(cplx)));
+}
+
+// Encode_impl (ckks_encoder.c:199-299).  vals: `len` real messages (host), zero padded to slots.
+// out: level (+ p_cnt) limbs, NTT form.
+void Context::encode(u64* out, const double* vals, size_t len, u32 level, u32 slots,
+                     u32 sf_degree, u32 p_cnt) {
+  init_encoder();
+  if (slots == 0) slots = N / 2;
+  if (level == 0) level = (u32)L;
+  if (len > slots || slots > N / 2 || (slots & (slots - 1)))
+    throw std::runtime_error("encode: bad slot count");
+  if (level > L || sf_degree < 1 || p_cnt > K) throw std::runtime_error("encode: bad level");
+  u32 logslots = 0;
+  while ((1u << logslots) < slots) logslots++;
+  cplx* hv = (cplx*)enc_host_;
+  cplx* dv = (cplx*)enc_buf_;
+  ACE_CUDA(cudaStreamSynchronize(stream));  // enc_host_ may still feed a previous encode
+  for (size_t i = 0; i < slots; i++) hv[i] = cplx{i < len ? vals[i] : 0.0, 0.0};
+  ACE_CUDA(cudaMemcpyAsync(dv, hv, slots * sizeof(cplx), cudaMemcpyHostToDevice, stream));
+  const cplx* tw = (const cplx*)enc_tw_;
+  for (u32 logm = logslots; logm > 0; logm--) {
+    u32 blocks = std::max<u32>(1, std::min<u32>(slots / 2 / 256, 1024));
+    emb_inv_stage_kernel<<<blocks, 256, 0, stream>>>(dv, tw, slots, logm);
+  }
+  const double delta = (double)((u64)1 << params.scaling_mod_size);
+  const u32 nl = level + p_cnt;
+  LimbBatch b;
+  b.base = out; b.src = nullptr; b.n = nl;
+  std::vector<u64> powp(nl, 0);
+  for (u32 l = 0; l < nl; l++) {
+    b.slot[l] = (uint16_t)l;
+    b.g[l]    = (uint16_t)(l < level ? l : L + (l - level));
+    if (sf_degree > 1 && l < level) {
+      u64 q = mod[l], p = (u64)delta % q;
+      for (u32 d = 2; d < sf_degree; d++) p = hm::mulmod(p, (u64)delta % q, q);
+      powp[l] = p;
+    }
+  }
+  const u64* dpow = nullptr;
+  if (sf_degree > 1) {
+    ACE_CUDA(cudaMemcpyAsync(enc_pow_, powp.data(), nl * sizeof(u64), cudaMemcpyHostToDevice,
+                             stream));
+    dpow = enc_pow_;
+  }
+  emb_round_rns_kernel<<<grid_for(N, nl), 256, 0, stream>>>(T, b, dv, slots, logslots, delta,
+                                                           dpow);
+  launch_ntt(T, b, stream);
+  launches += logslots + 1 + ((logN > 12) ? 2 : 1);
+}
+
+// Encode_val_at_level (ckks_encoder.c:464-528): constant plaintext, every coefficient of limb
+// l equals the same residue (NTT of a constant polynomial... the reference marks it NTT as is)
+void Context::encode_value(u64* out, double value, u32 level, u32 sf_degree) {
+  init_encoder();
+  if (level == 0) level = (u32)L;
+  const double sf = (double)((u64)1 << params.scaling_mod_size);
+  const int MAX_BITS_IN_WORD = 61;
+  int32_t log_sf     = (int32_t)ceil(log2(fabs(value * sf)));
+  int32_t log_valid  = (log_sf <= MAX_BITS_IN_WORD) ? log_sf : MAX_BITS_IN_WORD;
+  int32_t log_approx = log_sf - log_valid;
+  double  approx_factor = pow(2, log_approx);
+  double  scaled = value / approx_factor * sf + 0.5;
+  int64_t val    = (int64_t)scaled;
+  int64_t sf_deg_scalar = (int64_t)(sf + 0.5);
+  std::vector<u64> res(level);
+  for (u32 i = 0; i < level; i++) {
+    int64_t q = (int64_t)mod[i];
+    int64_t r = val % q;
+    if (r < 0) r += q;
+    for (u32 j = 1; j < sf_degree; j++) r = (int64_t)hm::mulmod((u64)r, (u64)(sf_deg_scalar % q), (u64)q);
+    res[i] = (u64)r;
+  }
+  if (log_approx > 0) {  // Scale_back_up_by_approxfactor (ckks_encoder.c:410-459)
+    int32_t log_step = (log_approx <= 60) ? log_approx : 60;  // MAX_LOG_STEP
+    std::vector<u64> approx(level);
+    int32_t left = log_approx;
+    for (u32 i = 0; i < level; i++) approx[i] = ((u64)1 << log_step) % mod[i];
+    left -= log_step;
+    while (left > 0) {
+      log_step = (left <= 60) ? left : 60;
+      for (u32 i = 0; i < level; i++)
+        approx[i] = hm::mulmod(approx[i], ((u64)1 << log_step) % mod[i], mod[i]);
+      left -= log_step;
+    }
+    for (u32 i = 0; i < level; i++) res[i] = hm::mulmod(res[i], approx[i], mod[i]);
+  }
+  ACE_CUDA(cudaStreamSynchronize(stream));
+  ACE_CUDA(cudaMemcpyAsync(enc_pow_, res.data(), level * sizeof(u64), cudaMemcpyHostToDevice,
+                           stream));
+  LimbBatch b = all_limbs(out, 0, level);
+  fill_limb_kernel<<<grid_for(N, level), 256, 0, stream>>>(T, b, enc_pow_);
+  launches++;
+}
+
+// ------------------------------------------------------------------------------ decode
+// Decode (ckks_encoder.c:649-703): INTT, exact CRT reconstruction (centred), truncating
+// conversion to double (mpz_get_d), divide by the scale, forward special FFT (Embedding).
+void Context::decode(double* out_re, double* out_im, const u64* pt, u32 level, u32 slots,
+                     double scale) {
+  init_encoder();
+  if (slots == 0) slots = N / 2;
+  std::vector<u64> h((size_t)level * N);
+  u64* coef = alloc_limbs(level, false);
+  intt_from(coef, pt, 0, level);
+  download(h.data(), coef, level);
+  free_limbs(coef);
+  const u32 half_n = N / 2, gap = half_n / slots;
+  // mixed-radix (Garner) digits give the exact integer x in [0, Q_level)
+  std::vector<u64> inv((size_t)level * level, 0);  // inv[j*level+i] = q_i^-1 mod q_j (i<j)
+  for (u32 j = 1; j < level; j++)
+    for (u32 i = 0; i < j; i++) inv[(size_t)j * level + i] = hm::invmod_prime(mod[i] % mod[j], mod[j]);
+  // big modulus and its half as little-endian limbs
+  auto mul_small = [](std::vector<u64>& a, u64 m) {
+    u64 carry = 0;
+    for (auto& w : a) { u128 t = (u128)w * m + carry; w = (u64)t; carry = (u64)(t >> 64); }
+    if (carry) a.push_back(carry);
+  };
+  std::vector<u64> bigM(1, 1);
+  for (u32 i = 0; i < level; i++) mul_small(bigM, mod[i]);
+  const size_t W = bigM.size() + 1;
+  bigM.resize(W, 0);
+  std::vector<u64> halfM(W, 0);
+  for (size_t k = 0; k < W; k++) halfM[k] = (bigM[k] >> 1) | (k + 1 < W ? bigM[k + 1] << 63 : 0);
+  auto cmp = [&](const std::vector<u64>& a, const std::vector<u64>& b) {
+    for (size_t k = W; k-- > 0;) {
+      if (a[k] != b[k]) return a[k] < b[k] ? -1 : 1;
+    }
+    return 0;
+  };
+  auto to_double_trunc = [&](const std::vector<u64>& a) {  // mpz_get_d: truncate toward zero
+    size_t top = W;
+    while (top > 0 && a[top - 1] == 0) top--;
+    if (top == 0) return 0.0;
+    int lz = __builtin_clzll(a[top - 1]);
+    size_t bits = top * 64 - lz;
+    if (bits <= 53) return (double)a[0];
+    size_t shift = bits - 53;  // keep the top 53 bits, drop the rest
+    u64 mant = 0;
+    size_t w = shift / 64, s = shift % 64;
+    mant = a[w] >> s;
+    if (s && w + 1 < W) mant |= a[w + 1] << (64 - s);
+    mant &= (((u64)1 << 53) - 1);
+    return ldexp((double)mant, (int)shift);
+  };
+  std::vector<std::complex<double>> msg(slots);
+  std::vector<u64> v(level), x(W), tmp(W);
+  for (u32 s = 0; s < 2 * slots; s++) {
+    const u32 n = (s < slots) ? s * gap : (s - slots) * gap + half_n;
+    for (u32 j = 0; j < level; j++) {
+      u64 qj = mod[j];
+      u64 t  = h[(size_t)j * N + n] % qj;
+      for (u32 i = 0; i < j; i++) {
+        u64 vi = v[i] % qj;
+        t = hm::mulmod(t >= vi ? t - vi : t + qj - vi, inv[(size_t)j * level + i], qj);
+      }
+      v[j] = t;
+    }
+    // x = v0 + q0 (v1 + q1 (v2 + ...))
+    std::fill(x.begin(), x.end(), 0);
+    for (u32 j = level; j-- > 0;) {
+      u64 carry = 0;
+      for (size_t k = 0; k < W; k++) {
+        u128 t = (u128)x[k] * mod[j] + carry;
+        x[k] = (u64)t; carry = (u64)(t >> 64);
+      }
+      u64 c = v[j];
+      for (size_t k = 0; k < W && c; k++) { u64 o = x[k]; x[k] += c; c = x[k] < o ? 1 : 0; }
+    }
+    double d;
+    if (cmp(x, halfM) > 0) {  // x - M, negative
+      u64 borrow = 0;
+      for (size_t k = 0; k < W; k++) {
+        u128 t = (u128)bigM[k] - x[k] - borrow;
+        tmp[k] = (u64)t; borrow = (t >> 64) ? 1 : 0;
+      }
+      d = -to_double_trunc(tmp);
+    } else {
+      d = to_double_trunc(x);
+    }
+    d /= scale;
+    if (s < slots) msg[s] = std::complex<double>(d, 0);
+    else msg[s - slots] = std::complex<double>(msg[s - slots].real(), d);
+  }
+  // Embedding (ntt.c:672-711)
+  const size_t M = 2 * (size_t)N;
+  u32 logslots = 0;
+  while ((1u << logslots) < slots) logslots++;
+  std::vector<std::complex<double>> r(slots);
+  for (u32 i = 0; i < slots; i++) r[hm::bit_reverse(i, logslots)] = msg[i];
+  for (u32 logm = 1; logm <= logslots; logm++) {
+    size_t idx_mod = (size_t)1 << (logm + 2), g = M / idx_mod, num = (size_t)1 << (logm - 1);
+    for (size_t j = 0; j < slots; j += ((size_t)1 << logm)) {
+      for (size_t i = 0; i < num; i++) {
+        auto w  = fft_rou_[(rot_group_[i] % idx_mod) * g];
+        auto b  = r[j + i + num];
+        // complex product exactly as gcc expands it: (ac - bd) + (ad + bc) i
+        std::complex<double> of(w.real() * b.real() - w.imag() * b.imag(),
+                                w.real() * b.imag() + w.imag() * b.real());
+        auto a  = r[j + i];
+        r[j + i]       = std::complex<double>(a.real() + of.real(), a.imag() + of.imag());
+        r[j + i + num] = std::complex<double>(a.real() - of.real(), a.imag() - of.imag());
+      }
+    }
+  }
+  for (u32 i = 0; i < slots; i++) {
+    out_re[i] = r[i].real();
+    if (out_im) out_im[i] = r[i].imag();
+  }
+}
+
+}  // namespace ace

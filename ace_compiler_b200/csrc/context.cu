@@ -171,6 +171,9 @@ Context::~Context() {
   for (auto& kv : rot_keys_) { cudaFree(kv.second.k0); cudaFree(kv.second.k1); }
   cudaFree(relin_key.k0);
   cudaFree(relin_key.k1);
+  cudaFree(sk_ntt); cudaFree(pk0); cudaFree(pk1);
+  cudaFree(enc_tw_); cudaFree(enc_buf_); cudaFree(enc_pow_);
+  if (enc_host_) cudaFreeHost(enc_host_);
   for (auto& kv : auto_orders_) cudaFree(kv.second);
   for (void* p : owned_) cudaFree(p);
   cudaStreamDestroy(stream);
@@ -289,9 +292,15 @@ void Context::fill_conv_desc(ConvDesc& d, const ModUpTab& t, const u64* x, u64* 
 // Decomp_modup (poly_eval.c:28-34): out = num_q + K limbs
 void Context::decomp_modup(u64* out, const u64* in, u32 num_q, u32 part) {
   const ModUpTab& t = modup_tab(num_q, part);
+  modup_from(out, in + (size_t)t.start * N, num_q, part);
+}
+
+// Mod_up (poly_eval.c:19-26): `digit` holds only the digit's own limbs (output of Decomp)
+void Context::modup_from(u64* out, const u64* digit, u32 num_q, u32 part) {
+  const ModUpTab& t = modup_tab(num_q, part);
   u64* coef = alloc_limbs(t.n_in, false);
-  copy_limbs(out + (size_t)t.start * N, in + (size_t)t.start * N, t.n_in, N, stream);
-  intt_from(coef, in + (size_t)t.start * N, t.start, t.n_in);
+  copy_limbs(out + (size_t)t.start * N, digit, t.n_in, N, stream);
+  intt_from(coef, digit, t.start, t.n_in);
   ConvDesc d;
   fill_conv_desc(d, t, coef, out);
   launch_base_conv(T, &d, 1, stream);

@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <complex>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -74,6 +75,12 @@ class Context {
 
   // ---- reference polynomial-level API (a5, a6, a8)
   void decomp_modup(u64* out, const u64* in, u32 num_q, u32 part);
+  void modup_from(u64* out, const u64* digit, u32 num_q, u32 part);
+  u32  digit_start(u32 part) const { return (u32)(part_size * part); }
+  u32  digit_len(u32 num_q, u32 part) const {
+    u32 beta = (u32)num_decomp(num_q), st = digit_start(part);
+    return part == beta - 1 ? num_q - st : (u32)part_size;
+  }
   void mod_down(u64* out, const u64* in, u32 num_q);
   void rescale(u64* out, const u64* in, u32 num_q);
 
@@ -93,6 +100,26 @@ class Context {
   void ct_rotate(u64* r0, u64* r1, const u64* c0, const u64* c1, u32 num_q, int32_t rot_idx);
   void ct_mul_relin(u64* r0, u64* r1, const u64* a0, const u64* a1, const u64* b0,
                     const u64* b1, u32 num_q);
+
+  // ---- client side (client.cu): keys, encryption, CKKS encode / decode
+  u64* sk_ntt = nullptr;  // [G][N] secret key, NTT form over Q then P
+  u64* pk0    = nullptr;  // [L][N]
+  u64* pk1    = nullptr;  // [L][N]
+  void keygen(u64 seed, const int32_t* rots, size_t n_rots);
+  void gen_secret_key(u64 seed);
+  void gen_public_key(u64 seed);
+  void gen_relin_key(u64 seed);
+  void gen_auto_key(u32 auto_idx, u64 seed);
+  void gen_switch_key(SwitchKey& key, const u64* new_key, const u64* old_key, u64 seed);
+  void import_secret_key(const u64* host_ntt_qp);
+  void import_public_key(const u64* host_pk0, const u64* host_pk1);
+  void encrypt(u64* c0, u64* c1, const u64* pt, u32 level, u64 seed);
+  void decrypt(u64* pt, const u64* c0, const u64* c1, u32 level);
+  void encode(u64* out, const double* vals, size_t len, u32 level, u32 slots, u32 sf_degree,
+              u32 p_cnt);
+  void encode_value(u64* out, double value, u32 level, u32 sf_degree);
+  void decode(double* out_re, double* out_im, const u64* pt, u32 level, u32 slots,
+              double scale);
 
   size_t launches = 0;  // kernels launched so far (bench.py reports the delta)
 
@@ -115,6 +142,15 @@ class Context {
   u64 *pinv_mod_q_, *pinv_mod_q_sh_;            // [L]
   // Rescale tables, row l (dropping q_l), column i < l
   u64 *qlinv_, *qlinv_sh_, *negqlinv_, *negqlinv_sh_;  // [L][L]
+
+  // encoder state
+  void  init_encoder();
+  void* enc_tw_   = nullptr;  // device: per-stage special-FFT twiddles
+  void* enc_buf_  = nullptr;  // device: N/2 complex doubles
+  u64*  enc_pow_  = nullptr;  // device: per-limb scalars
+  void* enc_host_ = nullptr;  // pinned staging buffer
+  std::vector<std::complex<double>> fft_rou_;
+  std::vector<u64>                  rot_group_;
 
   template <typename Tp>
   Tp* to_device(const std::vector<Tp>& v);

@@ -1,0 +1,843 @@
+// rt_shim.cu -- the reference's rt_ant function surface (include/rt_ant/rt_ant.h) implemented
+// on the B200 runtime.  One global context per process, like the reference's
+// `CKKS_CONTEXT* Context` (fhe-cmplr/rtlib/ant/src/rtlib/context.c:27).
+//
+// Reference behaviour mirrored (paths under fhe-cmplr/rtlib/):
+//   ant/src/rtlib/context.c:29-160, ant/src/rtlib/rtlib.c:41-87, common/src/io_lib.c,
+//   ant/src/ckks/cipher_eval.c:23-127,292-364, ant/include/util/ciphertext.h:179-325,
+//   ant/include/util/polynomial.h:54-77,335-347,425-438, ant/src/poly/poly_eval.c:11-49,
+//   ant/src/poly/poly_arith.c:14-56, ant/include/rtlib/key_gen.h:28-75,
+//   ant/src/ckks/plain_eval.c:19-80, common/src/pt_mgr.c, common/src/rt_stat.c:21-28
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <ctime>
+#include <map>
+#include <string>
+
+#include "../../include/rt_ant/rt_ant.h"
+#include "context.h"
+
+using namespace ace;
+
+#define API extern "C" __attribute__((visibility("default")))
+
+// callbacks of the emitted translation unit: weak, so the library also loads stand-alone
+extern "C" {
+__attribute__((weak)) CKKS_PARAMS*  Get_context_params(void);
+__attribute__((weak)) RT_DATA_INFO* Get_rt_data_info(void);
+__attribute__((weak)) DATA_SCHEME*  Get_encode_scheme(int idx);
+__attribute__((weak)) DATA_SCHEME*  Get_decode_scheme(int idx);
+__attribute__((weak)) bool          Main_graph(void);
+}
+
+struct SWITCH_KEY {
+  SwitchKey*  key;
+  POLYNOMIAL* pk0;  // [dnum] views into the device key
+  POLYNOMIAL* pk1;
+};
+
+namespace {
+
+Context*  g_ctx    = nullptr;
+MODULUS*  g_mod    = nullptr;  // [G] Q then P, contiguous like the reference's arrays
+int       g_device = 0;
+uint64_t  g_enc_seed = 1;
+std::map<std::string, CIPHERTEXT*> g_inputs, g_outputs;
+std::map<u32, SWITCH_KEY*>          g_swk;  // by automorphism index; 0 = relin key
+clock_t g_tm_stamp;
+
+[[noreturn]] void die(const char* msg) {
+  fprintf(stderr, "[ace_b200] fatal: %s\n", msg);
+  abort();  // FMT_ASSERT semantics (rtlib/include/common/error.h:23-29)
+}
+
+Context* ctx() {
+  if (!g_ctx) die("context not prepared (call Prepare_context first)");
+  return g_ctx;
+}
+
+inline u64*       U(int64_t* p) { return reinterpret_cast<u64*>(p); }
+inline const u64* U(const int64_t* p) { return reinterpret_cast<const u64*>(p); }
+
+template <typename F>
+void guard(F&& f) {
+  try {
+    f();
+  } catch (const std::exception& e) {
+    die(e.what());
+  }
+}
+
+std::string io_key(const char* name, size_t idx) { return std::string(name) + "#" + std::to_string(idx); }
+
+// Alloc_poly_data (polynomial.h:54-64): zero-filled limbs in HBM
+void alloc_poly_data(POLYNOMIAL* p, uint32_t degree, size_t nq, size_t np) {
+  p->_ring_degree      = degree;
+  p->_num_primes       = nq;
+  p->_num_primes_p     = np;
+  p->_num_alloc_primes = nq + np;
+  p->_is_ntt           = false;
+  guard([&] { p->_data = reinterpret_cast<int64_t*>(ctx()->alloc_limbs(nq + np, true)); });
+}
+
+void free_poly_data(POLYNOMIAL* p) {
+  if (p->_data) {
+    guard([&] { ctx()->free_limbs(U(p->_data)); });
+    p->_data = nullptr;
+  }
+  p->_num_alloc_primes = 0;
+}
+
+size_t poly_len(const POLYNOMIAL* p) { return (p->_num_primes + p->_num_primes_p) * (size_t)p->_ring_degree; }
+
+// Init_poly (polynomial.h:335-347): size like `poly`, contents zeroed
+void init_poly(POLYNOMIAL* res, const POLYNOMIAL* poly) {
+  if (res->_data == nullptr) {
+    alloc_poly_data(res, poly->_ring_degree, poly->_num_primes, poly->_num_primes_p);
+  } else if (res->_num_alloc_primes * (size_t)res->_ring_degree < poly_len(poly)) {
+    free_poly_data(res);
+    alloc_poly_data(res, poly->_ring_degree, poly->_num_primes, poly->_num_primes_p);
+  } else {
+    guard([&] {
+      ACE_CUDA(cudaMemsetAsync(res->_data, 0,
+                               res->_num_alloc_primes * (size_t)res->_ring_degree * 8,
+                               ctx()->stream));
+    });
+    res->_ring_degree  = poly->_ring_degree;
+    res->_num_primes   = poly->_num_primes;
+    res->_num_primes_p = poly->_num_primes_p;
+    res->_is_ntt       = false;
+  }
+}
+
+int64_t* p_coeffs(const POLYNOMIAL* p) {  // Get_p_coeffs (polynomial.h:214-217)
+  return p->_data + (p->_num_alloc_primes - p->_num_primes_p) * (size_t)p->_ring_degree;
+}
+
+void copy_polynomial(POLYNOMIAL* dst, const POLYNOMIAL* src) {  // polynomial.h:425-438
+  guard([&] {
+    Context* c = ctx();
+    ACE_CUDA(cudaMemcpyAsync(dst->_data, src->_data, dst->_num_primes * (size_t)c->N * 8,
+                             cudaMemcpyDeviceToDevice, c->stream));
+    if (src->_num_primes_p)
+      ACE_CUDA(cudaMemcpyAsync(p_coeffs(dst), p_coeffs(src), dst->_num_primes_p * (size_t)c->N * 8,
+                               cudaMemcpyDeviceToDevice, c->stream));
+  });
+  dst->_is_ntt = src->_is_ntt;
+}
+
+// Init_ciphertext_from_ciph (ciphertext.h:211-221)
+void init_ct_from_ct(CIPHERTEXT* res, CIPHERTEXT* ciph, double sf, uint32_t sf_degree) {
+  res->_scaling_factor = sf;
+  res->_sf_degree      = sf_degree;
+  res->_slots          = ciph->_slots;
+  if (res == ciph) return;
+  init_poly(&res->_c0_poly, &ciph->_c0_poly);
+  init_poly(&res->_c1_poly, &ciph->_c1_poly);
+}
+
+void set_level(CIPHERTEXT* c, size_t level) {
+  c->_c0_poly._num_primes = level;
+  c->_c1_poly._num_primes = level;
+}
+
+// Adjust_level with resize = false (ciphertext.h:283-319): the operand with fewer limbs
+CIPHERTEXT* lower_level(CIPHERTEXT* a, CIPHERTEXT* b) {
+  if (a->_c0_poly._data == nullptr) return b;
+  if (b->_c0_poly._data == nullptr) die("poly coeffs of input ciph is invalid");
+  return a->_c0_poly._num_primes > b->_c0_poly._num_primes ? b : a;
+}
+
+void init_cipher(CIPHERTEXT* res, CIPHERTEXT* ciph, double sc, uint32_t deg) {  // cipher_eval.c:23-30
+  init_ct_from_ct(res, ciph, sc, deg);
+  res->_c0_poly._is_ntt = res->_c1_poly._is_ntt = true;
+  set_level(res, ciph->_c0_poly._num_primes);
+}
+
+u32 mod_index(MODULUS* m) {
+  ptrdiff_t g = m - g_mod;
+  if (g < 0 || (size_t)g >= ctx()->G) die("MODULUS pointer does not belong to the context");
+  return (u32)g;
+}
+
+SWITCH_KEY* wrap_key(u32 slot, SwitchKey* k) {
+  auto it = g_swk.find(slot);
+  if (it != g_swk.end()) return it->second;
+  Context* c = ctx();
+  SWITCH_KEY* s = new SWITCH_KEY;
+  s->key = k;
+  s->pk0 = new POLYNOMIAL[c->dnum];
+  s->pk1 = new POLYNOMIAL[c->dnum];
+  for (size_t j = 0; j < c->dnum; j++) {
+    for (int w = 0; w < 2; w++) {
+      POLYNOMIAL* p = w ? &s->pk1[j] : &s->pk0[j];
+      p->_ring_degree = c->N; p->_num_primes = c->L; p->_num_primes_p = c->K;
+      p->_num_alloc_primes = c->G; p->_is_ntt = true;
+      p->_data = reinterpret_cast<int64_t*>((w ? k->k1 : k->k0) + j * c->G * (size_t)c->N);
+    }
+  }
+  g_swk[slot] = s;
+  return s;
+}
+
+// ---- weight file (DE_MSG_F32/F64): rt_data_def.h:90-109, pt_mgr.c:35-110 -----------------
+struct DataFileHdr {
+  char            magic[8];  // "!ANTFHE\0"
+  uint32_t        rt_ver;
+  uint16_t        flag;
+  uint8_t         ent_type;   // DATA_ENTRY_TYPE
+  uint8_t         ent_align;  // log2 of the entry alignment
+  uint64_t        ent_count;
+  uint64_t        lut_ofst;
+  struct timespec ctime;
+  char            model[48];
+  char            uuid[40];
+};
+struct LutEntry {
+  char     name[16];
+  uint32_t index;
+  uint32_t size;
+  uint64_t ent_ofst;
+};
+std::vector<char> g_wfile;
+const LutEntry*   g_lut   = nullptr;
+uint64_t          g_nent  = 0;
+uint32_t          g_etype = 0;
+
+}  // namespace
+
+// =========================================================================== context
+API void Ace_set_device(int device) { g_device = device; }
+API void* Ace_context(void) { return g_ctx; }
+
+API void Prepare_context(void) {
+  if (g_ctx) return;
+  if (!Get_context_params) die("Get_context_params() not linked (emitted unit missing)");
+  CKKS_PARAMS* p = Get_context_params();
+  size_t parts = p->_num_q_parts;
+  if (parts == 0) parts = p->_mul_depth > 3 ? 3 : (p->_mul_depth == 0 ? 1 : 2);  // fhe_std_parms.c:327-334
+  guard([&] {
+    Params prm{p->_poly_degree, p->_mul_depth, p->_first_mod_size, p->_scaling_mod_size, parts,
+               p->_hamming_weight};
+    g_ctx = new Context(prm, g_device);
+    g_mod = new MODULUS[g_ctx->G];
+    for (size_t g = 0; g < g_ctx->G; g++) {
+      g_mod[g]._val = (int64_t)g_ctx->mod[g];
+      g_mod[g]._br_k = g_mod[g]._br_m = 0;
+      g_mod[g]._prec128 = ~(unsigned __int128)0 / g_ctx->mod[g];
+    }
+    printf("ckks_param: _provider = %d, _poly_degree = %d, _sec_level = %ld, mul_depth = %ld, "
+           "_first_mod_size = %ld, _scaling_mod_size = %ld, _num_q_parts = %ld, _num_p = %ld, "
+           "_num_rot_idx = %ld,_hamming_wieght = %ld\n",
+           p->_provider, p->_poly_degree, p->_sec_level, p->_mul_depth, p->_first_mod_size,
+           p->_scaling_mod_size, parts, g_ctx->K, p->_num_rot_idx, p->_hamming_weight);
+    const char* no_keys = getenv("ACE_B200_NO_KEYGEN");  // parity runs import the oracle's keys
+    if (!(no_keys && no_keys[0] == '1')) {
+      const char* seed = getenv("ACE_B200_SEED");
+      g_ctx->keygen(seed ? strtoull(seed, nullptr, 10) : 20251017ull, p->_rot_idxs, p->_num_rot_idx);
+    }
+  });
+  if (Get_rt_data_info) {
+    RT_DATA_INFO* info = Get_rt_data_info();
+    if (info != nullptr) Pt_mgr_init(info->_file_name);
+  }
+}
+
+API void Finalize_context(void) {
+  if (!g_ctx) return;
+  for (auto& kv : g_swk) { delete[] kv.second->pk0; delete[] kv.second->pk1; delete kv.second; }
+  g_swk.clear();
+  Pt_mgr_fini();
+  delete g_ctx;
+  g_ctx = nullptr;
+  delete[] g_mod;
+  g_mod = nullptr;
+}
+
+API uint32_t Degree(void) { return ctx()->N; }
+API double   Get_default_sc(void) { return (double)((u64)1 << ctx()->params.scaling_mod_size); }
+API size_t   Get_q_parts(void) { return ctx()->dnum; }
+API size_t   Get_p_cnt(void) { return ctx()->K; }
+API MODULUS* Q_modulus(void) { ctx(); return g_mod; }
+API MODULUS* P_modulus(void) { return g_mod + ctx()->L; }
+
+// =========================================================================== tensors / IO
+API TENSOR* Alloc_tensor(size_t n, size_t c, size_t h, size_t w, const double* val) {
+  size_t  cnt = n * c * h * w;
+  TENSOR* t   = (TENSOR*)malloc(sizeof(TENSOR) + cnt * sizeof(double));
+  t->_shape = SHAPE{n, c, h, w};
+  if (val) memcpy(t->_vals, val, cnt * sizeof(double));
+  else memset(t->_vals, 0, cnt * sizeof(double));
+  return t;
+}
+API void Free_tensor(TENSOR* t) { free(t); }
+API void Print_tensor(FILE* fp, TENSOR* t) {
+  fprintf(fp, "\n[%zu %zu %zu %zu]: ", t->_shape._n, t->_shape._c, t->_shape._h, t->_shape._w);
+  size_t cnt = TENSOR_SIZE(t);
+  for (size_t i = 0; i < cnt && i < 16; i++) fprintf(fp, "%f ", t->_vals[i]);
+  fprintf(fp, "\n");
+}
+
+// Prepare_input (rtlib.c:41-54): encode at full level with default slots, then pk-encrypt
+API void Prepare_input(TENSOR* input, const char* name) {
+  Context* c = ctx();
+  size_t   len = TENSOR_SIZE(input);
+  CIPHERTEXT* ct = (CIPHERTEXT*)calloc(1, sizeof(CIPHERTEXT));
+  guard([&] {
+    u64* pt = c->alloc_limbs(c->L, false);
+    c->encode(pt, input->_vals, len, (u32)c->L, 0, 1, 0);
+    alloc_poly_data(&ct->_c0_poly, c->N, c->L, 0);
+    alloc_poly_data(&ct->_c1_poly, c->N, c->L, 0);
+    c->encrypt(U(ct->_c0_poly._data), U(ct->_c1_poly._data), pt, (u32)c->L, g_enc_seed++);
+    c->free_limbs(pt);
+  });
+  ct->_c0_poly._is_ntt = ct->_c1_poly._is_ntt = true;
+  ct->_slots          = c->N / 2;
+  ct->_scaling_factor = Get_default_sc();
+  ct->_sf_degree      = 1;
+  g_inputs[io_key(name, 0)] = ct;
+}
+
+API void Ace_set_input(const char* name, size_t idx, const int64_t* c0, const int64_t* c1,
+                       uint32_t level, uint32_t slots, double scale, uint32_t sf_degree) {
+  Context* c = ctx();
+  CIPHERTEXT* ct = (CIPHERTEXT*)calloc(1, sizeof(CIPHERTEXT));
+  alloc_poly_data(&ct->_c0_poly, c->N, level, 0);
+  alloc_poly_data(&ct->_c1_poly, c->N, level, 0);
+  guard([&] {
+    c->upload(U(ct->_c0_poly._data), U(c0), level);
+    c->upload(U(ct->_c1_poly._data), U(c1), level);
+    c->sync();
+  });
+  ct->_c0_poly._is_ntt = ct->_c1_poly._is_ntt = true;
+  ct->_slots = slots; ct->_scaling_factor = scale; ct->_sf_degree = sf_degree;
+  g_inputs[io_key(name, idx)] = ct;
+}
+
+API CIPHERTEXT Get_input_data(const char* name, size_t idx) {  // rtlib.c:74-80
+  auto it = g_inputs.find(io_key(name, idx));
+  if (it == g_inputs.end()) die("not find data");
+  CIPHERTEXT ret = *it->second;
+  free(it->second);
+  g_inputs.erase(it);
+  return ret;
+}
+
+API void Set_output_data(const char* name, size_t idx, CIPHER data) {  // rtlib.c:82-87
+  CIPHERTEXT* out = (CIPHERTEXT*)calloc(1, sizeof(CIPHERTEXT));
+  Copy_ciph(out, data);
+  Free_ciph_poly(data, 1);
+  auto key = io_key(name, idx);
+  auto it  = g_outputs.find(key);
+  if (it != g_outputs.end()) { Free_ciph_poly(it->second, 1); free(it->second); }
+  g_outputs[key] = out;
+}
+
+API CIPHER Ace_get_output(const char* name, size_t idx) {
+  auto it = g_outputs.find(io_key(name, idx));
+  return it == g_outputs.end() ? nullptr : it->second;
+}
+
+API double* Get_msg(CIPHER ciph) {  // cipher_eval.c:129-148 (non-extended ciphertexts)
+  Context* c = ctx();
+  u32 level = (u32)ciph->_c0_poly._num_primes, slots = ciph->_slots;
+  double* out = (double*)malloc(sizeof(double) * slots);
+  guard([&] {
+    u64* pt = c->alloc_limbs(level, false);
+    c->decrypt(pt, U(ciph->_c0_poly._data), U(ciph->_c1_poly._data), level);
+    c->decode(out, nullptr, pt, level, slots, ciph->_scaling_factor);
+    c->free_limbs(pt);
+  });
+  return out;
+}
+
+API double* Handle_output(const char* name) {  // rtlib.c:56-72
+  CIPHER ct = Ace_get_output(name, 0);
+  if (!ct) die("not find data");
+  double* r = Get_msg(ct);
+  Free_ciph_poly(ct, 1);
+  free(ct);
+  g_outputs.erase(io_key(name, 0));
+  return r;
+}
+
+API void Print_cipher_msg(FILE* fp, const char* name, CIPHER ciph, uint32_t len) {
+  double* d = Get_msg(ciph);
+  fprintf(fp, "\n[%s] ciph_info: %d %d %ld %ld\n[%s] msg: [ ", name, ciph->_sf_degree,
+          ciph->_slots, ciph->_c0_poly._num_primes, ciph->_c0_poly._num_primes_p, name);
+  for (uint32_t i = 0; i < len && i < ciph->_slots; i++) fprintf(fp, "%.17f ", d[i]);
+  fprintf(fp, "]\n");
+  free(d);
+}
+
+API void Run_main_graph(void) {  // common/src/rt_lib.c:16-20
+  if (!Main_graph) die("Main_graph() not linked");
+  if (!Main_graph()) die("Main_graph failed");
+  guard([&] { ctx()->sync(); });
+}
+
+API void Tm_start(const char* msg) {
+  (void)msg;
+  guard([&] { ctx()->sync(); });
+  g_tm_stamp = clock();
+}
+API void Tm_taken(const char* msg) {  // rt_stat.c:23-28; a stream sync makes it device-accurate
+  guard([&] { ctx()->sync(); });
+  clock_t cur = clock();
+  fprintf(stdout, "[RT_STAT] %s takes %.3f seconds.\n", msg,
+          ((double)(cur - g_tm_stamp)) / (double)CLOCKS_PER_SEC);
+  g_tm_stamp = cur;
+}
+
+// =========================================================================== polynomials
+API POLY Alloc_poly(uint32_t degree, size_t q_primes, bool extend_p) {  // poly_eval.h:29-37
+  if (q_primes == 0) die("Alloc_poly: q primes should not be NULL");
+  POLY p = (POLY)calloc(1, sizeof(POLYNOMIAL));
+  alloc_poly_data(p, degree, q_primes, extend_p ? ctx()->K : 0);
+  p->_is_ntt = true;
+  return p;
+}
+API void Free_poly_data(POLY poly) { free_poly_data(poly); }
+API void Free_poly(POLY poly) {
+  free_poly_data(poly);
+  free(poly);
+}
+API void Copy_poly(POLY res, POLY poly) { copy_polynomial(res, poly); }
+API void Set_coeffs(POLY dst, uint32_t level, uint32_t degree, int64_t* src) {  // poly_eval.h:74-79
+  guard([&] {
+    ACE_CUDA(cudaMemcpyAsync(dst->_data + (size_t)level * degree, src, sizeof(int64_t) * degree,
+                             cudaMemcpyDeviceToDevice, ctx()->stream));
+  });
+}
+API size_t Num_decomp(POLY poly) { return ctx()->num_decomp(poly->_num_primes); }
+
+API void Ace_download_poly(int64_t* host_dst, POLY poly) {
+  guard([&] { ctx()->download(U(host_dst), U(poly->_data), poly->_num_primes + poly->_num_primes_p); });
+}
+API void Ace_upload_poly(POLY poly, const int64_t* host_src) {
+  guard([&] {
+    ctx()->upload(U(poly->_data), U(host_src), poly->_num_primes + poly->_num_primes_p);
+    ctx()->sync();
+  });
+}
+
+API int64_t* Hw_modadd(int64_t* res, int64_t* a, int64_t* b, MODULUS* m, uint32_t degree) {
+  Context* c = ctx();
+  launch_ew(c->T, EW_ADD, U(res), U(a), U(b), mod_index(m), 1, c->stream);
+  c->launches++;
+  return res + degree;
+}
+API int64_t* Hw_modmul(int64_t* res, int64_t* a, int64_t* b, MODULUS* m, uint32_t degree) {
+  Context* c = ctx();
+  launch_ew(c->T, EW_MUL, U(res), U(a), U(b), mod_index(m), 1, c->stream);
+  c->launches++;
+  return res + degree;
+}
+API int64_t* Hw_rotate(int64_t* res, int64_t* a, int64_t* order, MODULUS* m, uint32_t degree) {
+  Context* c = ctx();
+  launch_gather(c->T, U(res), U(a), order, mod_index(m), 1, c->stream);
+  c->launches++;
+  return res + degree;
+}
+
+API POLY Decomp(POLY res, POLY poly, uint32_t part) {  // Decompose_poly, polynomial.c:848-875
+  Context* c = ctx();
+  u32 nq = (u32)poly->_num_primes, len = c->digit_len(nq, part), st = c->digit_start(part);
+  if (res->_num_alloc_primes < len) {
+    free_poly_data(res);
+    alloc_poly_data(res, poly->_ring_degree, len, 0);
+  } else {
+    res->_num_primes = len;
+    res->_num_primes_p = 0;
+  }
+  guard([&] {
+    ACE_CUDA(cudaMemcpyAsync(res->_data, poly->_data + (size_t)st * c->N, (size_t)len * c->N * 8,
+                             cudaMemcpyDeviceToDevice, c->stream));
+  });
+  res->_is_ntt = poly->_is_ntt;
+  return res;
+}
+API POLY Mod_up(POLY new_poly, POLY old_poly, uint32_t part) {  // poly_eval.c:19-26
+  guard([&] { ctx()->modup_from(U(new_poly->_data), U(old_poly->_data), (u32)new_poly->_num_primes, part); });
+  new_poly->_is_ntt = old_poly->_is_ntt;
+  return new_poly;
+}
+API POLY Decomp_modup(POLY res, POLY poly, uint32_t part) {  // poly_eval.c:28-34
+  guard([&] { ctx()->decomp_modup(U(res->_data), U(poly->_data), (u32)poly->_num_primes, part); });
+  res->_is_ntt = true;
+  return res;
+}
+API POLY Mod_down(POLY res, POLY poly) {  // poly_eval.c:36-41
+  guard([&] { ctx()->mod_down(U(res->_data), U(poly->_data), (u32)res->_num_primes); });
+  res->_is_ntt = poly->_is_ntt;
+  return res;
+}
+API POLY Rescale(POLY res, POLY poly) {  // poly_eval.c:43-49
+  guard([&] { ctx()->rescale(U(res->_data), U(poly->_data), (u32)poly->_num_primes); });
+  res->_is_ntt     = true;
+  res->_num_primes = res->_num_primes - 1;  // Mod_down_q_primes
+  return res;
+}
+
+// =========================================================================== keys
+API uint32_t Auto_idx(int32_t rot_idx) { return ctx()->auto_index(rot_idx); }
+API int64_t* Auto_order(int32_t rot_idx) {
+  int64_t* r = nullptr;
+  guard([&] { r = const_cast<int64_t*>(ctx()->auto_order(ctx()->auto_index(rot_idx))); });
+  return r;
+}
+API SW_KEY Swk(bool is_rot, int32_t rot_idx) {
+  Context* c = ctx();
+  if (!is_rot) {
+    if (!c->relin_key.k0) die("relinearisation key missing");
+    return wrap_key(0, &c->relin_key);
+  }
+  u32 k = c->auto_index(rot_idx);
+  if (!c->has_rot_key(k)) die("cannot find auto key");
+  return wrap_key(k, &c->rot_key(k));
+}
+API POLY Pk0_at(SW_KEY swk, uint32_t idx) { return &swk->pk0[idx]; }
+API POLY Pk1_at(SW_KEY swk, uint32_t idx) { return &swk->pk1[idx]; }
+
+API void Ace_import_switch_key(bool is_rot, int32_t rot_idx, uint32_t part, int which,
+                               const int64_t* host_poly) {
+  guard([&] {
+    Context* c = ctx();
+    SwitchKey& k = is_rot ? c->rot_key(c->auto_index(rot_idx)) : c->relin_key;
+    c->import_key_limbs(k, part, which, U(host_poly));
+  });
+}
+
+// =========================================================================== ciphertexts
+API void Init_ciph_same_scale(CIPHER res, CIPHER c1, CIPHER c2) {  // cipher_eval.c:32-43
+  CIPHER ciph = c2 != nullptr ? lower_level(c1, c2) : c1;
+  res->_scaling_factor = ciph->_scaling_factor;
+  res->_sf_degree      = ciph->_sf_degree;
+  res->_slots          = ciph->_slots;
+  size_t level = ciph->_c0_poly._num_primes, np = ciph->_c0_poly._num_primes_p;
+  if (res->_c0_poly._data == nullptr) alloc_poly_data(&res->_c0_poly, ciph->_c0_poly._ring_degree, level, np);
+  if (res->_c1_poly._data == nullptr) alloc_poly_data(&res->_c1_poly, ciph->_c0_poly._ring_degree, level, np);
+  res->_c0_poly._is_ntt = res->_c1_poly._is_ntt = true;
+}
+API void Init_ciph_same_scale_plain(CIPHER res, CIPHER ciph, PLAIN plain) {
+  (void)plain;
+  init_cipher(res, ciph, ciph->_scaling_factor, ciph->_sf_degree);
+}
+API void Init_ciph_up_scale(CIPHER res, CIPHER c1, CIPHER c2) {
+  CIPHER ciph = lower_level(c1, c2);
+  init_cipher(res, ciph, c1->_scaling_factor * c2->_scaling_factor, c1->_sf_degree + c2->_sf_degree);
+}
+API void Init_ciph_up_scale_plain(CIPHER res, CIPHER ciph, PLAIN plain) {
+  init_cipher(res, ciph, ciph->_scaling_factor * plain->_scaling_factor,
+              ciph->_sf_degree + plain->_sf_degree);
+}
+API void Init_ciph_down_scale(CIPHER res, CIPHER ciph) {
+  init_cipher(res, ciph, ciph->_scaling_factor / Get_default_sc(), ciph->_sf_degree - 1);
+}
+API void Init_ciph_same_scale_ciph3(CIPHER res, CIPHER3 ciph) {  // cipher_eval.c:65-75
+  res->_scaling_factor = ciph->_scaling_factor;
+  res->_sf_degree      = ciph->_sf_degree;
+  res->_slots          = ciph->_slots;
+  init_poly(&res->_c0_poly, &ciph->_c0_poly);
+  init_poly(&res->_c1_poly, &ciph->_c1_poly);
+  res->_c0_poly._is_ntt = res->_c1_poly._is_ntt = true;
+  set_level(res, ciph->_c0_poly._num_primes);
+}
+static void init_ct3(CIPHER3 res, POLYNOMIAL* like, double sf, uint32_t deg, uint32_t slots) {
+  res->_scaling_factor = sf;
+  res->_sf_degree      = deg;
+  res->_slots          = slots;
+  init_poly(&res->_c0_poly, like);
+  init_poly(&res->_c1_poly, like);
+  init_poly(&res->_c2_poly, like);
+  res->_c0_poly._is_ntt = res->_c1_poly._is_ntt = res->_c2_poly._is_ntt = true;
+  res->_c0_poly._num_primes = res->_c1_poly._num_primes = res->_c2_poly._num_primes = like->_num_primes;
+}
+API void Init_ciph3_same_scale_ciph3(CIPHER3 res, CIPHER3 c1, CIPHER3 c2) {
+  CIPHER3 ciph = c1;
+  if (c2 != nullptr && c1->_c0_poly._data != nullptr &&
+      c1->_c0_poly._num_primes > c2->_c0_poly._num_primes) ciph = c2;
+  if (c2 != nullptr && c1->_c0_poly._data == nullptr) ciph = c2;
+  if (res == ciph) return;
+  init_ct3(res, &ciph->_c0_poly, ciph->_scaling_factor, ciph->_sf_degree, ciph->_slots);
+}
+API void Init_ciph3_up_scale(CIPHER3 res, CIPHER c1, CIPHER c2) {  // cipher_eval.c:93-107
+  CIPHER ciph = lower_level(c1, c2);
+  init_ct3(res, &ciph->_c0_poly, c1->_scaling_factor * c2->_scaling_factor,
+           c1->_sf_degree + c2->_sf_degree, ciph->_slots);
+}
+API void Copy_ciph(CIPHER res, CIPHER ciph) {  // ciphertext.h:236-241
+  init_ct_from_ct(res, ciph, ciph->_scaling_factor, ciph->_sf_degree);
+  if (res == ciph) return;
+  copy_polynomial(&res->_c0_poly, &ciph->_c0_poly);
+  copy_polynomial(&res->_c1_poly, &ciph->_c1_poly);
+}
+API void Zero_ciph(CIPHER ciph) {
+  free_poly_data(&ciph->_c0_poly);
+  free_poly_data(&ciph->_c1_poly);
+  memset(ciph, 0, sizeof(*ciph));
+}
+API void Free_ciph_poly(CIPHER ciph, uint32_t cnt) {
+  for (uint32_t i = 0; i < cnt; i++) {
+    free_poly_data(&ciph[i]._c0_poly);
+    free_poly_data(&ciph[i]._c1_poly);
+  }
+}
+API size_t   Level(CIPHER ciph) { return ciph->_c0_poly._num_primes; }
+API uint32_t Sc_degree(CIPHER ciph) { return ciph->_sf_degree; }
+API uint32_t Get_slots(CIPHER ciph) { return ciph->_slots; }
+API void     Set_slots(CIPHER ciph, uint32_t slots) { ciph->_slots = slots; }
+
+// ---- CKKS-level API (cipher_eval.c:292-364 -> ckks_evaluator.c), non-extended ciphertexts
+static void ct_binary(EwOp op, CIPHER res, CIPHER a, CIPHER b) {
+  CIPHER low = lower_level(a, b);
+  u32 level = (u32)low->_c0_poly._num_primes;
+  if (res != a && res != b) init_ct_from_ct(res, low, low->_scaling_factor, low->_sf_degree);
+  Context* c = ctx();
+  launch_ew(c->T, op, U(res->_c0_poly._data), U(a->_c0_poly._data), U(b->_c0_poly._data), 0, level, c->stream);
+  launch_ew(c->T, op, U(res->_c1_poly._data), U(a->_c1_poly._data), U(b->_c1_poly._data), 0, level, c->stream);
+  c->launches += 2;
+  set_level(res, level);
+  res->_c0_poly._is_ntt = res->_c1_poly._is_ntt = true;
+}
+API CIPHER Add_ciph(CIPHER res, CIPHER a, CIPHER b) { ct_binary(EW_ADD, res, a, b); return res; }
+API CIPHER Sub_ciph(CIPHER res, CIPHER a, CIPHER b) { ct_binary(EW_SUB, res, a, b); return res; }
+
+API CIPHER Add_plain(CIPHER res, CIPHER ciph, PLAIN plain) {  // ckks_evaluator.c:103-118
+  init_ct_from_ct(res, ciph, ciph->_scaling_factor, ciph->_sf_degree);
+  Context* c = ctx();
+  u32 level = (u32)ciph->_c0_poly._num_primes;
+  launch_ew(c->T, EW_ADD, U(res->_c0_poly._data), U(ciph->_c0_poly._data), U(plain->_poly._data), 0, level, c->stream);
+  if (res != ciph) copy_polynomial(&res->_c1_poly, &ciph->_c1_poly);
+  res->_c0_poly._is_ntt = true;
+  c->launches++;
+  return res;
+}
+
+API CIPHER Mul_plain(CIPHER res, CIPHER ciph, PLAIN plain) {  // ckks_evaluator.c:181-206
+  double sf = ciph->_scaling_factor * plain->_scaling_factor;
+  uint32_t deg = ciph->_sf_degree + plain->_sf_degree;
+  init_ct_from_ct(res, ciph, sf, deg);
+  Context* c = ctx();
+  u32 level = (u32)ciph->_c0_poly._num_primes;
+  launch_ew(c->T, EW_MUL, U(res->_c0_poly._data), U(ciph->_c0_poly._data), U(plain->_poly._data), 0, level, c->stream);
+  launch_ew(c->T, EW_MUL, U(res->_c1_poly._data), U(ciph->_c1_poly._data), U(plain->_poly._data), 0, level, c->stream);
+  res->_c0_poly._is_ntt = res->_c1_poly._is_ntt = true;
+  c->launches += 2;
+  return res;
+}
+
+API CIPHER3 Mul_ciph3(CIPHER3 res, CIPHER a, CIPHER b) {  // ckks_evaluator.c:133-165
+  CIPHER low = lower_level(a, b);
+  u32 level = (u32)low->_c0_poly._num_primes;
+  POLYNOMIAL like = low->_c0_poly;
+  init_ct3(res, &like, a->_scaling_factor * b->_scaling_factor, a->_sf_degree + b->_sf_degree, low->_slots);
+  Context* c = ctx();
+  guard([&] {
+    u64* t = c->alloc_limbs(level, false);
+    launch_ew(c->T, EW_MUL, U(res->_c0_poly._data), U(a->_c0_poly._data), U(b->_c0_poly._data), 0, level, c->stream);
+    launch_ew(c->T, EW_MUL, U(res->_c1_poly._data), U(a->_c0_poly._data), U(b->_c1_poly._data), 0, level, c->stream);
+    launch_ew(c->T, EW_MUL, t, U(a->_c1_poly._data), U(b->_c0_poly._data), 0, level, c->stream);
+    launch_ew(c->T, EW_ADD, U(res->_c1_poly._data), U(res->_c1_poly._data), t, 0, level, c->stream);
+    launch_ew(c->T, EW_MUL, U(res->_c2_poly._data), U(a->_c1_poly._data), U(b->_c1_poly._data), 0, level, c->stream);
+    c->free_limbs(t);
+    c->launches += 5;
+  });
+  return res;
+}
+
+API CIPHER Relin(CIPHER res, CIPHER3 ciph) {  // ckks_evaluator.c:266-282
+  Context* c = ctx();
+  u32 level = (u32)ciph->_c2_poly._num_primes;
+  res->_scaling_factor = ciph->_scaling_factor;
+  res->_sf_degree      = ciph->_sf_degree;
+  res->_slots          = ciph->_slots;
+  init_poly(&res->_c0_poly, &ciph->_c2_poly);
+  init_poly(&res->_c1_poly, &ciph->_c2_poly);
+  guard([&] {
+    u64* t = c->alloc_limbs(2 * (size_t)level, false);
+    c->key_switch(t, t + (size_t)level * c->N, U(ciph->_c2_poly._data), level, c->relin_key, nullptr);
+    launch_ew(c->T, EW_ADD, U(res->_c0_poly._data), t, U(ciph->_c0_poly._data), 0, level, c->stream);
+    launch_ew(c->T, EW_ADD, U(res->_c1_poly._data), t + (size_t)level * c->N, U(ciph->_c1_poly._data), 0, level, c->stream);
+    c->free_limbs(t);
+    c->launches += 2;
+  });
+  res->_c0_poly._is_ntt = res->_c1_poly._is_ntt = true;
+  return res;
+}
+
+API CIPHER Mul_ciph(CIPHER res, CIPHER a, CIPHER b) {  // ckks_evaluator.c:167-179
+  CIPHER low = lower_level(a, b);
+  u32 level = (u32)low->_c0_poly._num_primes;
+  double sf = a->_scaling_factor * b->_scaling_factor;
+  uint32_t deg = a->_sf_degree + b->_sf_degree, slots = low->_slots;
+  Context* c = ctx();
+  CIPHERTEXT tmp;
+  memset(&tmp, 0, sizeof(tmp));
+  alloc_poly_data(&tmp._c0_poly, c->N, level, 0);
+  alloc_poly_data(&tmp._c1_poly, c->N, level, 0);
+  guard([&] {
+    c->ct_mul_relin(U(tmp._c0_poly._data), U(tmp._c1_poly._data), U(a->_c0_poly._data),
+                    U(a->_c1_poly._data), U(b->_c0_poly._data), U(b->_c1_poly._data), level);
+  });
+  free_poly_data(&res->_c0_poly);
+  free_poly_data(&res->_c1_poly);
+  res->_c0_poly = tmp._c0_poly;
+  res->_c1_poly = tmp._c1_poly;
+  res->_c0_poly._is_ntt = res->_c1_poly._is_ntt = true;
+  res->_scaling_factor = sf; res->_sf_degree = deg; res->_slots = slots;
+  return res;
+}
+
+API CIPHER Rescale_ciph(CIPHER res, CIPHER ciph) {  // ckks_evaluator.c:324-343
+  Context* c = ctx();
+  u32 level = (u32)ciph->_c0_poly._num_primes;
+  if (level < 2) die("rescale: multiply level is not big enough");
+  double sf = ciph->_scaling_factor / Get_default_sc();
+  uint32_t deg = ciph->_sf_degree - 1, slots = ciph->_slots;
+  CIPHERTEXT tmp;
+  memset(&tmp, 0, sizeof(tmp));
+  alloc_poly_data(&tmp._c0_poly, c->N, level, 0);
+  alloc_poly_data(&tmp._c1_poly, c->N, level, 0);
+  guard([&] {
+    c->rescale(U(tmp._c0_poly._data), U(ciph->_c0_poly._data), level);
+    c->rescale(U(tmp._c1_poly._data), U(ciph->_c1_poly._data), level);
+  });
+  if (res != ciph) { free_poly_data(&res->_c0_poly); free_poly_data(&res->_c1_poly); }
+  else { free_poly_data(&ciph->_c0_poly); free_poly_data(&ciph->_c1_poly); }
+  res->_c0_poly = tmp._c0_poly;
+  res->_c1_poly = tmp._c1_poly;
+  set_level(res, level - 1);
+  res->_c0_poly._is_ntt = res->_c1_poly._is_ntt = true;
+  res->_scaling_factor = sf; res->_sf_degree = deg; res->_slots = slots;
+  return res;
+}
+
+API CIPHER Rotate_ciph(CIPHER res, CIPHER ciph, int32_t rotation) {  // cipher_eval.c:353-364
+  Context* c = ctx();
+  u32 level = (u32)ciph->_c0_poly._num_primes;
+  CIPHERTEXT tmp;
+  memset(&tmp, 0, sizeof(tmp));
+  alloc_poly_data(&tmp._c0_poly, c->N, level, 0);
+  alloc_poly_data(&tmp._c1_poly, c->N, level, 0);
+  guard([&] {
+    c->ct_rotate(U(tmp._c0_poly._data), U(tmp._c1_poly._data), U(ciph->_c0_poly._data),
+                 U(ciph->_c1_poly._data), level, rotation);
+  });
+  double sf = ciph->_scaling_factor;
+  uint32_t deg = ciph->_sf_degree, slots = ciph->_slots;
+  free_poly_data(&res->_c0_poly);
+  free_poly_data(&res->_c1_poly);
+  res->_c0_poly = tmp._c0_poly;
+  res->_c1_poly = tmp._c1_poly;
+  res->_c0_poly._is_ntt = res->_c1_poly._is_ntt = true;
+  res->_scaling_factor = sf; res->_sf_degree = deg; res->_slots = slots;
+  return res;
+}
+
+API CIPHER Encrypt(CIPHER res, PLAIN plain) {  // cipher_eval.c:406-409
+  Context* c = ctx();
+  u32 level = (u32)plain->_poly._num_primes;
+  res->_scaling_factor = plain->_scaling_factor;
+  res->_sf_degree      = plain->_sf_degree;
+  res->_slots          = plain->_slots;
+  init_poly(&res->_c0_poly, &plain->_poly);
+  init_poly(&res->_c1_poly, &plain->_poly);
+  guard([&] { c->encrypt(U(res->_c0_poly._data), U(res->_c1_poly._data), U(plain->_poly._data), level, g_enc_seed++); });
+  res->_c0_poly._is_ntt = res->_c1_poly._is_ntt = true;
+  return res;
+}
+
+API CIPHER Bootstrap(CIPHER res, CIPHER ciph, uint32_t level_after_bts) {
+  (void)res; (void)ciph; (void)level_after_bts;
+  die("Bootstrap is not implemented in this round of the B200 runtime");
+}
+
+// =========================================================================== plaintexts
+static void init_plain(PLAIN plain, uint32_t slots, size_t level, double sf, uint32_t deg) {
+  Context* c = ctx();
+  plain->_scaling_factor = sf;
+  plain->_sf_degree      = deg;
+  plain->_slots          = slots;
+  if (plain->_poly._data == nullptr || plain->_poly._num_primes != level ||
+      plain->_poly._num_primes_p != 0) {
+    free_poly_data(&plain->_poly);
+    alloc_poly_data(&plain->_poly, c->N, level, 0);
+  }
+  plain->_poly._is_ntt = true;
+}
+
+static void encode_plain(PLAIN plain, const double* vals, size_t len, uint32_t sc_degree,
+                         uint32_t level) {
+  Context* c = ctx();
+  if (level == 0) level = (uint32_t)c->L;
+  double sf = Get_default_sc();
+  if (len == 1) {  // plain_eval.c:28-34: constant fast path
+    init_plain(plain, c->N / 2, level, pow(sf, sc_degree), sc_degree);
+    guard([&] { c->encode_value(U(plain->_poly._data), vals[0], level, sc_degree); });
+    return;
+  }
+  init_plain(plain, c->N / 2, level, pow(sf, sc_degree), sc_degree);
+  guard([&] { c->encode(U(plain->_poly._data), vals, len, level, 0, sc_degree, 0); });
+}
+
+API void Encode_plain_from_float(PLAIN plain, float* input, size_t len, uint32_t sc_degree,
+                                 uint32_t level) {
+  std::vector<double> v(len);
+  for (size_t i = 0; i < len; i++) v[i] = (double)input[i];
+  encode_plain(plain, v.data(), len, sc_degree, level);
+}
+API void Encode_plain_from_double(PLAIN plain, double* input, size_t len, uint32_t sc_degree,
+                                  uint32_t level) {
+  encode_plain(plain, input, len, sc_degree, level);
+}
+API void Free_plain_poly(PLAIN plain) { free_poly_data(&plain->_poly); }
+
+API bool Pt_mgr_init(const char* fname) {  // pt_mgr.c:35-110 (message files only)
+  const char* override_path = getenv("ACE_B200_DATA_FILE");
+  if (override_path && override_path[0]) fname = override_path;
+  int fd = open(fname, O_RDONLY);
+  if (fd < 0) {
+    fprintf(stderr, "[ace_b200] cannot open weight data file %s\n", fname);
+    die("weight data file missing");
+  }
+  struct stat st;
+  fstat(fd, &st);
+  g_wfile.resize(st.st_size);
+  size_t got = 0;
+  while (got < (size_t)st.st_size) {
+    ssize_t r = pread(fd, g_wfile.data() + got, st.st_size - got, got);
+    if (r <= 0) die("short read on weight data file");
+    got += r;
+  }
+  close(fd);
+  const DataFileHdr* h = reinterpret_cast<const DataFileHdr*>(g_wfile.data());
+  if (memcmp(h->magic, "!ANTFHE", 7) != 0) die("bad weight data file magic");
+  g_etype = h->ent_type;
+  g_nent  = h->ent_count;
+  g_lut   = reinterpret_cast<const LutEntry*>(g_wfile.data() + h->lut_ofst);
+  if (g_etype != DE_MSG_F32 && g_etype != DE_MSG_F64) die("only message data files are supported");
+  return true;
+}
+API void Pt_mgr_fini(void) {
+  g_wfile.clear();
+  g_wfile.shrink_to_fit();
+  g_lut = nullptr;
+  g_nent = 0;
+}
+// Pt_from_msg (pt_mgr.c:182-191): look the message up and encode it at run time
+API void Pt_from_msg(void* pt, uint32_t index, size_t len, uint32_t scale, uint32_t level) {
+  if (!g_lut || index >= g_nent) die("Pt_from_msg: index out of range");
+  const LutEntry& e = g_lut[index];
+  const char* data = g_wfile.data() + e.ent_ofst;
+  if (g_etype == DE_MSG_F32) {
+    Encode_plain_from_float((PLAIN)pt, (float*)data, len, scale, level);
+  } else {
+    Encode_plain_from_double((PLAIN)pt, (double*)data, len, scale, level);
+  }
+}

@@ -1,0 +1,2 @@
+/* forwards to the single B200 rt_ant header (reference: fhe-cmplr/rtlib/include/common/rt_api.h) */
+#include "rt_ant/rt_ant.h"

@@ -1,0 +1,2 @@
+/* forwards to the single B200 rt_ant header (reference: fhe-cmplr/rtlib/include/rt_ant/ant_api.h) */
+#include "rt_ant/rt_ant.h"

@@ -1,0 +1,41 @@
+"""Compiles ACE-emitted C (the checked-in example programs under
+/root/reference/fhe-cmplr/rtlib/ant/example, used UNMODIFIED, where they lie) against OUR
+header tree (include/) and libace_b200.so.  This is the drop-in check of the boundary: the
+same translation units the reference links against libFHErt_ant.a.
+Binaries go to tests/_emitted_bin/ (git-ignored, shipped to the GPU box by gpurun).
+Run in the container that has /root/reference; a no-op elsewhere."""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_EX = "/root/reference/fhe-cmplr/rtlib/ant/example"
+OUT = os.path.join(ROOT, "tests", "_emitted_bin")
+EXAMPLES = ["add", "add_const", "mul_const", "rotate", "rotate_02", "relin", "relin_02",
+            "gemm", "gemm_02", "conv2d", "avg_pool", "relu"]
+
+
+def build_all(verbose=False):
+    if not os.path.isdir(REF_EX):
+        return []
+    os.makedirs(OUT, exist_ok=True)
+    built = []
+    for name in EXAMPLES:
+        src = os.path.join(REF_EX, "eg_fhertlib_%s.c" % name)
+        exe = os.path.join(OUT, "eg_" + name)
+        cmd = ["gcc", "-O2", "-w", "-std=gnu11", "-I", os.path.join(ROOT, "include"), "-I", REF_EX,
+               src, "-o", exe, "-L", os.path.join(ROOT, "ace_compiler_b200"), "-lace_b200",
+               "-Wl,-rpath,$ORIGIN/../../ace_compiler_b200", "-lm"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            print("FAILED", name, r.stderr[:2000])
+        else:
+            built.append(exe)
+            if verbose:
+                print("built", exe)
+    return built
+
+
+if __name__ == "__main__":
+    b = build_all(verbose=True)
+    print(len(b), "of", len(EXAMPLES), "example programs built")
