@@ -54,6 +54,14 @@ SIGNATURES = {
     "ace_ct_rotate": (C.c_int, [vp, vp, vp, vp, vp, u32, i32]),
     "ace_ct_mul_relin": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, u32]),
     "ace_ct_rescale": (C.c_int, [vp, vp, vp, vp, vp, u32]),
+    "ace_keygen": (C.c_int, [vp, C.c_uint64, vp, sz]),
+    "ace_sk_import": (C.c_int, [vp, vp]),
+    "ace_pk_import": (C.c_int, [vp, vp, vp]),
+    "ace_encode": (C.c_int, [vp, vp, vp, sz, u32, u32, u32, u32]),
+    "ace_encode_value": (C.c_int, [vp, vp, C.c_double, u32, u32]),
+    "ace_encrypt": (C.c_int, [vp, vp, vp, vp, u32, C.c_uint64]),
+    "ace_decrypt": (C.c_int, [vp, vp, vp, vp, u32]),
+    "ace_decode": (C.c_int, [vp, vp, vp, vp, u32, u32, C.c_double]),
     "ace_timer_start": (C.c_int, [vp]),
     "ace_timer_stop_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
 }
@@ -247,3 +255,42 @@ class Context:
         d0, d1, r0, r1 = self.put(c0), self.put(c1), self.empty(nq - 1), self.empty(nq - 1)
         self._ck(self.lib.ace_ct_rescale(self.h, r0.ptr, r1.ptr, d0.ptr, d1.ptr, nq))
         return r0.get(), r1.get()
+
+    # ---- client side
+    def keygen(self, seed, rots):
+        r = (i32 * max(1, len(rots)))(*rots)
+        self._ck(self.lib.ace_keygen(self.h, seed, r, len(rots)))
+
+    def import_secret_key(self, sk):
+        sk = np.ascontiguousarray(sk, dtype=np.int64)
+        self._ck(self.lib.ace_sk_import(self.h, _hp(sk)))
+
+    def encode(self, vals, level, slots=0, sf_degree=1, p_cnt=0):
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        out = self.empty((level or self.L) + p_cnt)
+        self._ck(self.lib.ace_encode(self.h, out.ptr, _hp(vals), len(vals), level, slots,
+                                     sf_degree, p_cnt))
+        return out
+
+    def encode_value(self, value, level, sf_degree=1):
+        out = self.empty(level or self.L)
+        self._ck(self.lib.ace_encode_value(self.h, out.ptr, float(value), level, sf_degree))
+        return out
+
+    def encrypt(self, pt, level, seed=1):
+        c = self.empty(2 * level)
+        self._ck(self.lib.ace_encrypt(self.h, c.ptr, c.ptr + level * self.N * 8, pt.ptr, level,
+                                      seed))
+        return c
+
+    def decrypt_decode(self, c0, c1, level, slots, scale):
+        """c0/c1: device pointers; returns the decoded real parts (host)"""
+        pt = self.empty(level)
+        self._ck(self.lib.ace_decrypt(self.h, pt.ptr, c0, c1, level))
+        return self.decode(pt, level, slots, scale)
+
+    def decode(self, pt, level, slots, scale):
+        re = np.zeros(slots, np.float64)
+        im = np.zeros(slots, np.float64)
+        self._ck(self.lib.ace_decode(self.h, _hp(re), _hp(im), pt.ptr, level, slots, scale))
+        return re + 1j * im

@@ -194,6 +194,34 @@ int ace_ct_rescale(ace_ctx* ctx, int64_t* r0, int64_t* r1, const int64_t* c0, co
           ctx->c->rescale(U(r1), U(c1), num_q))
 }
 
+int ace_keygen(ace_ctx* ctx, uint64_t seed, const int32_t* rots, size_t n) {
+  ACE_TRY(ctx->c->keygen(seed, rots, n))
+}
+int ace_sk_import(ace_ctx* ctx, const int64_t* sk) { ACE_TRY(ctx->c->import_secret_key(U(sk))) }
+int ace_pk_import(ace_ctx* ctx, const int64_t* p0, const int64_t* p1) {
+  ACE_TRY(ctx->c->import_public_key(U(p0), U(p1)))
+}
+int ace_encode(ace_ctx* ctx, int64_t* out, const double* vals, size_t len, uint32_t level,
+               uint32_t slots, uint32_t sf_degree, uint32_t p_cnt) {
+  ACE_TRY(ctx->c->encode(U(out), vals, len, level, slots, sf_degree, p_cnt))
+}
+int ace_encode_value(ace_ctx* ctx, int64_t* out, double value, uint32_t level,
+                     uint32_t sf_degree) {
+  ACE_TRY(ctx->c->encode_value(U(out), value, level, sf_degree))
+}
+int ace_encrypt(ace_ctx* ctx, int64_t* c0, int64_t* c1, const int64_t* pt, uint32_t level,
+                uint64_t seed) {
+  ACE_TRY(check_level(ctx->c, level); ctx->c->encrypt(U(c0), U(c1), U(pt), level, seed))
+}
+int ace_decrypt(ace_ctx* ctx, int64_t* pt, const int64_t* c0, const int64_t* c1,
+                uint32_t level) {
+  ACE_TRY(check_level(ctx->c, level); ctx->c->decrypt(U(pt), U(c0), U(c1), level))
+}
+int ace_decode(ace_ctx* ctx, double* re, double* im, const int64_t* pt, uint32_t level,
+               uint32_t slots, double scale) {
+  ACE_TRY(check_level(ctx->c, level); ctx->c->decode(re, im, U(pt), level, slots, scale))
+}
+
 int ace_timer_start(ace_ctx* ctx) { ACE_TRY(ACE_CUDA(cudaEventRecord(ctx->ev0, ctx->c->stream))) }
 int ace_timer_stop_ms(ace_ctx* ctx, float* ms) {
   ACE_TRY(ACE_CUDA(cudaEventRecord(ctx->ev1, ctx->c->stream));

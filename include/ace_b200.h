@@ -91,6 +91,26 @@ int ace_ct_rotate(ace_ctx* ctx, int64_t* r0, int64_t* r1, const int64_t* c0, con
 int ace_ct_mul_relin(ace_ctx* ctx, int64_t* r0, int64_t* r1, const int64_t* a0, const int64_t* a1, const int64_t* b0, const int64_t* b1, uint32_t num_q);
 int ace_ct_rescale(ace_ctx* ctx, int64_t* r0, int64_t* r1, const int64_t* c0, const int64_t* c1, uint32_t num_q);
 
+/* ---- client side: keys, encryption, CKKS encode/decode.
+ *      keygen:  Alloc_ckks_key_generator (ant/src/util/ckks_key_generator.c:13-37): secret,
+ *               public, relinearisation key and one rotation key per index.  Sampling uses the
+ *               runtime's own generator (valid keys, not bit-identical to the reference's).
+ *      import:  take the reference's keys instead (parity runs).
+ *      encode:  Encode_at_level_with_sf (ant/src/util/ckks_encoder.c:199-299), FP64 on the GPU,
+ *               bit-exact; `vals` is a HOST array of len reals, out = level (+p_cnt) limbs.
+ *      encode_value: Encode_val_at_level (ckks_encoder.c:464-528).
+ *      encrypt / decrypt: ant/src/util/ckks_encryptor.c:20-95, ckks_decryptor.c:19-65.
+ *      decode:  Decode (ckks_encoder.c:649-703); pt = level limbs NTT form (device),
+ *               out_re/out_im HOST arrays of `slots` doubles (out_im may be NULL). */
+int ace_keygen(ace_ctx* ctx, uint64_t seed, const int32_t* rot_idxs, size_t num_rot_idx);
+int ace_sk_import(ace_ctx* ctx, const int64_t* host_sk_ntt_qp);          /* L+K limbs */
+int ace_pk_import(ace_ctx* ctx, const int64_t* host_pk0, const int64_t* host_pk1); /* L limbs each */
+int ace_encode(ace_ctx* ctx, int64_t* out, const double* vals, size_t len, uint32_t level, uint32_t slots, uint32_t sf_degree, uint32_t p_cnt);
+int ace_encode_value(ace_ctx* ctx, int64_t* out, double value, uint32_t level, uint32_t sf_degree);
+int ace_encrypt(ace_ctx* ctx, int64_t* c0, int64_t* c1, const int64_t* pt, uint32_t level, uint64_t seed);
+int ace_decrypt(ace_ctx* ctx, int64_t* pt, const int64_t* c0, const int64_t* c1, uint32_t level);
+int ace_decode(ace_ctx* ctx, double* out_re, double* out_im, const int64_t* pt, uint32_t level, uint32_t slots, double scale);
+
 /* ---- timing helpers for the benchmark: CUDA events on the context's stream */
 int ace_timer_start(ace_ctx* ctx);
 int ace_timer_stop_ms(ace_ctx* ctx, float* ms);
