@@ -62,6 +62,12 @@ SIGNATURES = {
     "ace_encrypt": (C.c_int, [vp, vp, vp, vp, u32, C.c_uint64]),
     "ace_decrypt": (C.c_int, [vp, vp, vp, vp, u32]),
     "ace_decode": (C.c_int, [vp, vp, vp, vp, u32, u32, C.c_double]),
+    "ace_bootstrap_depth": (C.c_int, [vp]),
+    "ace_bootstrap_setup": (C.c_int, [vp, u32]),
+    "ace_bootstrap_rot_indices": (C.c_int, [vp, u32, vp, sz]),
+    "ace_keygen_rotations": (C.c_int, [vp, C.c_uint64, vp, sz]),
+    "ace_bootstrap": (C.c_int, [vp, vp, vp, C.POINTER(u32), C.POINTER(C.c_double), C.POINTER(u32),
+                                vp, vp, u32, u32, C.c_double, u32, u32]),
     "ace_timer_start": (C.c_int, [vp]),
     "ace_timer_stop_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
 }
@@ -255,6 +261,35 @@ class Context:
         d0, d1, r0, r1 = self.put(c0), self.put(c1), self.empty(nq - 1), self.empty(nq - 1)
         self._ck(self.lib.ace_ct_rescale(self.h, r0.ptr, r1.ptr, d0.ptr, d1.ptr, nq))
         return r0.get(), r1.get()
+
+    # ---- bootstrap
+    def bootstrap_depth(self):
+        return self.lib.ace_bootstrap_depth(self.h)
+
+    def bootstrap_rot_indices(self, slots=0):
+        buf = (i32 * 4096)()
+        n = self.lib.ace_bootstrap_rot_indices(self.h, slots, buf, 4096)
+        if n < 0:
+            self._ck(n)
+        return [int(buf[i]) for i in range(n)]
+
+    def bootstrap_setup(self, slots=0):
+        self._ck(self.lib.ace_bootstrap_setup(self.h, slots))
+
+    def keygen_rotations(self, seed, rots):
+        r = (i32 * max(1, len(rots)))(*rots)
+        self._ck(self.lib.ace_keygen_rotations(self.h, seed, r, len(rots)))
+
+    def bootstrap(self, c0, c1, slots, scale, sf_degree, level_after):
+        """host in / host out; returns (r0, r1, scale, sf_degree)"""
+        nq = c0.shape[0]
+        d0, d1 = self.put(c0), self.put(c1)
+        r0, r1 = self.empty(self.L), self.empty(self.L)
+        lvl, sfd, sc = u32(0), u32(0), C.c_double(0)
+        self._ck(self.lib.ace_bootstrap(self.h, r0.ptr, r1.ptr, C.byref(lvl), C.byref(sc),
+                                        C.byref(sfd), d0.ptr, d1.ptr, nq, slots, scale,
+                                        sf_degree, level_after))
+        return r0.get()[: lvl.value], r1.get()[: lvl.value], sc.value, sfd.value
 
     # ---- client side
     def keygen(self, seed, rots):

@@ -6,7 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libace_b200.so")
-SOURCES = ["kernels.cu", "context.cu", "client.cu", "capi.cu", "rt_shim.cu"]
+SOURCES = ["kernels.cu", "kernels_ext.cu", "context.cu", "client.cu", "evaluator.cu",
+           "chebyshev.cu", "bootstrap.cu", "capi.cu", "rt_shim.cu"]
 
 
 def needs_build():

@@ -5,12 +5,13 @@
 #include <string>
 
 #include "../../include/ace_b200.h"
-#include "context.h"
+#include "evaluator.h"
 
 using namespace ace;
 
 struct ace_ctx {
   Context*    c;
+  Evaluator*  ev;
   cudaEvent_t ev0, ev1;
 };
 
@@ -47,6 +48,7 @@ int ace_ctx_create(ace_ctx** out, uint32_t poly_degree, size_t mul_depth, size_t
              hamming_weight};
     ace_ctx* h = new ace_ctx;
     h->c       = new Context(p, device);
+    h->ev      = new Evaluator(h->c);
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
     *out = h;
@@ -61,6 +63,7 @@ void ace_ctx_destroy(ace_ctx* ctx) {
   if (!ctx) return;
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
+  delete ctx->ev;
   delete ctx->c;
   delete ctx;
 }
@@ -220,6 +223,44 @@ int ace_decrypt(ace_ctx* ctx, int64_t* pt, const int64_t* c0, const int64_t* c1,
 int ace_decode(ace_ctx* ctx, double* re, double* im, const int64_t* pt, uint32_t level,
                uint32_t slots, double scale) {
   ACE_TRY(check_level(ctx->c, level); ctx->c->decode(re, im, U(pt), level, slots, scale))
+}
+
+// ---- bootstrap
+int ace_bootstrap_depth(const ace_ctx* ctx) {
+  return (int)Evaluator::bootstrap_depth(ctx->c->params.hamming_weight);
+}
+int ace_bootstrap_setup(ace_ctx* ctx, uint32_t slots) { ACE_TRY(ctx->ev->bootstrap_setup(slots)) }
+int ace_bootstrap_rot_indices(ace_ctx* ctx, uint32_t slots, int32_t* out, size_t cap) {
+  try {
+    if (!ctx) { g_err = "null context"; return -1; }
+    std::vector<int32_t> v = ctx->ev->bootstrap_rot_indices(slots);
+    for (size_t i = 0; i < v.size() && i < cap; i++) out[i] = v[i];
+    return (int)v.size();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+int ace_keygen_rotations(ace_ctx* ctx, uint64_t seed, const int32_t* rots, size_t n) {
+  ACE_TRY(for (size_t i = 0; i < n; i++) {
+    u32 k = ctx->c->auto_index(rots[i]);
+    if (!ctx->c->has_rot_key(k)) ctx->c->gen_auto_key(k, seed + i);
+  })
+}
+int ace_bootstrap(ace_ctx* ctx, int64_t* r0, int64_t* r1, uint32_t* out_level, double* out_scale,
+                  uint32_t* out_sf_degree, const int64_t* c0, const int64_t* c1, uint32_t level,
+                  uint32_t slots, double scale, uint32_t sf_degree, uint32_t level_after_bts) {
+  ACE_TRY(check_level(ctx->c, level);
+          Ct in; in.c0 = const_cast<u64*>(U(c0)); in.c1 = const_cast<u64*>(U(c1));
+          in.nq = level; in.np = 0; in.cap = level; in.sf = scale; in.sfd = sf_degree;
+          in.slots = slots ? slots : ctx->c->N / 2;
+          Ct out;
+          ctx->ev->bootstrap(out, in, level_after_bts);
+          size_t bytes = (size_t)out.nq * ctx->c->N * sizeof(u64);
+          ACE_CUDA(cudaMemcpyAsync(r0, out.c0, bytes, cudaMemcpyDeviceToDevice, ctx->c->stream));
+          ACE_CUDA(cudaMemcpyAsync(r1, out.c1, bytes, cudaMemcpyDeviceToDevice, ctx->c->stream));
+          *out_level = out.nq; *out_scale = out.sf; *out_sf_degree = out.sfd;
+          ctx->ev->release(out))
 }
 
 int ace_timer_start(ace_ctx* ctx) { ACE_TRY(ACE_CUDA(cudaEventRecord(ctx->ev0, ctx->c->stream))) }

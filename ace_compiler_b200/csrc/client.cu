@@ -337,6 +337,15 @@ void Context::init_encoder() {
 // out: level (+ p_cnt) limbs, NTT form.
 void Context::encode(u64* out, const double* vals, size_t len, u32 level, u32 slots,
                      u32 sf_degree, u32 p_cnt) {
+  encode_any(out, vals, nullptr, len, level, slots, sf_degree, p_cnt);
+}
+// complex messages (the C2S / S2C diagonals of the bootstrap, Encode_ext_at_level)
+void Context::encode_cplx(u64* out, const std::complex<double>* vals, size_t len, u32 level,
+                          u32 slots, u32 sf_degree, u32 p_cnt) {
+  encode_any(out, nullptr, vals, len, level, slots, sf_degree, p_cnt);
+}
+void Context::encode_any(u64* out, const double* vals, const std::complex<double>* cvals,
+                         size_t len, u32 level, u32 slots, u32 sf_degree, u32 p_cnt) {
   init_encoder();
   if (slots == 0) slots = N / 2;
   if (level == 0) level = (u32)L;
@@ -348,7 +357,12 @@ void Context::encode(u64* out, const double* vals, size_t len, u32 level, u32 sl
   cplx* hv = (cplx*)enc_host_;
   cplx* dv = (cplx*)enc_buf_;
   ACE_CUDA(cudaStreamSynchronize(stream));  // enc_host_ may still feed a previous encode
-  for (size_t i = 0; i < slots; i++) hv[i] = cplx{i < len ? vals[i] : 0.0, 0.0};
+  if (cvals) {
+    for (size_t i = 0; i < slots; i++)
+      hv[i] = i < len ? cplx{cvals[i].real(), cvals[i].imag()} : cplx{0.0, 0.0};
+  } else {
+    for (size_t i = 0; i < slots; i++) hv[i] = cplx{i < len ? vals[i] : 0.0, 0.0};
+  }
   ACE_CUDA(cudaMemcpyAsync(dv, hv, slots * sizeof(cplx), cudaMemcpyHostToDevice, stream));
   const cplx* tw = (const cplx*)enc_tw_;
   for (u32 logm = logslots; logm > 0; logm--) {
@@ -383,8 +397,7 @@ void Context::encode(u64* out, const double* vals, size_t len, u32 level, u32 sl
 
 // Encode_val_at_level (ckks_encoder.c:464-528): constant plaintext, every coefficient of limb
 // l equals the same residue (NTT of a constant polynomial... the reference marks it NTT as is)
-void Context::encode_value(u64* out, double value, u32 level, u32 sf_degree) {
-  init_encoder();
+std::vector<u64> Context::value_residues(double value, u32 level, u32 sf_degree) const {
   if (level == 0) level = (u32)L;
   const double sf = (double)((u64)1 << params.scaling_mod_size);
   const int MAX_BITS_IN_WORD = 61;
@@ -417,6 +430,13 @@ void Context::encode_value(u64* out, double value, u32 level, u32 sf_degree) {
     }
     for (u32 i = 0; i < level; i++) res[i] = hm::mulmod(res[i], approx[i], mod[i]);
   }
+  return res;
+}
+
+void Context::encode_value(u64* out, double value, u32 level, u32 sf_degree) {
+  init_encoder();
+  if (level == 0) level = (u32)L;
+  std::vector<u64> res = value_residues(value, level, sf_degree);
   ACE_CUDA(cudaStreamSynchronize(stream));
   ACE_CUDA(cudaMemcpyAsync(enc_pow_, res.data(), level * sizeof(u64), cudaMemcpyHostToDevice,
                            stream));

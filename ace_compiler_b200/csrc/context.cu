@@ -120,7 +120,7 @@ Context::Context(const Params& p, int dev) : params(p), device(dev) {
   T.n_inv_sh = to_device(n_inv_sh);
 
   // ---- ModDown constants (crt.c Precompute_primes(p) + Precompute_new_base(p, q))
-  std::vector<u64> phi(K), phi_sh(K), phm(L * K), pinv(L), pinv_sh(L);
+  std::vector<u64> phi(K), phi_sh(K), phm(L * K), pinv(L), pinv_sh(L), pm(L), pm_sh(L);
   for (size_t i = 0; i < K; i++) {
     u64 pi = mod[L + i], hat = 1;
     for (size_t k = 0; k < K; k++)
@@ -139,12 +139,18 @@ Context::Context(const Params& p, int dev) : params(p), device(dev) {
     }
     pinv[j]    = hm::invmod_prime(prod, qj);
     pinv_sh[j] = hm::shoup(pinv[j], qj);
+    pm[j]      = prod;  // P mod q_j (Get_pmodq, crt.h:697-700)
+    pm_sh[j]   = hm::shoup(prod, qj);
   }
   phat_inv_      = to_device(phi);
   phat_inv_sh_   = to_device(phi_sh);
   phat_mod_q_    = to_device(phm);
   pinv_mod_q_    = to_device(pinv);
   pinv_mod_q_sh_ = to_device(pinv_sh);
+  // P mod q_j lifts a Q-basis polynomial into the extended basis (Switch_key_ext and the
+  // add_first term of Fast_rotate_ext, ckks_evaluator.c:462-489, 566-573)
+  pmodq_    = to_device(pm);
+  pmodq_sh_ = to_device(pm_sh);
 
   // ---- Rescale constants (crt.c:270-330).  _ql_ql_inv_mod_ql_div_ql_mod_qi equals
   // -q_l^-1 mod q_i: (Q/q_l)*[(Q/q_l)^-1]_{q_l} = 1 + k*q_l and is 0 mod q_i, so the stored
@@ -384,17 +390,12 @@ void Context::import_key_limbs(SwitchKey& key, u32 part, int which, const u64* h
 }
 
 // ---------------------------------------------------------------------------- key switch
-// Same dataflow as the emitted Rotate()/Relinearize() bodies, but batched: one INTT launch
-// for all digits, one base-conversion launch (one descriptor per digit), one NTT launch for
-// all complement limbs, one inner-product launch that reads the key once, and one ModDown
-// for both output polynomials.
-void Context::key_switch(u64* out0, u64* out1, const u64* d, u32 num_q, const SwitchKey& key,
-                         const u64* add0) {
-  if (!key.k0 || !key.k1) throw std::runtime_error("switch key not loaded");
+// Switch_key_precompute (polynomial.c:1224-1239, 1337-1343): ext[j] = ModUp of digit j, j < beta.
+// Only the complement limbs of ext[j] are written; the digit's own limbs are the limbs of `d`
+// themselves and ksw_acc reads them from there.
+void Context::modup_all(u64* ext, const u64* d, u32 num_q) {
   const u32 beta = (u32)num_decomp(num_q), W = num_q + (u32)K;
   u64* coef = alloc_limbs(num_q, false);
-  u64* ext  = alloc_limbs((size_t)beta * W, false);
-  u64* acc  = alloc_limbs(2 * (size_t)W, false);
   intt_from(coef, d, 0, num_q);
   ConvDesc  descs[6];
   LimbBatch nb;
@@ -420,23 +421,29 @@ void Context::key_switch(u64* out0, u64* out1, const u64* d, u32 num_q, const Sw
   }
   launch_ntt(T, nb, stream);
   launches += (logN > 12) ? 2 : 1;
-  u64 *acc0 = acc, *acc1 = acc + (size_t)W * N;
-  launch_ksw_inner(T, acc0, acc1, ext, d, (u32)part_size, key.k0, key.k1, beta, num_q, (u32)L,
-                   (u32)K, stream);
+  free_limbs(coef);
+}
+
+// Fast_switch_key_ext (ckks_evaluator.c:418-460): acc0/acc1 = sum_j ext_j (.) key_j over the
+// num_q + K limbs of the extended basis (no ModDown)
+void Context::ksw_acc(u64* acc0, u64* acc1, const u64* ext, const u64* d, u32 num_q,
+                      const SwitchKey& key) {
+  if (!key.k0 || !key.k1) throw std::runtime_error("switch key not loaded");
+  launch_ksw_inner(T, acc0, acc1, ext, d, (u32)part_size, key.k0, key.k1,
+                   (u32)num_decomp(num_q), num_q, (u32)L, (u32)K, stream);
   launches++;
-  // ModDown of both accumulators
-  u64* pc   = alloc_limbs(2 * K, false);
-  u64* conv = alloc_limbs(2 * (size_t)num_q, false);
-  LimbBatch pb;
-  pb.base = pc; pb.src = acc; pb.n = 2 * (u32)K;
-  for (u32 i = 0; i < 2 * K; i++) {
-    pb.slot[i]     = (u16)i;
-    pb.src_slot[i] = (u16)((i / K) * W + num_q + i % K);
-    pb.g[i]        = (u16)(L + i % K);
-  }
-  launch_intt(T, pb, stream);
+}
+
+// Reduce_rns_base of two extended polynomials at once (polynomial.c:928-967); a0/a1 are laid
+// out [num_q | K]; add0 (optional) is added to out0.  a1 == nullptr: one polynomial only.
+void Context::mod_down_pair(u64* out0, u64* out1, const u64* a0, const u64* a1, u32 num_q,
+                            const u64* add0) {
+  const u32 np = a1 ? 2 : 1;
+  u64* pc   = alloc_limbs(np * K, false);
+  u64* conv = alloc_limbs(np * (size_t)num_q, false);
   ConvDesc md[2];
-  for (int h = 0; h < 2; h++) {
+  for (u32 h = 0; h < np; h++) {
+    intt_from(pc + (size_t)h * K * N, (h ? a1 : a0) + (size_t)num_q * N, (u32)L, (u32)K);
     ConvDesc& c = md[h];
     c.x = pc + (size_t)h * K * N; c.out = conv + (size_t)h * num_q * N;
     c.hatinv = phat_inv_; c.hatinv_sh = phat_inv_sh_; c.hatmod = phat_mod_q_;
@@ -444,16 +451,33 @@ void Context::key_switch(u64* out0, u64* out1, const u64* d, u32 num_q, const Sw
     for (u32 i = 0; i < K; i++) c.g_in[i] = (u16)(L + i);
     for (u32 o = 0; o < num_q; o++) { c.g_out[o] = (u16)o; c.out_slot[o] = (u16)o; }
   }
-  launch_base_conv(T, md, 2, stream);
+  launch_base_conv(T, md, np, stream);
   LimbBatch cb;
-  cb.base = conv; cb.src = nullptr; cb.n = 2 * num_q;
-  for (u32 i = 0; i < 2 * num_q; i++) { cb.slot[i] = (u16)i; cb.g[i] = (u16)(i % num_q); }
+  cb.base = conv; cb.src = nullptr; cb.n = np * num_q;
+  for (u32 i = 0; i < np * num_q; i++) { cb.slot[i] = (u16)i; cb.g[i] = (u16)(i % num_q); }
   launch_ntt(T, cb, stream);
-  launch_moddown_tail(T, out0, acc0, conv, add0, pinv_mod_q_, pinv_mod_q_sh_, num_q, stream);
-  launch_moddown_tail(T, out1, acc1, conv + (size_t)num_q * N, nullptr, pinv_mod_q_,
-                      pinv_mod_q_sh_, num_q, stream);
-  launches += 3 + 2 * ((logN > 12) ? 2 : 1);
-  free_limbs(coef); free_limbs(ext); free_limbs(acc); free_limbs(pc); free_limbs(conv);
+  launch_moddown_tail(T, out0, a0, conv, add0, pinv_mod_q_, pinv_mod_q_sh_, num_q, stream);
+  if (a1)
+    launch_moddown_tail(T, out1, a1, conv + (size_t)num_q * N, nullptr, pinv_mod_q_,
+                        pinv_mod_q_sh_, num_q, stream);
+  launches += 1 + np + ((logN > 12) ? 2 : 1);
+  free_limbs(pc); free_limbs(conv);
+}
+
+// Same dataflow as the emitted Rotate()/Relinearize() bodies, but batched: one INTT launch
+// for all digits, one base-conversion launch (one descriptor per digit), one NTT launch for
+// all complement limbs, one inner-product launch that reads the key once, and one ModDown
+// for both output polynomials.
+void Context::key_switch(u64* out0, u64* out1, const u64* d, u32 num_q, const SwitchKey& key,
+                         const u64* add0) {
+  if (!key.k0 || !key.k1) throw std::runtime_error("switch key not loaded");
+  const u32 beta = (u32)num_decomp(num_q), W = num_q + (u32)K;
+  u64* ext = alloc_limbs((size_t)beta * W, false);
+  u64* acc = alloc_limbs(2 * (size_t)W, false);
+  modup_all(ext, d, num_q);
+  ksw_acc(acc, acc + (size_t)W * N, ext, d, num_q, key);
+  mod_down_pair(out0, out1, acc, acc + (size_t)W * N, num_q, add0);
+  free_limbs(ext); free_limbs(acc);
 }
 
 // emitted Rotate(): key switch c1, add c0, apply the automorphism to both polynomials

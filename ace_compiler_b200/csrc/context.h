@@ -97,6 +97,11 @@ class Context {
   // to out0 after ModDown (the c0 of a rotation).
   void key_switch(u64* out0, u64* out1, const u64* d, u32 num_q, const SwitchKey& key,
                   const u64* add0);
+  void modup_all(u64* ext, const u64* d, u32 num_q);
+  void ksw_acc(u64* acc0, u64* acc1, const u64* ext, const u64* d, u32 num_q,
+               const SwitchKey& key);
+  void mod_down_pair(u64* out0, u64* out1, const u64* a0, const u64* a1, u32 num_q,
+                     const u64* add0);
   void ct_rotate(u64* r0, u64* r1, const u64* c0, const u64* c1, u32 num_q, int32_t rot_idx);
   void ct_mul_relin(u64* r0, u64* r1, const u64* a0, const u64* a1, const u64* b0,
                     const u64* b1, u32 num_q);
@@ -140,6 +145,14 @@ class Context {
   // ModDown tables
   u64 *phat_inv_, *phat_inv_sh_, *phat_mod_q_;  // [K], [K], [L][K]
   u64 *pinv_mod_q_, *pinv_mod_q_sh_;            // [L]
+ public:
+  u64 *pmodq_, *pmodq_sh_;                      // [L] P mod q_j
+  std::vector<u64> value_residues(double value, u32 level, u32 sf_degree) const;
+  void encode_cplx(u64* out, const std::complex<double>* vals, size_t len, u32 level,
+                   u32 slots, u32 sf_degree, u32 p_cnt);
+  void encode_any(u64* out, const double* vals, const std::complex<double>* cvals, size_t len,
+                  u32 level, u32 slots, u32 sf_degree, u32 p_cnt);
+ private:
   // Rescale tables, row l (dropping q_l), column i < l
   u64 *qlinv_, *qlinv_sh_, *negqlinv_, *negqlinv_sh_;  // [L][L]
 

@@ -91,3 +91,69 @@ void launch_rescale_post(const DeviceTables& T, u64* out, const u64* c, const u6
                          const u64* qlinv, const u64* qlinv_sh, u32 n_limbs, cudaStream_t s);
 
 }  // namespace ace
+
+// ---- kernels_ext.cu: extended-basis (Q u P) variants and the bootstrap-only kernels ------
+namespace ace {
+
+// A polynomial over the extended basis is laid out [nq Q limbs | np P limbs] (Q limbs of the
+// reference's POLYNOMIAL first, Get_p_coeffs after them, polynomial.h:214-217).  Limb y uses
+// modulus index  y < nq ? y : pbase + (y - nq)   (pbase = L, the first P prime).
+struct Basis {
+  u32 nq, np, pbase;
+  __host__ __device__ u32 width() const { return nq + np; }
+  __host__ __device__ u32 g(u32 y) const { return y < nq ? y : pbase + (y - nq); }
+};
+
+// r = a op b over all limbs of the basis (Add_poly / Sub_poly / Multiply_ntt with p primes,
+// polynomial.c:16-146)
+void launch_ew_basis(const DeviceTables& T, EwOp op, u64* r, const u64* a, const u64* b,
+                     Basis bs, cudaStream_t s);
+// r[y][i] = a[y][order[i]] over all limbs (Automorphism_transform, polynomial.c:299-340)
+void launch_gather_basis(const DeviceTables& T, u64* r, const u64* a, const int64_t* order,
+                         Basis bs, cudaStream_t s);
+// Per-limb scalars passed by value (no staging copy, no sync): v[y] < q_y, sh[y] its Shoup
+// companion floor(v * 2^64 / q).
+struct ScalarPack {
+  u64 v[64];
+  u64 sh[64];
+};
+// r[y][i] = a[y][i] + v[y]   (Add_const: a constant plaintext in NTT form is the same residue
+// in every coefficient, ckks_encoder.c:505-516; Add_plaintext, ckks_evaluator.c:103-118)
+void launch_add_scalar(const DeviceTables& T, u64* r, const u64* a, const ScalarPack& sc,
+                       u32 g0, u32 n_limbs, cudaStream_t s);
+// r[y][i] = a[y][i] * v[y]   (Mul_const / Mul_integer, ckks_evaluator.c:208-232)
+void launch_mul_scalar_pack(const DeviceTables& T, u64* r, const u64* a, const ScalarPack& sc,
+                            Basis bs, cudaStream_t s);
+// ModRaise (Transform_values_from_level0, ckks_bootstrap_context.c:1527-1550):
+// out[0] = in, out[y] = Switch_modulus(in, q_0, q_y) for 0 < y < n_limbs; coefficient form
+void launch_mod_raise(const DeviceTables& T, u64* out, const u64* in, u32 n_limbs,
+                      cudaStream_t s);
+
+// out[y] = the monomial +-X^index in coefficient form over n_limbs Q limbs: coefficient `index`
+// is 1 (or q_y - 1 when negative), all others 0   (Mul_by_monomial, ckks_evaluator.c:234-264)
+void launch_monomial(const DeviceTables& T, u64* out, u32 index, bool negative, u32 n_limbs,
+                     cudaStream_t s);
+
+// Plaintext inner product of the baby-step/giant-step linear transform
+// (Rotate_iteration, ckks_bootstrap_context.c:1299-1322):
+//   out0 = sum_j a0[j] (.) pt[j],   out1 = sum_j a1[j] (.) pt[j]      over the basis `bs`
+// a0/a1[j]: extended polynomials laid out [nq | np]; pt[j]: plaintext with its Q limbs at
+// limb y and its P limbs starting at limb pt_pstart (a plaintext encoded at a higher level
+// and derived down, Derive_plain).  128-bit accumulation, one reduction per output.
+constexpr int kMaxDot = 32;
+struct DotArgs {
+  const u64* a0[kMaxDot];
+  const u64* a1[kMaxDot];
+  const u64* pt[kMaxDot];
+  u32        n;
+  u32        pt_pstart;
+};
+void launch_pt_dot(const DeviceTables& T, u64* out0, u64* out1, const DotArgs& args, Basis bs,
+                   cudaStream_t s);
+
+// acc0[y] += c0[y] * sc[y] on the Q limbs only, then nothing else: the "add_first" term of
+// Fast_rotate_ext (ckks_evaluator.c:566-573); r may alias acc.
+void launch_mul_scalar_add(const DeviceTables& T, u64* r, const u64* acc, const u64* c,
+                           const u64* sc, const u64* sc_sh, u32 n_limbs, cudaStream_t s);
+
+}  // namespace ace

@@ -1,0 +1,161 @@
+// kernels_ext.cu -- element-wise kernels over the extended basis Q u P and the kernels only the
+// CKKS bootstrap needs (ModRaise, scalar add, plaintext inner product).  All HBM-bound: one
+// thread per coefficient, grid.y = limb, every output limb written exactly once.
+#include "kernels.cuh"
+
+namespace ace {
+
+static inline dim3 grid_for(const DeviceTables& T, u32 n_limbs) {
+  return dim3((T.N + 255) / 256, n_limbs);
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256) ew_basis_kernel(DeviceTables T, u64* __restrict__ r,
+                                                       const u64* __restrict__ a,
+                                                       const u64* __restrict__ b, Basis bs) {
+  const Modulus m   = T.mod[bs.g(blockIdx.y)];
+  const size_t  off = (size_t)blockIdx.y * T.N;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
+    u64 x = a[off + i], y = b[off + i], z;
+    if (OP == EW_ADD) z = add_mod(x, y, m.q);
+    if (OP == EW_SUB) z = sub_mod(x, y, m.q);
+    if (OP == EW_MUL) z = mul_mod(x, y, m);
+    r[off + i] = z;
+  }
+}
+
+void launch_ew_basis(const DeviceTables& T, EwOp op, u64* r, const u64* a, const u64* b,
+                     Basis bs, cudaStream_t s) {
+  if (bs.width() == 0) return;
+  dim3 grid = grid_for(T, bs.width());
+  switch (op) {
+    case EW_ADD: ew_basis_kernel<EW_ADD><<<grid, 256, 0, s>>>(T, r, a, b, bs); break;
+    case EW_SUB: ew_basis_kernel<EW_SUB><<<grid, 256, 0, s>>>(T, r, a, b, bs); break;
+    case EW_MUL: ew_basis_kernel<EW_MUL><<<grid, 256, 0, s>>>(T, r, a, b, bs); break;
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_basis_kernel(DeviceTables T, u64* __restrict__ r,
+                                                           const u64* __restrict__ a,
+                                                           const int64_t* __restrict__ order,
+                                                           Basis bs) {
+  const u64    q   = T.mod[bs.g(blockIdx.y)].q;
+  const size_t off = (size_t)blockIdx.y * T.N;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
+    int64_t k = order[i];
+    r[off + i] = k >= 0 ? a[off + k] : q - a[off - k];
+  }
+}
+
+void launch_gather_basis(const DeviceTables& T, u64* r, const u64* a, const int64_t* order,
+                         Basis bs, cudaStream_t s) {
+  if (bs.width() == 0) return;
+  gather_basis_kernel<<<grid_for(T, bs.width()), 256, 0, s>>>(T, r, a, order, bs);
+}
+
+__global__ void __launch_bounds__(256) add_scalar_kernel(DeviceTables T, u64* __restrict__ r,
+                                                         const u64* __restrict__ a,
+                                                         ScalarPack sc, u32 g0) {
+  const u64    q   = T.mod[g0 + blockIdx.y].q;
+  const u64    v   = sc.v[blockIdx.y];
+  const size_t off = (size_t)blockIdx.y * T.N;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x)
+    r[off + i] = add_mod(a[off + i], v, q);
+}
+
+void launch_add_scalar(const DeviceTables& T, u64* r, const u64* a, const ScalarPack& sc,
+                       u32 g0, u32 n_limbs, cudaStream_t s) {
+  if (n_limbs == 0) return;
+  add_scalar_kernel<<<grid_for(T, n_limbs), 256, 0, s>>>(T, r, a, sc, g0);
+}
+
+__global__ void __launch_bounds__(256) mul_scalar_pack_kernel(DeviceTables T,
+                                                              u64* __restrict__ r,
+                                                              const u64* __restrict__ a,
+                                                              ScalarPack sc, Basis bs) {
+  const u64    q   = T.mod[bs.g(blockIdx.y)].q;
+  const u64    w = sc.v[blockIdx.y], wsh = sc.sh[blockIdx.y];
+  const size_t off = (size_t)blockIdx.y * T.N;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x)
+    r[off + i] = mul_shoup(a[off + i], w, wsh, q);
+}
+
+void launch_mul_scalar_pack(const DeviceTables& T, u64* r, const u64* a, const ScalarPack& sc,
+                            Basis bs, cudaStream_t s) {
+  if (bs.width() == 0) return;
+  mul_scalar_pack_kernel<<<grid_for(T, bs.width()), 256, 0, s>>>(T, r, a, sc, bs);
+}
+
+__global__ void __launch_bounds__(256) mod_raise_kernel(DeviceTables T, u64* __restrict__ out,
+                                                        const u64* __restrict__ in) {
+  const u32    y   = blockIdx.y;
+  const u64    q0 = T.mod[0].q, qy = T.mod[y].q;
+  const size_t off = (size_t)y * T.N;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
+    u64 v = in[i];
+    out[off + i] = y == 0 ? v : switch_modulus(v, q0, qy);
+  }
+}
+
+void launch_mod_raise(const DeviceTables& T, u64* out, const u64* in, u32 n_limbs,
+                      cudaStream_t s) {
+  if (n_limbs == 0) return;
+  mod_raise_kernel<<<grid_for(T, n_limbs), 256, 0, s>>>(T, out, in);
+}
+
+__global__ void __launch_bounds__(256) monomial_kernel(DeviceTables T, u64* __restrict__ out,
+                                                       u32 index, u32 negative) {
+  const u64    q   = T.mod[blockIdx.y].q;
+  const size_t off = (size_t)blockIdx.y * T.N;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x)
+    out[off + i] = i == index ? (negative ? q - 1 : 1) : 0;
+}
+
+void launch_monomial(const DeviceTables& T, u64* out, u32 index, bool negative, u32 n_limbs,
+                     cudaStream_t s) {
+  if (n_limbs == 0) return;
+  monomial_kernel<<<grid_for(T, n_limbs), 256, 0, s>>>(T, out, index, negative ? 1u : 0u);
+}
+
+__global__ void __launch_bounds__(256) pt_dot_kernel(DeviceTables T, u64* __restrict__ out0,
+                                                     u64* __restrict__ out1, DotArgs A,
+                                                     Basis bs) {
+  const u32     y    = blockIdx.y;
+  const Modulus m    = T.mod[bs.g(y)];
+  const size_t  off  = (size_t)y * T.N;
+  const size_t  poff = (size_t)(y < bs.nq ? y : A.pt_pstart + (y - bs.nq)) * T.N;
+  const u32     i    = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T.N) return;
+  u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+  for (u32 j = 0; j < A.n; j++) {
+    const u64 p = A.pt[j][poff + i];
+    mac128(lo0, hi0, A.a0[j][off + i], p);
+    mac128(lo1, hi1, A.a1[j][off + i], p);
+  }
+  out0[off + i] = reduce128(lo0, hi0, m);
+  out1[off + i] = reduce128(lo1, hi1, m);
+}
+
+void launch_pt_dot(const DeviceTables& T, u64* out0, u64* out1, const DotArgs& args, Basis bs,
+                   cudaStream_t s) {
+  if (bs.width() == 0 || args.n == 0) return;
+  pt_dot_kernel<<<grid_for(T, bs.width()), 256, 0, s>>>(T, out0, out1, args, bs);
+}
+
+__global__ void __launch_bounds__(256) mul_scalar_add_kernel(
+    DeviceTables T, u64* __restrict__ r, const u64* __restrict__ acc, const u64* __restrict__ c,
+    const u64* __restrict__ sc, const u64* __restrict__ sc_sh) {
+  const u64    q   = T.mod[blockIdx.y].q;
+  const u64    w = sc[blockIdx.y], wsh = sc_sh[blockIdx.y];
+  const size_t off = (size_t)blockIdx.y * T.N;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x)
+    r[off + i] = add_mod(acc[off + i], mul_shoup(c[off + i], w, wsh, q), q);
+}
+
+void launch_mul_scalar_add(const DeviceTables& T, u64* r, const u64* acc, const u64* c,
+                           const u64* sc, const u64* sc_sh, u32 n_limbs, cudaStream_t s) {
+  if (n_limbs == 0) return;
+  mul_scalar_add_kernel<<<grid_for(T, n_limbs), 256, 0, s>>>(T, r, acc, c, sc, sc_sh);
+}
+
+}  // namespace ace

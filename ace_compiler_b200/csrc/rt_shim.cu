@@ -20,7 +20,7 @@
 #include <string>
 
 #include "../../include/rt_ant/rt_ant.h"
-#include "context.h"
+#include "evaluator.h"
 
 using namespace ace;
 
@@ -44,6 +44,7 @@ struct SWITCH_KEY {
 namespace {
 
 Context*  g_ctx    = nullptr;
+Evaluator* g_ev    = nullptr;
 MODULUS*  g_mod    = nullptr;  // [G] Q then P, contiguous like the reference's arrays
 int       g_device = 0;
 uint64_t  g_enc_seed = 1;
@@ -159,6 +160,19 @@ void init_cipher(CIPHERTEXT* res, CIPHERTEXT* ciph, double sc, uint32_t deg) {  
   set_level(res, ciph->_c0_poly._num_primes);
 }
 
+// Bootstrap_keygen (ckks_bootstrap_context.c:1194-1226): rotation keys of the linear
+// transforms plus the conjugation key (automorphism index 2N-1)
+void bootstrap_keygen(u32 slots, u64 seed) {
+  Context* c = g_ctx;
+  std::vector<int32_t> rots = g_ev->bootstrap_rot_indices(slots);
+  for (size_t i = 0; i < rots.size(); i++) {
+    u32 k = c->auto_index(rots[i]);
+    if (!c->has_rot_key(k)) c->gen_auto_key(k, seed + 100000 + i + slots);
+  }
+  u32 conj = 2 * c->N - 1;
+  if (!c->has_rot_key(conj)) c->gen_auto_key(conj, seed + 99999);
+}
+
 u32 mod_index(MODULUS* m) {
   ptrdiff_t g = m - g_mod;
   if (g < 0 || (size_t)g >= ctx()->G) die("MODULUS pointer does not belong to the context");
@@ -236,10 +250,16 @@ API void Prepare_context(void) {
            "_num_rot_idx = %ld,_hamming_wieght = %ld\n",
            p->_provider, p->_poly_degree, p->_sec_level, p->_mul_depth, p->_first_mod_size,
            p->_scaling_mod_size, parts, g_ctx->K, p->_num_rot_idx, p->_hamming_weight);
+    g_ev = new Evaluator(g_ctx);
     const char* no_keys = getenv("ACE_B200_NO_KEYGEN");  // parity runs import the oracle's keys
-    if (!(no_keys && no_keys[0] == '1')) {
-      const char* seed = getenv("ACE_B200_SEED");
-      g_ctx->keygen(seed ? strtoull(seed, nullptr, 10) : 20251017ull, p->_rot_idxs, p->_num_rot_idx);
+    const bool  own_keys = !(no_keys && no_keys[0] == '1');
+    const char* seed_env = getenv("ACE_B200_SEED");
+    const u64   seed = seed_env ? strtoull(seed_env, nullptr, 10) : 20251017ull;
+    if (own_keys) g_ctx->keygen(seed, p->_rot_idxs, p->_num_rot_idx);
+    // Bootstrap_precom(N/2) (context.c:80-82, 162-185): plaintext tables + bootstrap keys
+    if (g_ev->bootstrap_supported()) {
+      g_ev->bootstrap_setup(g_ctx->N / 2);
+      if (own_keys) bootstrap_keygen(g_ctx->N / 2, seed);
     }
   });
   if (Get_rt_data_info) {
@@ -253,6 +273,8 @@ API void Finalize_context(void) {
   for (auto& kv : g_swk) { delete[] kv.second->pk0; delete[] kv.second->pk1; delete kv.second; }
   g_swk.clear();
   Pt_mgr_fini();
+  delete g_ev;
+  g_ev = nullptr;
   delete g_ctx;
   g_ctx = nullptr;
   delete[] g_mod;
@@ -753,9 +775,33 @@ API CIPHER Encrypt(CIPHER res, PLAIN plain) {  // cipher_eval.c:406-409
   return res;
 }
 
+// Bootstrap (cipher_eval.c:366-404) -> Evaluator::bootstrap
 API CIPHER Bootstrap(CIPHER res, CIPHER ciph, uint32_t level_after_bts) {
-  (void)res; (void)ciph; (void)level_after_bts;
-  die("Bootstrap is not implemented in this round of the B200 runtime");
+  Context* c = ctx();
+  if (ciph->_c0_poly._num_primes_p != 0) die("Bootstrap: extended ciphertext");
+  guard([&] {
+    Ct in;
+    in.c0 = U(ciph->_c0_poly._data); in.c1 = U(ciph->_c1_poly._data);
+    in.nq = (u32)ciph->_c0_poly._num_primes; in.np = 0; in.cap = in.nq;
+    in.sf = ciph->_scaling_factor; in.sfd = ciph->_sf_degree; in.slots = ciph->_slots;
+    const bool own_keys = !(getenv("ACE_B200_NO_KEYGEN") && getenv("ACE_B200_NO_KEYGEN")[0] == '1');
+    if (own_keys && in.slots != c->N / 2) {  // Bootstrap_precom(num_slots) on first use
+      const char* seed_env = getenv("ACE_B200_SEED");
+      bootstrap_keygen(in.slots, seed_env ? strtoull(seed_env, nullptr, 10) : 20251017ull);
+    }
+    Ct out;
+    g_ev->bootstrap(out, in, level_after_bts);
+    if (res != ciph) { free_poly_data(&res->_c0_poly); free_poly_data(&res->_c1_poly); }
+    else { free_poly_data(&ciph->_c0_poly); free_poly_data(&ciph->_c1_poly); }
+    for (int w = 0; w < 2; w++) {
+      POLYNOMIAL* p = w ? &res->_c1_poly : &res->_c0_poly;
+      p->_ring_degree = c->N; p->_num_primes = out.nq; p->_num_primes_p = 0;
+      p->_num_alloc_primes = out.cap; p->_is_ntt = true;
+      p->_data = reinterpret_cast<int64_t*>(w ? out.c1 : out.c0);
+    }
+    res->_scaling_factor = out.sf; res->_sf_degree = out.sfd; res->_slots = out.slots;
+  });
+  return res;
 }
 
 // =========================================================================== plaintexts

@@ -111,6 +111,23 @@ int ace_encrypt(ace_ctx* ctx, int64_t* c0, int64_t* c1, const int64_t* pt, uint3
 int ace_decrypt(ace_ctx* ctx, int64_t* pt, const int64_t* c0, const int64_t* c1, uint32_t level);
 int ace_decode(ace_ctx* ctx, double* out_re, double* out_im, const int64_t* pt, uint32_t level, uint32_t slots, double scale);
 
+/* ---- bootstrap (a11): Bootstrap -> Eval_bootstrap (ant/src/ckks/cipher_eval.c:366-404,
+ *      ant/src/util/ckks_bootstrap_context.c:1050-1192, 1237-1860, ckks_chebyshev.c).
+ *      depth:        Get_bootstrap_depth with level budget {3,3} (ckks_bootstrap_context.h:275-283)
+ *      setup:        Bootstrap_setup for `slots` (0 = N/2): C2S/S2C plaintext tables into HBM
+ *      rot_indices:  Find_rot_indices: the rotation keys Bootstrap_keygen generates; returns the
+ *                    count (may exceed cap).  The conjugation key is rotation index 2N-1 in
+ *                    ace_swk_import / ace_keygen_rotations.
+ *      bootstrap:    r0/r1 must hold L limbs; level/scale/sf_degree of the result are returned.
+ *      Environment switches follow the reference: RTLIB_BTS_EVEN_POLY, RT_BTS_CLEAR_IMAG. */
+int ace_bootstrap_depth(const ace_ctx* ctx);
+int ace_bootstrap_setup(ace_ctx* ctx, uint32_t slots);
+int ace_bootstrap_rot_indices(ace_ctx* ctx, uint32_t slots, int32_t* out, size_t cap);
+int ace_keygen_rotations(ace_ctx* ctx, uint64_t seed, const int32_t* rot_idxs, size_t num_rot_idx);
+int ace_bootstrap(ace_ctx* ctx, int64_t* r0, int64_t* r1, uint32_t* out_level, double* out_scale,
+                  uint32_t* out_sf_degree, const int64_t* c0, const int64_t* c1, uint32_t level,
+                  uint32_t slots, double scale, uint32_t sf_degree, uint32_t level_after_bts);
+
 /* ---- timing helpers for the benchmark: CUDA events on the context's stream */
 int ace_timer_start(ace_ctx* ctx);
 int ace_timer_stop_ms(ace_ctx* ctx, float* ms);

@@ -229,6 +229,18 @@ int ref_swk_export(int is_rot, int32_t rot_idx, uint32_t part, int which,
   return (int)Get_num_alloc_primes(p);
 }
 
+/* same, looked up by automorphism index (the conjugation key 2N-1 has no rotation index);
+ * returns -2 when the key does not exist */
+int ref_swk_export_auto(uint32_t auto_idx, uint32_t part, int which, int64_t* out) {
+  CKKS_KEY_GENERATOR* kg  = (CKKS_KEY_GENERATOR*)Get_key_gen(Context);
+  SWITCH_KEY*         swk = Get_auto_key(kg, auto_idx);
+  if (swk == NULL) return -2;
+  if (part >= Get_swk_size(swk)) return -1;
+  POLY p = which ? Pk1_at(swk, part) : Pk0_at(swk, part);
+  memcpy(out, Get_poly_coeffs(p), Get_poly_mem_size(p));
+  return (int)Get_num_alloc_primes(p);
+}
+
 /* secret key in NTT form over Q then P */
 void ref_sk_export(int64_t* out) {
   CKKS_KEY_GENERATOR* kg = (CKKS_KEY_GENERATOR*)Get_key_gen(Context);

@@ -75,6 +75,7 @@ class RefLib:
         L.ref_mod_down.argtypes = [vp, vp, sz]
         L.ref_rescale.argtypes = [vp, vp, sz]
         L.ref_swk_export.argtypes = [C.c_int, i32, u32, C.c_int, vp]
+        L.ref_swk_export_auto.argtypes = [u32, u32, C.c_int, vp]
         L.ref_encode.argtypes = [vp, vp, sz, u32, u32, u32, vp]
         L.ref_encode_float.argtypes = [vp, vp, sz, u32, u32, vp, vp]
         L.ref_encode_double.argtypes = [vp, vp, sz, u32, u32, vp, vp]
@@ -151,6 +152,16 @@ class RefLib:
             n = self.lib.ref_swk_export(int(is_rot), rot, part, 0, _p(k0[part]))
             assert n == self.L + self.K, n
             self.lib.ref_swk_export(int(is_rot), rot, part, 1, _p(k1[part]))
+        return k0, k1
+
+    def swk_auto(self, auto_idx):
+        """switch key looked up by automorphism index (conjugation key: 2N-1)"""
+        k0 = np.zeros((self.parts, self.L + self.K, self.N), np.int64)
+        k1 = np.zeros_like(k0)
+        for part in range(self.parts):
+            n = self.lib.ref_swk_export_auto(auto_idx, part, 0, _p(k0[part]))
+            assert n == self.L + self.K, (auto_idx, n)
+            self.lib.ref_swk_export_auto(auto_idx, part, 1, _p(k1[part]))
         return k0, k1
 
     def sk(self):

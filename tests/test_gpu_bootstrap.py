@@ -1,0 +1,34 @@
+"""GPU parity of Bootstrap: ace_bootstrap through the C ABI vs the compiled
+reference (oracle/_ref/libace_ref.so) on the same keys and the same input ciphertext --
+identical limbs, level, scale.  Each case runs in its own process because the reference owns a
+single global context.  Bar: bit-exact."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CASES = [
+    # N, depth, hamming weight, slots, input level, level_after_bts, even polynomial
+    (1024, 17, 192, 512, 2, 3, 1),     # fully packed, even sine polynomial (ResNet setting)
+    (1024, 17, 192, 512, 1, 2, 0),     # odd+even polynomial table
+    (4096, 20, 192, 2048, 3, 5, 1),    # 3 digits of 7 limbs, K = 7
+    (2048, 24, 0, 1024, 2, 4, 0),      # dense-secret table (K=512, 6 double angles, degree 88)
+    (2048, 18, 192, 256, 2, 3, 1),     # sparsely packed: partial sums + extra rotation
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "N%d_d%d_hw%d_s%d_even%d" % (c[0], c[1], c[2], c[3], c[6]))
+def test_bootstrap_bit_exact(case):
+    N, depth, hw, slots, lin, lafter, even = case
+    env = dict(os.environ)
+    env["RTLIB_BTS_EVEN_POLY"] = str(even)
+    r = subprocess.run([sys.executable, os.path.join(HERE, "bootstrap_case.py"), str(N), str(depth),
+                        str(hw), str(slots), str(lin), str(lafter)],
+                       env=env, capture_output=True, text=True, timeout=1500)
+    sys.stdout.write(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-2000:] + "\n" + r.stderr[-4000:]
+    assert "BOOTSTRAP PARITY OK" in r.stdout
