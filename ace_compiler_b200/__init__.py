@@ -65,6 +65,10 @@ SIGNATURES = {
     "ace_bootstrap_depth": (C.c_int, [vp]),
     "ace_bootstrap_setup": (C.c_int, [vp, u32]),
     "ace_bootstrap_rot_indices": (C.c_int, [vp, u32, vp, sz]),
+    "ace_bootstrap_linear": (C.c_int, [vp, vp, vp, C.POINTER(u32), C.POINTER(C.c_double), C.POINTER(u32),
+                                       vp, vp, u32, u32, C.c_double, u32, C.c_int]),
+    "ace_bootstrap_plain": (vp, [vp, u32, C.c_int, u32, u32, C.POINTER(u32)]),
+    "ace_bootstrap_fft_diagonals": (sz, [u32, u32, C.c_int, C.c_int, vp]),
     "ace_keygen_rotations": (C.c_int, [vp, C.c_uint64, vp, sz]),
     "ace_bootstrap": (C.c_int, [vp, vp, vp, C.POINTER(u32), C.POINTER(C.c_double), C.POINTER(u32),
                                 vp, vp, u32, u32, C.c_double, u32, u32]),
@@ -290,6 +294,26 @@ class Context:
                                         C.byref(sfd), d0.ptr, d1.ptr, nq, slots, scale,
                                         sf_degree, level_after))
         return r0.get()[: lvl.value], r1.get()[: lvl.value], sc.value, sfd.value
+
+    def bootstrap_linear(self, c0, c1, slots, scale, sf_degree, encoding):
+        nq = c0.shape[0]
+        d0, d1 = self.put(c0), self.put(c1)
+        r0, r1 = self.empty(self.L), self.empty(self.L)
+        lvl, sfd, sc = u32(0), u32(0), C.c_double(0)
+        self._ck(self.lib.ace_bootstrap_linear(self.h, r0.ptr, r1.ptr, C.byref(lvl), C.byref(sc),
+                                               C.byref(sfd), d0.ptr, d1.ptr, nq, slots, scale,
+                                               sf_degree, int(encoding)))
+        return r0.get()[: lvl.value], r1.get()[: lvl.value], sc.value, sfd.value
+
+    def bootstrap_plain(self, slots, encoding, step, idx):
+        lvl = u32(0)
+        ptr = self.lib.ace_bootstrap_plain(self.h, slots, int(encoding), step, idx, C.byref(lvl))
+        if not ptr:
+            return None
+        n = lvl.value + self.K
+        out = np.zeros((n, self.N), np.int64)
+        self._ck(self.lib.ace_download(self.h, _hp(out), ptr, n))
+        return out
 
     # ---- client side
     def keygen(self, seed, rots):

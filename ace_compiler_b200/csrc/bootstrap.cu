@@ -660,6 +660,49 @@ void Evaluator::eval_bootstrap(Ct& res, Ct& in, u32 raise_level, BtsPrecom& pc) 
   if (res.nq <= init_q) copy(res, in);  // bootstrapping earned nothing: return the input
 }
 
+void Evaluator::linear_transform(Ct& res, Ct& in, bool encoding) {
+  if (!precom_.count(in.slots)) bootstrap_setup(in.slots);
+  coeff_slots_transform(res, in, *precom_[in.slots], encoding);
+}
+
+const u64* Evaluator::diagonal_plain(u32 slots, bool encoding, u32 step, u32 idx, u32* level) {
+  if (slots == 0) slots = c->N / 2;
+  if (!precom_.count(slots)) bootstrap_setup(slots);
+  BtsPrecom& pc = *precom_[slots];
+  auto& tab = encoding ? pc.c2s : pc.s2c;
+  if (step >= tab.size() || idx >= tab[step].size()) return nullptr;
+  *level = (encoding ? pc.c2s_level : pc.s2c_level)[step];
+  return tab[step][idx];
+}
+
+// host-only view of the collapsed FFT diagonals (no device work): [level][row][slots] (re, im)
+size_t Evaluator::fft_diagonals(u32 slots, u32 budget, bool flag, bool encoding, double* out) {
+  const u32 slots4 = 4 * slots;
+  std::vector<u32> rot_group(slots);
+  u32 five = 1;
+  for (u32 i = 0; i < slots; i++) {
+    rot_group[i] = five;
+    five *= 5;
+    five %= slots4;
+  }
+  vcd ksi(slots4 + 1);
+  for (size_t i = 0; i < slots4; i++) {
+    double angle = 2.0 * M_PI * i / slots4;
+    ksi[i] = cd(cos(angle), sin(angle));
+  }
+  ksi[slots4] = ksi[0];
+  vvvcd co = coeff_collapse(ksi, rot_group, budget, flag, encoding);
+  size_t n = 0;
+  for (auto& lvl : co)
+    for (auto& row : lvl)
+      for (cd& v : row) {
+        out[2 * n] = v.real();
+        out[2 * n + 1] = v.imag();
+        n++;
+      }
+  return n;
+}
+
 // Bootstrap (src/ckks/cipher_eval.c:366-404)
 void Evaluator::bootstrap(Ct& res, Ct& in, u32 level_after_bts) {
   const u32 slots = in.slots, q_cnt = (u32)c->L;

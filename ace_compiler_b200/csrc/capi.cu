@@ -2,6 +2,7 @@
 // No torch types, no exceptions across the boundary: errors become negative return codes
 // plus a thread-local message.
 #include <cstring>
+#include <functional>
 #include <string>
 
 #include "../../include/ace_b200.h"
@@ -241,6 +242,44 @@ int ace_bootstrap_rot_indices(ace_ctx* ctx, uint32_t slots, int32_t* out, size_t
     return -1;
   }
 }
+static void run_ct(ace_ctx* ctx, int64_t* r0, int64_t* r1, uint32_t* out_level, double* out_scale,
+                   uint32_t* out_sf_degree, const int64_t* c0, const int64_t* c1, uint32_t level,
+                   uint32_t slots, double scale, uint32_t sf_degree,
+                   const std::function<void(Ct&, Ct&)>& op) {
+  Ct in;
+  in.c0 = const_cast<u64*>(U(c0)); in.c1 = const_cast<u64*>(U(c1));
+  in.nq = level; in.np = 0; in.cap = level; in.sf = scale; in.sfd = sf_degree;
+  in.slots = slots ? slots : ctx->c->N / 2;
+  Ct out;
+  op(out, in);
+  size_t bytes = (size_t)out.nq * ctx->c->N * sizeof(u64);
+  ACE_CUDA(cudaMemcpyAsync(r0, out.c0, bytes, cudaMemcpyDeviceToDevice, ctx->c->stream));
+  ACE_CUDA(cudaMemcpyAsync(r1, out.c1, bytes, cudaMemcpyDeviceToDevice, ctx->c->stream));
+  *out_level = out.nq; *out_scale = out.sf; *out_sf_degree = out.sfd;
+  ctx->ev->release(out);
+}
+int ace_bootstrap_linear(ace_ctx* ctx, int64_t* r0, int64_t* r1, uint32_t* out_level,
+                         double* out_scale, uint32_t* out_sf_degree, const int64_t* c0,
+                         const int64_t* c1, uint32_t level, uint32_t slots, double scale,
+                         uint32_t sf_degree, int encoding) {
+  ACE_TRY(check_level(ctx->c, level);
+          run_ct(ctx, r0, r1, out_level, out_scale, out_sf_degree, c0, c1, level, slots, scale,
+                 sf_degree, [&](Ct& o, Ct& i) { ctx->ev->linear_transform(o, i, encoding != 0); }))
+}
+const int64_t* ace_bootstrap_plain(ace_ctx* ctx, uint32_t slots, int encoding, uint32_t step,
+                                   uint32_t idx, uint32_t* level) {
+  try {
+    cudaSetDevice(ctx->c->device);
+    return reinterpret_cast<const int64_t*>(ctx->ev->diagonal_plain(slots, encoding != 0, step, idx, level));
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+size_t ace_bootstrap_fft_diagonals(uint32_t slots, uint32_t level_budget, int flag, int encoding,
+                                   double* out) {
+  return Evaluator::fft_diagonals(slots, level_budget, flag != 0, encoding != 0, out);
+}
 int ace_keygen_rotations(ace_ctx* ctx, uint64_t seed, const int32_t* rots, size_t n) {
   ACE_TRY(for (size_t i = 0; i < n; i++) {
     u32 k = ctx->c->auto_index(rots[i]);
@@ -251,16 +290,8 @@ int ace_bootstrap(ace_ctx* ctx, int64_t* r0, int64_t* r1, uint32_t* out_level, d
                   uint32_t* out_sf_degree, const int64_t* c0, const int64_t* c1, uint32_t level,
                   uint32_t slots, double scale, uint32_t sf_degree, uint32_t level_after_bts) {
   ACE_TRY(check_level(ctx->c, level);
-          Ct in; in.c0 = const_cast<u64*>(U(c0)); in.c1 = const_cast<u64*>(U(c1));
-          in.nq = level; in.np = 0; in.cap = level; in.sf = scale; in.sfd = sf_degree;
-          in.slots = slots ? slots : ctx->c->N / 2;
-          Ct out;
-          ctx->ev->bootstrap(out, in, level_after_bts);
-          size_t bytes = (size_t)out.nq * ctx->c->N * sizeof(u64);
-          ACE_CUDA(cudaMemcpyAsync(r0, out.c0, bytes, cudaMemcpyDeviceToDevice, ctx->c->stream));
-          ACE_CUDA(cudaMemcpyAsync(r1, out.c1, bytes, cudaMemcpyDeviceToDevice, ctx->c->stream));
-          *out_level = out.nq; *out_scale = out.sf; *out_sf_degree = out.sfd;
-          ctx->ev->release(out))
+          run_ct(ctx, r0, r1, out_level, out_scale, out_sf_degree, c0, c1, level, slots, scale,
+                 sf_degree, [&](Ct& o, Ct& i) { ctx->ev->bootstrap(o, i, level_after_bts); }))
 }
 
 int ace_timer_start(ace_ctx* ctx) { ACE_TRY(ACE_CUDA(cudaEventRecord(ctx->ev0, ctx->c->stream))) }

@@ -101,7 +101,7 @@ void Context::gen_secret_key(u64 seed) {
   }
   int64_t* dv = nullptr;
   ACE_CUDA(cudaMalloc(&dv, N * sizeof(int64_t)));
-  ACE_CUDA(cudaMemcpy(dv, s.data(), N * sizeof(int64_t), cudaMemcpyHostToDevice));
+  h2d_sync(dv, s.data(), N * sizeof(int64_t));
   if (!sk_ntt) ACE_CUDA(cudaMalloc(&sk_ntt, G * (size_t)N * sizeof(u64)));
   LimbBatch b = all_limbs(sk_ntt, 0, (u32)G);
   small_to_rns_kernel<<<grid_for(N, (u32)G), 256, 0, stream>>>(T, b, dv);
@@ -112,14 +112,14 @@ void Context::gen_secret_key(u64 seed) {
 
 void Context::import_secret_key(const u64* host_ntt_qp) {
   if (!sk_ntt) ACE_CUDA(cudaMalloc(&sk_ntt, G * (size_t)N * sizeof(u64)));
-  ACE_CUDA(cudaMemcpy(sk_ntt, host_ntt_qp, G * (size_t)N * sizeof(u64), cudaMemcpyHostToDevice));
+  h2d_sync(sk_ntt, host_ntt_qp, G * (size_t)N * sizeof(u64));
 }
 
 void Context::import_public_key(const u64* h0, const u64* h1) {
   if (!pk0) ACE_CUDA(cudaMalloc(&pk0, L * (size_t)N * sizeof(u64)));
   if (!pk1) ACE_CUDA(cudaMalloc(&pk1, L * (size_t)N * sizeof(u64)));
-  ACE_CUDA(cudaMemcpy(pk0, h0, L * (size_t)N * sizeof(u64), cudaMemcpyHostToDevice));
-  ACE_CUDA(cudaMemcpy(pk1, h1, L * (size_t)N * sizeof(u64), cudaMemcpyHostToDevice));
+  h2d_sync(pk0, h0, L * (size_t)N * sizeof(u64));
+  h2d_sync(pk1, h1, L * (size_t)N * sizeof(u64));
 }
 
 // pk = (-a s + e, a) over Q  (ckks_key_generator.c:84-125)
@@ -326,7 +326,7 @@ void Context::init_encoder() {
   }
   cplx* d = nullptr;
   ACE_CUDA(cudaMalloc(&d, tw.size() * sizeof(cplx)));
-  ACE_CUDA(cudaMemcpy(d, tw.data(), tw.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+  h2d_sync(d, tw.data(), tw.size() * sizeof(cplx));
   enc_tw_ = d;
   ACE_CUDA(cudaMalloc(&enc_buf_, half * sizeof(cplx)));
   ACE_CUDA(cudaMalloc(&enc_pow_, G * sizeof(u64)));

@@ -13,6 +13,7 @@
 #include <cstring>
 
 #include "host_math.h"
+#include "rou_table.h"
 
 namespace ace {
 
@@ -22,7 +23,7 @@ template <typename Tp>
 Tp* Context::to_device(const std::vector<Tp>& v) {
   Tp* d = nullptr;
   ACE_CUDA(cudaMalloc(&d, v.size() * sizeof(Tp) + 16));
-  ACE_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(Tp), cudaMemcpyHostToDevice));
+  h2d_sync(d, v.data(), v.size() * sizeof(Tp));
   owned_.push_back(d);
   return d;
 }
@@ -90,7 +91,9 @@ Context::Context(const Params& p, int dev) : params(p), device(dev) {
     M.mu64    = (u64)((((u128)1) << (62 + nbits)) / m);
     M.pad     = 0;
     // psi = g^((q-1)/2N) with g the smallest generator (number_theory.c:132-157)
-    psi[g] = hm::powmod(hm::smallest_generator(m), (m - 1) / (2 * (u64)N), m);
+    // ... unless the reference's fixed-root table has an entry (fhe_std_parms.c:200-271)
+    psi[g] = fixed_root(2 * (u64)N, m);
+    if (psi[g] == 0) psi[g] = hm::powmod(hm::smallest_generator(m), (m - 1) / (2 * (u64)N), m);
     u64 psi_inv = hm::invmod_prime(psi[g], m), pw = 1, ipw = 1;
     u64* t  = tw.data() + g * (size_t)N;
     u64* ts = tw_sh.data() + g * (size_t)N;
@@ -376,7 +379,7 @@ const int64_t* Context::auto_order(u32 k) {  // number_theory.c:201-214 (is_ntt 
   }
   int64_t* d = nullptr;
   ACE_CUDA(cudaMalloc(&d, N * sizeof(int64_t)));
-  ACE_CUDA(cudaMemcpy(d, ord.data(), N * sizeof(int64_t), cudaMemcpyHostToDevice));
+  h2d_sync(d, ord.data(), N * sizeof(int64_t));
   auto_orders_[k] = d;
   return d;
 }
@@ -386,7 +389,7 @@ void Context::import_key_limbs(SwitchKey& key, u32 part, int which, const u64* h
   size_t per = G * (size_t)N;
   u64**  dst = which ? &key.k1 : &key.k0;
   if (*dst == nullptr) ACE_CUDA(cudaMalloc(dst, dnum * per * sizeof(u64)));
-  ACE_CUDA(cudaMemcpy(*dst + part * per, host, per * sizeof(u64), cudaMemcpyHostToDevice));
+  h2d_sync(*dst + part * per, host, per * sizeof(u64));
 }
 
 // ---------------------------------------------------------------------------- key switch

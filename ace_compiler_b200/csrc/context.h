@@ -61,6 +61,13 @@ class Context {
   void upload(u64* dst, const u64* src, size_t n_limbs);
   void download(u64* dst, const u64* src, size_t n_limbs);
   void sync();
+  // Host -> device copy that is complete, and ordered before later work on `stream`, when it
+  // returns.  (A plain cudaMemcpy from pageable memory may return while the DMA is still in
+  // flight on the legacy stream, which the non-blocking context stream does not wait for.)
+  void h2d_sync(void* dst, const void* src, size_t bytes) {
+    ACE_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+    ACE_CUDA(cudaStreamSynchronize(stream));
+  }
 
   size_t num_decomp(size_t num_q) const {
     size_t n = (num_q + part_size - 1) / part_size;

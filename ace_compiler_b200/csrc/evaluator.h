@@ -79,6 +79,13 @@ class Evaluator {
   std::vector<int32_t> bootstrap_rot_indices(u32 slots); // Find_rot_indices :280-299
   void       bootstrap(Ct& res, Ct& in, u32 level_after_bts);  // Bootstrap + Eval_bootstrap
 
+  // Coeffs_to_slots / Slots_to_coeffs alone (:1494-1504) and read access to the diagonal tables
+  void linear_transform(Ct& res, Ct& in, bool encoding);
+  const u64* diagonal_plain(u32 slots, bool encoding, u32 step, u32 idx, u32* level);
+
+  // collapsed FFT diagonals of C2S/S2C as the set-up computes them (host FP64 only)
+  static size_t fft_diagonals(u32 slots, u32 budget, bool flag, bool encoding, double* out);
+
   // ---- ckks_chebyshev.c
   void eval_chebyshev(Ct& out, Ct& in, const std::vector<double>& coeffs, double a, double b);
 

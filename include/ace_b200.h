@@ -123,6 +123,19 @@ int ace_decode(ace_ctx* ctx, double* out_re, double* out_im, const int64_t* pt, 
 int ace_bootstrap_depth(const ace_ctx* ctx);
 int ace_bootstrap_setup(ace_ctx* ctx, uint32_t slots);
 int ace_bootstrap_rot_indices(ace_ctx* ctx, uint32_t slots, int32_t* out, size_t cap);
+/*      linear:       Coeffs_to_slots (encoding != 0) / Slots_to_coeffs alone (:1494-1504)
+ *      plain:        device pointer to diagonal plaintext [step][idx] of the C2S (encoding) or S2C
+ *                    table: *level Q limbs followed by K P limbs; NULL where the table has no entry */
+int ace_bootstrap_linear(ace_ctx* ctx, int64_t* r0, int64_t* r1, uint32_t* out_level, double* out_scale,
+                         uint32_t* out_sf_degree, const int64_t* c0, const int64_t* c1, uint32_t level,
+                         uint32_t slots, double scale, uint32_t sf_degree, int encoding);
+const int64_t* ace_bootstrap_plain(ace_ctx* ctx, uint32_t slots, int encoding, uint32_t step, uint32_t idx, uint32_t* level);
+/*      fft_diagonals: host-only (no device): the collapsed FFT diagonals Coeff_collapse
+ *                    (ckks_bootstrap_context.c:612-776) produces for `slots` and a level budget,
+ *                    flattened [level][row][slot] as (re, im) doubles; returns the count of
+ *                    complex values.  out needs budget * (2^(ceil(log2(slots)/budget)+1)) * slots
+ *                    * 2 doubles at most. */
+size_t ace_bootstrap_fft_diagonals(uint32_t slots, uint32_t level_budget, int flag, int encoding, double* out);
 int ace_keygen_rotations(ace_ctx* ctx, uint64_t seed, const int32_t* rot_idxs, size_t num_rot_idx);
 int ace_bootstrap(ace_ctx* ctx, int64_t* r0, int64_t* r1, uint32_t* out_level, double* out_scale,
                   uint32_t* out_sf_degree, const int64_t* c0, const int64_t* c1, uint32_t level,

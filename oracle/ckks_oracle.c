@@ -8,6 +8,7 @@
  * Paths are relative to /root/reference/fhe-cmplr/rtlib/ant/.
  */
 #include "ckks_oracle.h"
+#include "rou_table.h"
 
 #include <complex.h>
 #include <math.h>
@@ -202,8 +203,12 @@ orc_ctx* orc_create(uint32_t degree, size_t mul_depth, size_t first_mod_size,
   c->rou_inv = (u64**)calloc(G, sizeof(u64*));
   for (size_t g = 0; g < G; g++) {
     u64 m     = c->mod[g];
-    u64 gen   = find_generator(m);
-    c->psi[g] = powmod(gen, (m - 1) / (2 * (u64)degree), m);
+    /* Root_of_unity (number_theory.c:140-157): fixed-root table first, then g^((q-1)/2N) */
+    c->psi[g] = orc_fixed_root(2 * (u64)degree, m);
+    if (c->psi[g] == 0) {
+      u64 gen   = find_generator(m);
+      c->psi[g] = powmod(gen, (m - 1) / (2 * (u64)degree), m);
+    }
     c->n_inv[g]   = invmod(degree % m, m);
     c->rou[g]     = (u64*)calloc(degree, sizeof(u64));
     c->rou_inv[g] = (u64*)calloc(degree, sizeof(u64));

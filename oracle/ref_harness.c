@@ -414,6 +414,76 @@ void ref_ct_bootstrap(REF_CT* res, const REF_CT* a, uint32_t level_after_bts) {
   Free_ciphertext(z);
 }
 
+/* one diagonal plaintext of the bootstrap tables (u0hatt_pre_fft for encoding, u0_pre_fft for
+ * decoding): copies num_q + num_p limbs, returns num_q (0: entry unused, -1: no tables) */
+int ref_bts_plain(uint32_t slots, int encoding, uint32_t step, uint32_t idx, int64_t* out) {
+  CKKS_BTS_CTX*    bts    = Get_bts_ctx((CKKS_EVALUATOR*)Get_eval(Context));
+  CKKS_BTS_PRECOM* precom = Get_bts_precom(bts, slots);
+  if (!precom) return -1;
+  VL_VL_PLAIN* tab = encoding ? Get_u0hatt_pre_fft(precom) : Get_u0_pre_fft(precom);
+  VALUE_LIST*  row = Get_vl_value_at(tab, step);
+  if (idx >= LIST_LEN(row)) return 0;
+  PLAINTEXT* pt = (PLAINTEXT*)Get_ptr_value_at(row, idx);
+  if (pt == NULL) return 0;
+  POLYNOMIAL* p = Get_plain_poly(pt);
+  memcpy(out, Get_poly_coeffs(p), Get_poly_mem_size(p));
+  return (int)Get_num_q(p);
+}
+
+/* Coeffs_to_slots / Slots_to_coeffs alone (ckks_bootstrap_context.c:1494-1504) */
+void ref_bts_linear(REF_CT* res, const REF_CT* a, int encoding) {
+  CKKS_BTS_CTX*    bts    = Get_bts_ctx((CKKS_EVALUATOR*)Get_eval(Context));
+  CKKS_BTS_PRECOM* precom = Get_bts_precom(bts, a->slots);
+  CIPHERTEXT       x;
+  CIPHERTEXT*      z = Alloc_ciphertext();
+  Wrap_ct(&x, a);
+  if (encoding) Coeffs_to_slots(z, &x, Get_u0hatt_pre_fft(precom), bts);
+  else Slots_to_coeffs(z, &x, Get_u0_pre_fft(precom), bts);
+  Unwrap_ct(res, z);
+  Free_ciphertext(z);
+}
+
+/* collapsed FFT diagonals of the bootstrap linear transforms (Coeff_collapse,
+ * ckks_bootstrap_context.c:612-776) with the root table of Bootstrap_setup (:1107-1121);
+ * out: [level][row][slots] complex doubles (re, im), rows as the reference sizes them;
+ * returns the number of complex values written */
+VALUE_LIST* Coeff_collapse(VALUE_LIST* ksipows, VALUE_LIST* rot_group, uint32_t level_budget,
+                           bool flag, bool encoding);
+size_t ref_coeff_collapse(uint32_t slots, uint32_t budget, int flag, int encoding, double* out) {
+  uint32_t    slots_4   = 4 * slots;
+  VALUE_LIST* rot_group = Alloc_value_list(UI32_TYPE, slots);
+  uint32_t    five_pows = 1;
+  FOR_ALL_ELEM(rot_group, idx) {
+    UI32_VALUE_AT(rot_group, idx) = five_pows;
+    five_pows *= 5;
+    five_pows %= slots_4;
+  }
+  VALUE_LIST* ksi_pows = Alloc_value_list(DCMPLX_TYPE, slots_4 + 1);
+  for (size_t idx = 0; idx < slots_4; idx++) {
+    double angle                   = 2.0 * M_PI * idx / slots_4;
+    DCMPLX_VALUE_AT(ksi_pows, idx) = cos(angle) + sin(angle) * I;
+  }
+  DCMPLX_VALUE_AT(ksi_pows, slots_4) = DCMPLX_VALUE_AT(ksi_pows, 0);
+  VALUE_LIST* coeffs = Coeff_collapse(ksi_pows, rot_group, budget, flag, encoding);
+  size_t      n      = 0;
+  FOR_ALL_ELEM(coeffs, i) {
+    VALUE_LIST* lvl = Get_vl_value_at(coeffs, i);
+    FOR_ALL_ELEM(lvl, j) {
+      VALUE_LIST* row = Get_vl_value_at(lvl, j);
+      FOR_ALL_ELEM(row, k) {
+        DCMPLX v     = Get_dcmplx_value_at(row, k);
+        out[2 * n]   = creal(v);
+        out[2 * n + 1] = cimag(v);
+        n++;
+      }
+    }
+  }
+  Free_value_list(coeffs);
+  Free_value_list(rot_group);
+  Free_value_list(ksi_pows);
+  return n;
+}
+
 /* ---- CPU baseline: the chain HMult+relin -> rescale -> rotate on independent ciphertexts,
  *      one per thread, sharing the (read-only) context like the reference's OpenMP image
  *      loop does (ant/dataset/resnet_cifar.main.inc:81).  Returns wall seconds. ---------- */

@@ -84,6 +84,8 @@ class RefLib:
         L.ref_ct_mul_plain.argtypes = [vp, vp, vp, dbl, u32]
         L.ref_ct_rotate.argtypes = [vp, vp, i32]
         L.ref_ct_bootstrap.argtypes = [vp, vp, u32]
+        L.ref_bts_linear.argtypes = [vp, vp, C.c_int]
+        L.ref_bts_plain.argtypes = [u32, C.c_int, u32, u32, vp]
         if RefLib._inited is None:
             r = (i32 * max(1, len(rots)))(*rots)
             L.ref_init(N, depth, q0_bits, sf_bits, parts, hw, r, len(rots), int(with_bootstrap))
@@ -234,6 +236,15 @@ class RefLib:
 
     def ct_bootstrap(self, ct, level_after):
         return self._unary(self.lib.ref_ct_bootstrap, ct, level_after, out_level=self.L)
+
+    def bts_linear(self, ct, encoding):
+        return self._unary(self.lib.ref_bts_linear, ct, int(encoding), out_level=self.L)
+
+    def bts_plain(self, slots, encoding, step, idx):
+        """diagonal plaintext (num_q + K limbs) of the bootstrap tables, or None"""
+        out = np.zeros((self.L + self.K, self.N), np.int64)
+        nq = self.lib.ref_bts_plain(slots, int(encoding), step, idx, _p(out))
+        return None if nq <= 0 else out[: nq + self.K]
 
     def ct_mul_plain(self, ct, pt, pt_scale, pt_sf_degree=1):
         pt = np.ascontiguousarray(pt)

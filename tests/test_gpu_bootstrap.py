@@ -18,6 +18,8 @@ CASES = [
     (4096, 20, 192, 2048, 3, 5, 1),    # 3 digits of 7 limbs, K = 7
     (2048, 24, 0, 1024, 2, 4, 0),      # dense-secret table (K=512, 6 double angles, degree 88)
     (2048, 18, 192, 256, 2, 3, 1),     # sparsely packed: partial sums + extra rotation
+    (16384, 17, 192, 8192, 2, 3, 1),   # 5 collapsed FFT layers (b=4) + fixed-root table for the P primes
+    (65536, 33, 192, 32768, 3, 15, 1), # ResNet-20's parameter set and call (GEN20:1577, 7148-7150)
 ]
 
 
