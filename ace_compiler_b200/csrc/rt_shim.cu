@@ -21,6 +21,7 @@
 
 #include "../../include/rt_ant/rt_ant.h"
 #include "evaluator.h"
+#include "op_queue.h"
 
 using namespace ace;
 
@@ -45,6 +46,7 @@ namespace {
 
 Context*  g_ctx    = nullptr;
 Evaluator* g_ev    = nullptr;
+OpQueue*   g_queue = nullptr;  // deferred Hw_modadd / Hw_modmul / Hw_rotate calls
 MODULUS*  g_mod    = nullptr;  // [G] Q then P, contiguous like the reference's arrays
 int       g_device = 0;
 uint64_t  g_enc_seed = 1;
@@ -52,14 +54,59 @@ std::map<std::string, CIPHERTEXT*> g_inputs, g_outputs;
 std::map<u32, SWITCH_KEY*>          g_swk;  // by automorphism index; 0 = relin key
 clock_t g_tm_stamp;
 
+// ACE_B200_STATS=1: per-entry-point call counts and host wall time (with a stream sync around
+// the timed calls), printed by Finalize_context -- where Main_graph's time goes
+struct Stat { const char* name; uint64_t calls; double secs; };
+Stat g_stats[] = {{"Hw_modadd", 0, 0}, {"Hw_modmul", 0, 0}, {"Hw_rotate", 0, 0},
+                  {"Decomp_modup", 0, 0}, {"Mod_down", 0, 0}, {"Rescale", 0, 0},
+                  {"Encode(Pt_from_msg)", 0, 0}, {"Bootstrap", 0, 0}, {"Alloc/Init", 0, 0},
+                  {"Free", 0, 0}, {"Copy/Set_coeffs", 0, 0}};
+enum { ST_ADD, ST_MUL, ST_ROT, ST_MODUP, ST_MODDOWN, ST_RESCALE, ST_ENCODE, ST_BTS, ST_ALLOC,
+       ST_FREE, ST_COPY, ST_COUNT };
+bool g_no_batch = false;
+bool g_stats_on = false, g_stats_sync = false;  // =2: sync around every scope (true GPU time)
+void stats_sync();
+inline double wall() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+struct StatScope {
+  int id; double t0;
+  explicit StatScope(int i) : id(i), t0(0) {
+    if (!g_stats_on) return;
+    if (g_stats_sync) stats_sync();
+    t0 = wall();
+  }
+  ~StatScope() {
+    if (!g_stats_on) return;
+    if (g_stats_sync) stats_sync();
+    g_stats[id].calls++;
+    g_stats[id].secs += wall() - t0;
+  }
+};
+
 [[noreturn]] void die(const char* msg) {
   fprintf(stderr, "[ace_b200] fatal: %s\n", msg);
   abort();  // FMT_ASSERT semantics (rtlib/include/common/error.h:23-29)
 }
 
-Context* ctx() {
+void stats_sync() {
+  if (!g_ctx) return;
+  if (g_queue) g_queue->flush();
+  cudaStreamSynchronize(g_ctx->stream);
+}
+
+// ctx_nf(): metadata only.  ctx(): the caller is about to touch device data or the stream, so
+// every recorded limb op is issued first (keeps program order on the stream).
+Context* ctx_nf() {
   if (!g_ctx) die("context not prepared (call Prepare_context first)");
   return g_ctx;
+}
+Context* ctx() {
+  Context* c = ctx_nf();
+  if (g_queue && !g_queue->empty()) g_queue->flush();
+  return c;
 }
 
 inline u64*       U(int64_t* p) { return reinterpret_cast<u64*>(p); }
@@ -78,15 +125,18 @@ std::string io_key(const char* name, size_t idx) { return std::string(name) + "#
 
 // Alloc_poly_data (polynomial.h:54-64): zero-filled limbs in HBM
 void alloc_poly_data(POLYNOMIAL* p, uint32_t degree, size_t nq, size_t np) {
+  StatScope ss(ST_ALLOC);
   p->_ring_degree      = degree;
   p->_num_primes       = nq;
   p->_num_primes_p     = np;
   p->_num_alloc_primes = nq + np;
   p->_is_ntt           = false;
-  guard([&] { p->_data = reinterpret_cast<int64_t*>(ctx()->alloc_limbs(nq + np, true)); });
+  // fresh memory: nothing recorded can refer to it, no flush needed
+  guard([&] { p->_data = reinterpret_cast<int64_t*>(ctx_nf()->alloc_limbs(nq + np, true)); });
 }
 
 void free_poly_data(POLYNOMIAL* p) {
+  StatScope ss(ST_FREE);
   if (p->_data) {
     guard([&] { ctx()->free_limbs(U(p->_data)); });
     p->_data = nullptr;
@@ -121,6 +171,7 @@ int64_t* p_coeffs(const POLYNOMIAL* p) {  // Get_p_coeffs (polynomial.h:214-217)
 }
 
 void copy_polynomial(POLYNOMIAL* dst, const POLYNOMIAL* src) {  // polynomial.h:425-438
+  StatScope ss(ST_COPY);
   guard([&] {
     Context* c = ctx();
     ACE_CUDA(cudaMemcpyAsync(dst->_data, src->_data, dst->_num_primes * (size_t)c->N * 8,
@@ -175,7 +226,7 @@ void bootstrap_keygen(u32 slots, u64 seed) {
 
 u32 mod_index(MODULUS* m) {
   ptrdiff_t g = m - g_mod;
-  if (g < 0 || (size_t)g >= ctx()->G) die("MODULUS pointer does not belong to the context");
+  if (g < 0 || (size_t)g >= ctx_nf()->G) die("MODULUS pointer does not belong to the context");
   return (u32)g;
 }
 
@@ -231,6 +282,8 @@ API void* Ace_context(void) { return g_ctx; }
 
 API void Prepare_context(void) {
   if (g_ctx) return;
+  g_stats_on   = getenv("ACE_B200_STATS") && getenv("ACE_B200_STATS")[0] >= '1';
+  g_stats_sync = g_stats_on && getenv("ACE_B200_STATS")[0] == '2';
   if (!Get_context_params) die("Get_context_params() not linked (emitted unit missing)");
   CKKS_PARAMS* p = Get_context_params();
   size_t parts = p->_num_q_parts;
@@ -251,6 +304,8 @@ API void Prepare_context(void) {
            p->_provider, p->_poly_degree, p->_sec_level, p->_mul_depth, p->_first_mod_size,
            p->_scaling_mod_size, parts, g_ctx->K, p->_num_rot_idx, p->_hamming_weight);
     g_ev = new Evaluator(g_ctx);
+    g_queue = new OpQueue(&g_ctx->T, g_ctx->stream, &g_ctx->launches);
+    g_no_batch = getenv("ACE_B200_NO_BATCH") && getenv("ACE_B200_NO_BATCH")[0] == '1';
     const char* no_keys = getenv("ACE_B200_NO_KEYGEN");  // parity runs import the oracle's keys
     const bool  own_keys = !(no_keys && no_keys[0] == '1');
     const char* seed_env = getenv("ACE_B200_SEED");
@@ -270,9 +325,19 @@ API void Prepare_context(void) {
 
 API void Finalize_context(void) {
   if (!g_ctx) return;
+  if (g_stats_on) {
+    printf("[ace_b200 stats] kernels launched: %zu; limb-op batches %zu for %zu ops\n",
+           g_ctx->launches, g_queue->batches, g_queue->ops);
+    for (int i = 0; i < ST_COUNT; i++)
+      printf("[ace_b200 stats] %-22s calls %9llu  host time %8.3f s\n", g_stats[i].name,
+             (unsigned long long)g_stats[i].calls, g_stats[i].secs);
+  }
   for (auto& kv : g_swk) { delete[] kv.second->pk0; delete[] kv.second->pk1; delete kv.second; }
   g_swk.clear();
   Pt_mgr_fini();
+  if (g_queue) g_queue->flush();
+  delete g_queue;
+  g_queue = nullptr;
   delete g_ev;
   g_ev = nullptr;
   delete g_ctx;
@@ -281,12 +346,12 @@ API void Finalize_context(void) {
   g_mod = nullptr;
 }
 
-API uint32_t Degree(void) { return ctx()->N; }
-API double   Get_default_sc(void) { return (double)((u64)1 << ctx()->params.scaling_mod_size); }
-API size_t   Get_q_parts(void) { return ctx()->dnum; }
-API size_t   Get_p_cnt(void) { return ctx()->K; }
-API MODULUS* Q_modulus(void) { ctx(); return g_mod; }
-API MODULUS* P_modulus(void) { return g_mod + ctx()->L; }
+API uint32_t Degree(void) { return ctx_nf()->N; }
+API double   Get_default_sc(void) { return (double)((u64)1 << ctx_nf()->params.scaling_mod_size); }
+API size_t   Get_q_parts(void) { return ctx_nf()->dnum; }
+API size_t   Get_p_cnt(void) { return ctx_nf()->K; }
+API MODULUS* Q_modulus(void) { ctx_nf(); return g_mod; }
+API MODULUS* P_modulus(void) { return g_mod + ctx_nf()->L; }
 
 // =========================================================================== tensors / IO
 API TENSOR* Alloc_tensor(size_t n, size_t c, size_t h, size_t w, const double* val) {
@@ -420,7 +485,7 @@ API void Tm_taken(const char* msg) {  // rt_stat.c:23-28; a stream sync makes it
 API POLY Alloc_poly(uint32_t degree, size_t q_primes, bool extend_p) {  // poly_eval.h:29-37
   if (q_primes == 0) die("Alloc_poly: q primes should not be NULL");
   POLY p = (POLY)calloc(1, sizeof(POLYNOMIAL));
-  alloc_poly_data(p, degree, q_primes, extend_p ? ctx()->K : 0);
+  alloc_poly_data(p, degree, q_primes, extend_p ? ctx_nf()->K : 0);
   p->_is_ntt = true;
   return p;
 }
@@ -431,12 +496,13 @@ API void Free_poly(POLY poly) {
 }
 API void Copy_poly(POLY res, POLY poly) { copy_polynomial(res, poly); }
 API void Set_coeffs(POLY dst, uint32_t level, uint32_t degree, int64_t* src) {  // poly_eval.h:74-79
+  StatScope ss(ST_COPY);
   guard([&] {
     ACE_CUDA(cudaMemcpyAsync(dst->_data + (size_t)level * degree, src, sizeof(int64_t) * degree,
                              cudaMemcpyDeviceToDevice, ctx()->stream));
   });
 }
-API size_t Num_decomp(POLY poly) { return ctx()->num_decomp(poly->_num_primes); }
+API size_t Num_decomp(POLY poly) { return ctx_nf()->num_decomp(poly->_num_primes); }
 
 API void Ace_download_poly(int64_t* host_dst, POLY poly) {
   guard([&] { ctx()->download(U(host_dst), U(poly->_data), poly->_num_primes + poly->_num_primes_p); });
@@ -448,22 +514,27 @@ API void Ace_upload_poly(POLY poly, const int64_t* host_src) {
   });
 }
 
+// Hw_modadd / Hw_modmul / Hw_rotate (poly_arith.c:14-56) are recorded and issued in batches
+// (op_queue.h); ACE_B200_NO_BATCH=1 launches one kernel per call instead.
 API int64_t* Hw_modadd(int64_t* res, int64_t* a, int64_t* b, MODULUS* m, uint32_t degree) {
-  Context* c = ctx();
-  launch_ew(c->T, EW_ADD, U(res), U(a), U(b), mod_index(m), 1, c->stream);
-  c->launches++;
+  StatScope ss(ST_ADD);
+  ctx_nf();
+  g_queue->push_ew(EW_ADD, U(res), U(a), U(b), mod_index(m));
+  if (g_no_batch) g_queue->flush();
   return res + degree;
 }
 API int64_t* Hw_modmul(int64_t* res, int64_t* a, int64_t* b, MODULUS* m, uint32_t degree) {
-  Context* c = ctx();
-  launch_ew(c->T, EW_MUL, U(res), U(a), U(b), mod_index(m), 1, c->stream);
-  c->launches++;
+  StatScope ss(ST_MUL);
+  ctx_nf();
+  g_queue->push_ew(EW_MUL, U(res), U(a), U(b), mod_index(m));
+  if (g_no_batch) g_queue->flush();
   return res + degree;
 }
 API int64_t* Hw_rotate(int64_t* res, int64_t* a, int64_t* order, MODULUS* m, uint32_t degree) {
-  Context* c = ctx();
-  launch_gather(c->T, U(res), U(a), order, mod_index(m), 1, c->stream);
-  c->launches++;
+  StatScope ss(ST_ROT);
+  ctx_nf();
+  g_queue->push_gather(U(res), U(a), order, mod_index(m));
+  if (g_no_batch) g_queue->flush();
   return res + degree;
 }
 
@@ -490,16 +561,19 @@ API POLY Mod_up(POLY new_poly, POLY old_poly, uint32_t part) {  // poly_eval.c:1
   return new_poly;
 }
 API POLY Decomp_modup(POLY res, POLY poly, uint32_t part) {  // poly_eval.c:28-34
+  StatScope ss(ST_MODUP);
   guard([&] { ctx()->decomp_modup(U(res->_data), U(poly->_data), (u32)poly->_num_primes, part); });
   res->_is_ntt = true;
   return res;
 }
 API POLY Mod_down(POLY res, POLY poly) {  // poly_eval.c:36-41
+  StatScope ss(ST_MODDOWN);
   guard([&] { ctx()->mod_down(U(res->_data), U(poly->_data), (u32)res->_num_primes); });
   res->_is_ntt = poly->_is_ntt;
   return res;
 }
 API POLY Rescale(POLY res, POLY poly) {  // poly_eval.c:43-49
+  StatScope ss(ST_RESCALE);
   guard([&] { ctx()->rescale(U(res->_data), U(poly->_data), (u32)poly->_num_primes); });
   res->_is_ntt     = true;
   res->_num_primes = res->_num_primes - 1;  // Mod_down_q_primes
@@ -507,14 +581,14 @@ API POLY Rescale(POLY res, POLY poly) {  // poly_eval.c:43-49
 }
 
 // =========================================================================== keys
-API uint32_t Auto_idx(int32_t rot_idx) { return ctx()->auto_index(rot_idx); }
+API uint32_t Auto_idx(int32_t rot_idx) { return ctx_nf()->auto_index(rot_idx); }
 API int64_t* Auto_order(int32_t rot_idx) {
   int64_t* r = nullptr;
-  guard([&] { r = const_cast<int64_t*>(ctx()->auto_order(ctx()->auto_index(rot_idx))); });
+  guard([&] { r = const_cast<int64_t*>(ctx_nf()->auto_order(ctx_nf()->auto_index(rot_idx))); });
   return r;
 }
 API SW_KEY Swk(bool is_rot, int32_t rot_idx) {
-  Context* c = ctx();
+  Context* c = ctx_nf();
   if (!is_rot) {
     if (!c->relin_key.k0) die("relinearisation key missing");
     return wrap_key(0, &c->relin_key);
@@ -777,6 +851,7 @@ API CIPHER Encrypt(CIPHER res, PLAIN plain) {  // cipher_eval.c:406-409
 
 // Bootstrap (cipher_eval.c:366-404) -> Evaluator::bootstrap
 API CIPHER Bootstrap(CIPHER res, CIPHER ciph, uint32_t level_after_bts) {
+  StatScope ss(ST_BTS);
   Context* c = ctx();
   if (ciph->_c0_poly._num_primes_p != 0) die("Bootstrap: extended ciphertext");
   guard([&] {
@@ -820,6 +895,7 @@ static void init_plain(PLAIN plain, uint32_t slots, size_t level, double sf, uin
 
 static void encode_plain(PLAIN plain, const double* vals, size_t len, uint32_t sc_degree,
                          uint32_t level) {
+  StatScope ss(ST_ENCODE);
   Context* c = ctx();
   if (level == 0) level = (uint32_t)c->L;
   double sf = Get_default_sc();

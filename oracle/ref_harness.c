@@ -52,15 +52,56 @@ static void Pin_random(void) {
   Prng->_buffer_idx = 0;
 }
 
-/* ---- callbacks the runtime expects from the emitted translation unit ---- */
-static CKKS_PARAMS* Harness_params = NULL;
-CKKS_PARAMS*        Get_context_params() { return Harness_params; }
-RT_DATA_INFO*       Get_rt_data_info() { return NULL; }
-int                 Get_input_count() { return 0; }
-int                 Get_output_count() { return 0; }
-DATA_SCHEME*        Get_encode_scheme(int idx) { (void)idx; return NULL; }
-DATA_SCHEME*        Get_decode_scheme(int idx) { (void)idx; return NULL; }
-bool                Main_graph() { return true; }
+/* ---- callbacks the runtime expects from the emitted translation unit ----
+ * Stand-alone (primitive tests) they answer from Harness_params; when an emitted model unit
+ * (oracle/_ref/<model>_ref.so, built from the reference's .onnx.inc with these entry points
+ * renamed) registers itself through ref_set_callbacks they forward to it. */
+typedef struct {
+  CKKS_PARAMS* (*get_params)(void);
+  RT_DATA_INFO* (*get_data_info)(void);
+  bool (*main_graph)(void);
+  DATA_SCHEME* (*enc_scheme)(int);
+  DATA_SCHEME* (*dec_scheme)(int);
+} REF_CALLBACKS;
+static REF_CALLBACKS Cb;
+static CKKS_PARAMS*  Harness_params = NULL;
+static RT_DATA_INFO  Data_info_override;
+static char          Data_file_override[4096];
+
+void ref_set_callbacks(void* get_params, void* get_data_info, void* main_graph, void* enc_scheme,
+                       void* dec_scheme) {
+  Cb.get_params    = (CKKS_PARAMS * (*)(void)) get_params;
+  Cb.get_data_info = (RT_DATA_INFO * (*)(void)) get_data_info;
+  Cb.main_graph    = (bool (*)(void))main_graph;
+  Cb.enc_scheme    = (DATA_SCHEME * (*)(int)) enc_scheme;
+  Cb.dec_scheme    = (DATA_SCHEME * (*)(int)) dec_scheme;
+}
+CKKS_PARAMS* Get_context_params() { return Cb.get_params ? Cb.get_params() : Harness_params; }
+RT_DATA_INFO* Get_rt_data_info() {
+  if (!Cb.get_data_info) return NULL;
+  RT_DATA_INFO* info = Cb.get_data_info();
+  if (info == NULL || Data_file_override[0] == 0) return info;
+  Data_info_override            = *info; /* emitted paths are absolute (/app/release/...) */
+  Data_info_override._file_name = Data_file_override;
+  return &Data_info_override;
+}
+int          Get_input_count() { return Cb.main_graph ? 1 : 0; }
+int          Get_output_count() { return Cb.main_graph ? 1 : 0; }
+DATA_SCHEME* Get_encode_scheme(int idx) { return Cb.enc_scheme ? Cb.enc_scheme(idx) : NULL; }
+DATA_SCHEME* Get_decode_scheme(int idx) { return Cb.dec_scheme ? Cb.dec_scheme(idx) : NULL; }
+bool         Main_graph() { return Cb.main_graph ? Cb.main_graph() : true; }
+
+/* whole-model runs: Prepare_context with the emitted unit's own parameters, rotation
+ * indices and (overridden) weight file; randomness pinned first */
+int ref_init_emitted(const char* data_file) {
+  if (Context != NULL) return -1;
+  if (!Cb.get_params || !Cb.main_graph) return -2;
+  Data_file_override[0] = 0;
+  if (data_file) strncpy(Data_file_override, data_file, sizeof(Data_file_override) - 1);
+  Pin_random();
+  Prepare_context();
+  return 0;
+}
 
 /* ---- context ------------------------------------------------------------ */
 int ref_init(uint32_t degree, size_t mul_depth, size_t first_mod_size,
@@ -402,6 +443,32 @@ void ref_ct_mul_plain(REF_CT* res, const REF_CT* a, int64_t* pt, double pt_scale
   Mul_plain(z, &x, &p);
   Unwrap_ct(res, z);
   Free_ciphertext(z);
+}
+
+/* ---- whole-model runs (the emitted Main_graph through the reference's own driver API,
+ *      ant/src/rtlib/rtlib.c:41-87, common/src/rt_lib.c:16-20) -------------------------- */
+void* Io_get_input(const char* name, size_t idx);
+void* Io_get_output(const char* name, size_t idx);
+
+void ref_prepare_input(const double* vals, size_t n, size_t c, size_t h, size_t w,
+                       const char* name) {
+  TENSOR* t = Alloc_tensor(n, c, h, w, vals);
+  Prepare_input(t, name);
+  Free_tensor(t);
+}
+static int Copy_io(REF_CT* out, CIPHERTEXT* ct) {
+  if (ct == NULL) return -1;
+  Unwrap_ct(out, ct);
+  return (int)out->level;
+}
+/* copies (does not consume) the pending input / produced output ciphertext; buffers: L limbs */
+int  ref_peek_input(const char* name, REF_CT* out) { return Copy_io(out, (CIPHERTEXT*)Io_get_input(name, 0)); }
+int  ref_peek_output(const char* name, REF_CT* out) { return Copy_io(out, (CIPHERTEXT*)Io_get_output(name, 0)); }
+void ref_run_main_graph(void) { Run_main_graph(); }
+void ref_handle_output(const char* name, double* out, size_t n) {
+  double* r = Handle_output(name);
+  memcpy(out, r, n * sizeof(double));
+  free(r);
 }
 
 /* bootstrap (a11); res buffers must hold level_after_bts(+) limbs: use num_q limbs */

@@ -11,6 +11,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_EX = "/root/reference/fhe-cmplr/rtlib/ant/example"
 OUT = os.path.join(ROOT, "tests", "_emitted_bin")
+REF_DS = "/root/reference/fhe-cmplr/rtlib/ant/dataset"
+# ACE-emitted CIFAR ResNets checked in by the reference
+MODELS = ["resnet20_cifar10_pre", "resnet32_cifar100_pre", "resnet56_cifar10_pre",
+          "resnet110_cifar10_train"]
 EXAMPLES = ["add", "add_const", "mul_const", "rotate", "rotate_02", "relin", "relin_02",
             "gemm", "gemm_02", "conv2d", "avg_pool", "relu"]
 
@@ -29,6 +33,33 @@ def build_all(verbose=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             print("FAILED", name, r.stderr[:2000])
+        else:
+            built.append(exe)
+            if verbose:
+                print("built", exe)
+    built += build_models(verbose)
+    return built
+
+
+def build_models(verbose=False, models=MODELS):
+    """the emitted ResNet translation units, #included unmodified by tests/emitted/resnet_driver.c"""
+    built = []
+    drv = os.path.join(ROOT, "tests", "emitted", "resnet_driver.c")
+    for m in models:
+        inc = os.path.join(REF_DS, m + ".onnx.inc")
+        if not os.path.exists(inc):
+            continue
+        exe = os.path.join(OUT, m)
+        if os.path.exists(exe) and os.path.getmtime(exe) > max(os.path.getmtime(drv), os.path.getmtime(inc)):
+            built.append(exe)
+            continue
+        cmd = ["gcc", "-O1", "-w", "-std=gnu11", "-DMODEL_INC=\"%s\"" % inc, "-I",
+               os.path.join(ROOT, "include"), drv, "-o", exe, "-L",
+               os.path.join(ROOT, "ace_compiler_b200"), "-lace_b200",
+               "-Wl,-rpath,$ORIGIN/../../ace_compiler_b200", "-lm"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            print("FAILED", m, r.stderr[:2000])
         else:
             built.append(exe)
             if verbose:

@@ -263,6 +263,68 @@ class RefLib:
         return self._binary(self.lib.ref_ct_mul, a, b)
 
 
+class RefModel:
+    """An ACE-emitted model unit (oracle/_ref/<model>_ref.so) running on the reference runtime,
+    driven through the reference's own Prepare_context / Prepare_input / Run_main_graph /
+    Handle_output.  One per process.  Randomness is pinned by the harness, so keys, the
+    encrypted input and every output limb are reproducible."""
+
+    def __init__(self, model, data_file):
+        self.lib = L = C.CDLL(REF_SO, mode=C.RTLD_GLOBAL)
+        self.unit = C.CDLL(os.path.join(os.path.dirname(REF_SO), model + "_ref.so"))
+        L.ref_set_callbacks.argtypes = [vp] * 5
+        self.unit.model_register.argtypes = [vp]
+        self.unit.model_register(C.cast(L.ref_set_callbacks, vp))
+        L.ref_init_emitted.argtypes = [C.c_char_p]
+        rc = L.ref_init_emitted(data_file.encode())
+        if rc != 0:
+            raise RuntimeError("ref_init_emitted failed: %d" % rc)
+        RefLib._inited = ("model", model)
+        for f in ("ref_num_q", "ref_num_p", "ref_num_parts", "ref_part_size"):
+            getattr(L, f).restype = sz
+        L.ref_prepare_input.argtypes = [vp, sz, sz, sz, sz, C.c_char_p]
+        L.ref_peek_input.argtypes = [C.c_char_p, vp]
+        L.ref_peek_output.argtypes = [C.c_char_p, vp]
+        L.ref_handle_output.argtypes = [C.c_char_p, vp, sz]
+        L.ref_swk_export.argtypes = [C.c_int, i32, u32, C.c_int, vp]
+        L.ref_swk_export_auto.argtypes = [u32, u32, C.c_int, vp]
+        L.ref_decrypt.argtypes = [vp, vp]
+        self.N, self.L, self.K = L.ref_degree(), L.ref_num_q(), L.ref_num_p()
+        self.parts = L.ref_num_parts()
+
+    swk = RefLib.swk
+    swk_auto = RefLib.swk_auto
+    _rc = RefLib._rc
+    decrypt = RefLib.decrypt
+
+    def _peek(self, fn, name):
+        out = Ct(np.zeros((self.L, self.N), np.int64), np.zeros((self.L, self.N), np.int64), 0, 0, 0.0)
+        rc = RefCt(_p(out.c0), _p(out.c1), self.L, 0, 0, 0.0)
+        if fn(name.encode(), C.byref(rc)) < 0:
+            raise RuntimeError("no ciphertext named " + name)
+        out.c0, out.c1 = out.c0[: rc.level], out.c1[: rc.level]
+        out.slots, out.sf_degree, out.scale = rc.slots, rc.sf_degree, rc.scale
+        return out
+
+    def prepare_input(self, image, name="input"):
+        v = np.ascontiguousarray(image, dtype=np.float64)
+        self.lib.ref_prepare_input(_p(v), 1, 3, 32, 32, name.encode())
+
+    def peek_input(self, name="input"):
+        return self._peek(self.lib.ref_peek_input, name)
+
+    def run(self):
+        self.lib.ref_run_main_graph()
+
+    def peek_output(self, name="output"):
+        return self._peek(self.lib.ref_peek_output, name)
+
+    def handle_output(self, n, name="output"):
+        out = np.zeros(n)
+        self.lib.ref_handle_output(name.encode(), _p(out), n)
+        return out
+
+
 class PortLib:
     def __init__(self, N, depth, q0_bits, sf_bits, parts):
         L = self.lib = C.CDLL(PORT_SO)
