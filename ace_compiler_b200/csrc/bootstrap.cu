@@ -442,12 +442,16 @@ void Evaluator::rotate_iteration(Ct& result, BtsPrecom& pc,
       const int64_t* order = c->auto_order(c->auto_index(val));
       launch_gather_basis(c->T, r0, acc, order, ext_b, c->stream);
       launch_gather_basis(c->T, r1, acc + WN, order, ext_b, c->stream);
+      c->tr(Context::TR_LIMB_MUL, 0, nq);
+      c->tr(Context::TR_LIMB_ADD, 0, nq);
+      c->tr(Context::TR_LIMB_ROT, 0, 2 * W);
       c->launches += 3;
     } else {  // Switch_key_ext: lift (c0, c1) by P, P limbs are zero
       launch_mul_scalar(c->T, r0, result.c0, c->pmodq_, c->pmodq_sh_, 0, nq, c->stream);
       launch_mul_scalar(c->T, r1, result.c1, c->pmodq_, c->pmodq_sh_, 0, nq, c->stream);
       ACE_CUDA(cudaMemsetAsync(r0 + (size_t)nq * N, 0, (size_t)K * N * sizeof(u64), c->stream));
       ACE_CUDA(cudaMemsetAsync(r1 + (size_t)nq * N, 0, (size_t)K * N * sizeof(u64), c->stream));
+      c->tr(Context::TR_LIMB_MUL, 0, 2 * nq);
       c->launches += 2;
     }
   }
@@ -474,6 +478,8 @@ void Evaluator::rotate_iteration(Ct& result, BtsPrecom& pc,
     }
     u64 *in0 = i == 0 ? first : inner, *in1 = i == 0 ? outer + WN : inner + WN;
     launch_pt_dot(c->T, in0, in1, da, ext_b, c->stream);
+    c->tr(Context::TR_LIMB_MUL, 0, 2ull * da.n * W);   // Mul_plaintext per rotation ...
+    c->tr(Context::TR_LIMB_ADD, 0, 2ull * (da.n - 1) * W);  // ... and Add_ciphertext
     c->launches++;
     if (i == 0) continue;  // first = inner.c0, outer = (0, inner.c1)
     int32_t val = rout[step][i];
@@ -495,10 +501,13 @@ void Evaluator::rotate_iteration(Ct& result, BtsPrecom& pc,
         launch_ew_basis(c->T, EW_ADD, outer, outer, tmp, ext_b, c->stream);
       }
       launch_ew_basis(c->T, EW_ADD, outer + WN, outer + WN, tmp + WN, ext_b, c->stream);
+      c->tr(Context::TR_LIMB_ROT, 0, 3 * W);
+      c->tr(Context::TR_LIMB_ADD, 0, 3 * W);
       c->launches += 6;
     } else {
       launch_ew_basis(c->T, EW_ADD, first, first, inner, ext_b, c->stream);
       launch_ew_basis(c->T, EW_ADD, outer + WN, outer + WN, inner + WN, ext_b, c->stream);
+      c->tr(Context::TR_LIMB_ADD, 0, 2 * W);
       c->launches += 2;
     }
   }
@@ -509,6 +518,7 @@ void Evaluator::rotate_iteration(Ct& result, BtsPrecom& pc,
     launch_ew_basis(c->T, EW_ADD, outer, outer, first, ext_b, c->stream);
     c->launches++;
   }
+  c->tr(Context::TR_LIMB_ADD, 0, W);
   (void)q_b;
   c->mod_down_pair(result.c0, result.c1, outer, outer + WN, nq, nullptr);
   const double delta = (double)((u64)1 << c->params.scaling_mod_size);
@@ -597,6 +607,8 @@ void Evaluator::eval_bootstrap(Ct& res, Ct& in, u32 raise_level, BtsPrecom& pc) 
   c->intt_from(coef + N, raised.c1, 0, 1);
   launch_mod_raise(c->T, nw.c0, coef, raise_level, c->stream);
   launch_mod_raise(c->T, nw.c1, coef + N, raise_level, c->stream);
+  c->tr(Context::TR_LIMB_NTT, 0, 2);         // the two INTTs above (intt_from does not count)
+  c->tr(Context::TR_LIMB_ADD, 0, 2 * raise_level);  // Switch_modulus pass ~ one limb add each
   c->launches += 2;
   c->ntt(nw.c0, 0, raise_level);
   c->ntt(nw.c1, 0, raise_level);

@@ -242,37 +242,94 @@ void Context::decrypt(u64* pt, const u64* c0, const u64* c1, u32 level) {
 // contraction): every operation is an explicit _rn intrinsic.
 struct cplx { double re, im; };
 
-// one stage of Embedding_inv (ntt.c:725-747): (a, b) -> (a + b, (a - b) * w)
-__global__ void emb_inv_stage_kernel(cplx* __restrict__ v, const cplx* __restrict__ tw,
-                                     u32 slots, u32 logm) {
-  const u32 num2 = 1u << (logm - 1);
-  for (u32 p = blockIdx.x * blockDim.x + threadIdx.x; p < slots / 2;
-       p += gridDim.x * blockDim.x) {
-    const u32 i  = p & (num2 - 1);
-    const u32 lo = ((p >> (logm - 1)) << logm) | i;
-    const cplx a = v[lo], b = v[lo + num2], w = tw[num2 - 1 + i];
-    cplx s, d, r;
-    s.re = __dadd_rn(a.re, b.re);
-    s.im = __dadd_rn(a.im, b.im);
-    d.re = __dsub_rn(a.re, b.re);
-    d.im = __dsub_rn(a.im, b.im);
-    r.re = __dsub_rn(__dmul_rn(d.re, w.re), __dmul_rn(d.im, w.im));
-    r.im = __dadd_rn(__dmul_rn(d.re, w.im), __dmul_rn(d.im, w.re));
-    v[lo]        = s;
-    v[lo + num2] = r;
+// Embedding_inv (ntt.c:713-753): log2(slots) Gentleman-Sande stages (a, b) -> (a + b, (a - b) w),
+// w = rou[(idx_mod - rot_group[i] % idx_mod) * gap] folded into tw[num2 - 1 + i].  Each
+// butterfly performs exactly the reference's operations (unfused _rn arithmetic), so fusing
+// stages into two launches does not change a single bit:
+//   emb_inv_strided<SA>: the top SA = log2(slots) - 12 stages in registers (a thread owns the
+//                        2^SA elements of one column at stride 4096), input conversion fused in;
+//   emb_inv_tile:        the remaining <= 12 stages on a contiguous tile in shared memory.
+enum SrcKind { SRC_F32 = 0, SRC_F64 = 1, SRC_C64 = 2 };
+
+__device__ __forceinline__ cplx emb_load(const void* src, int kind, u32 idx, u32 len) {
+  if (idx >= len) return cplx{0.0, 0.0};
+  if (kind == SRC_F32) return cplx{(double)reinterpret_cast<const float*>(src)[idx], 0.0};
+  if (kind == SRC_F64) return cplx{reinterpret_cast<const double*>(src)[idx], 0.0};
+  return reinterpret_cast<const cplx*>(src)[idx];
+}
+
+__device__ __forceinline__ void emb_butterfly(cplx& a, cplx& b, const cplx w) {
+  cplx s, d;
+  s.re = __dadd_rn(a.re, b.re);
+  s.im = __dadd_rn(a.im, b.im);
+  d.re = __dsub_rn(a.re, b.re);
+  d.im = __dsub_rn(a.im, b.im);
+  a    = s;
+  b.re = __dsub_rn(__dmul_rn(d.re, w.re), __dmul_rn(d.im, w.im));
+  b.im = __dadd_rn(__dmul_rn(d.re, w.im), __dmul_rn(d.im, w.re));
+}
+
+constexpr u32 kEmbTileLog = 12, kEmbTile = 1u << kEmbTileLog;
+
+template <int SA>
+__global__ void __launch_bounds__(128) emb_inv_strided(cplx* __restrict__ v,
+                                                       const cplx* __restrict__ tw,
+                                                       const void* __restrict__ src, int kind,
+                                                       u32 len, u32 logslots) {
+  constexpr int R = 1 << SA;
+  const u32 stride = kEmbTile, col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= stride) return;
+  cplx x[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) x[r] = emb_load(src, kind, r * stride + col, len);
+#pragma unroll
+  for (int s = 0; s < SA; s++) {
+    const u32 num2 = 1u << (logslots - s - 1);  // half the butterfly span of this stage
+    const int tr   = R >> (s + 1);
+#pragma unroll
+    for (int p = 0; p < R / 2; p++) {
+      const int lo = (p / tr) * 2 * tr + (p % tr);
+      const u32 i  = ((u32)lo * stride + col) & (num2 - 1);
+      emb_butterfly(x[lo], x[lo + tr], tw[num2 - 1 + i]);
+    }
   }
+#pragma unroll
+  for (int r = 0; r < R; r++) v[r * stride + col] = x[r];
+}
+
+// tile = min(slots, 4096) elements; from_src: no strided phase ran, convert the input here
+__global__ void __launch_bounds__(512) emb_inv_tile(cplx* __restrict__ v,
+                                                    const cplx* __restrict__ tw,
+                                                    const void* __restrict__ src, int kind,
+                                                    u32 len, u32 logtile, int from_src) {
+  extern __shared__ double emb_sm[];
+  cplx* t = reinterpret_cast<cplx*>(emb_sm);
+  const u32 tile = 1u << logtile, base = blockIdx.x * tile;
+  for (u32 e = threadIdx.x; e < tile; e += blockDim.x)
+    t[e] = from_src ? emb_load(src, kind, base + e, len) : v[base + e];
+  __syncthreads();
+  for (u32 logm = logtile; logm > 0; logm--) {
+    const u32 num2 = 1u << (logm - 1);
+    for (u32 p = threadIdx.x; p < tile / 2; p += blockDim.x) {
+      const u32 i  = p & (num2 - 1);
+      const u32 lo = ((p >> (logm - 1)) << logm) | i;
+      emb_butterfly(t[lo], t[lo + num2], tw[num2 - 1 + i]);
+    }
+    __syncthreads();
+  }
+  for (u32 e = threadIdx.x; e < tile; e += blockDim.x) v[base + e] = t[e];
 }
 
 // bit-reverse, divide by slots, scale by Delta, round, spread with `gap`, reduce into every limb
 // (ckks_encoder.c:247-263 + polynomial.c:362-392); powp[l] = Delta^(sf_degree-1) mod q_l or 0
 __global__ void emb_round_rns_kernel(DeviceTables T, LimbBatch b, const cplx* __restrict__ v,
                                      u32 slots, u32 logslots, double delta,
-                                     const u64* __restrict__ powp) {
+                                     const ScalarPack powp, int use_pow) {
   const u32     limb = blockIdx.y;
   const Modulus m    = T.mod[b.g[limb]];
   u64*          out  = b.base + (size_t)b.slot[limb] * T.N;
   const u32     gap  = T.N / (2 * slots);
-  const u64     pw   = powp ? powp[limb] : 0;
+  const u64     pw   = use_pow ? powp.v[limb] : 0;
   for (u32 n = blockIdx.x * blockDim.x + threadIdx.x; n < T.N; n += gridDim.x * blockDim.x) {
     u64 res = 0;
     if (n % gap == 0) {
@@ -294,10 +351,10 @@ __global__ void emb_round_rns_kernel(DeviceTables T, LimbBatch b, const cplx* __
   }
 }
 
-__global__ void fill_limb_kernel(DeviceTables T, LimbBatch b, const u64* __restrict__ val) {
+__global__ void fill_limb_kernel(DeviceTables T, LimbBatch b, const ScalarPack val) {
   const u32 limb = blockIdx.y;
   u64*      out  = b.base + (size_t)b.slot[limb] * T.N;
-  const u64 v    = val[limb];
+  const u64 v    = val.v[limb];
   for (u32 n = blockIdx.x * blockDim.x + threadIdx.x; n < T.N; n += gridDim.x * blockDim.x)
     out[n] = v;
 }
@@ -346,53 +403,75 @@ void Context::encode_cplx(u64* out, const std::complex<double>* vals, size_t len
 }
 void Context::encode_any(u64* out, const double* vals, const std::complex<double>* cvals,
                          size_t len, u32 level, u32 slots, u32 sf_degree, u32 p_cnt) {
+  // host message -> device staging (stream-ordered; a pageable source is staged by the driver
+  // before the call returns, so the caller's buffer is free again immediately)
+  const size_t bytes = len * (cvals ? sizeof(cplx) : sizeof(double));
+  void* d = nullptr;
+  ACE_CUDA(cudaMallocAsync(&d, bytes ? bytes : 16, stream));
+  if (bytes)
+    ACE_CUDA(cudaMemcpyAsync(d, cvals ? (const void*)cvals : (const void*)vals, bytes,
+                             cudaMemcpyHostToDevice, stream));
+  encode_dev(out, d, cvals ? SRC_C64 : SRC_F64, len, level, slots, sf_degree, p_cnt);
+  ACE_CUDA(cudaFreeAsync(d, stream));
+}
+
+// Encode_impl on a message that already lives in HBM (kind: 0 float32, 1 float64, 2 complex)
+void Context::encode_dev(u64* out, const void* dev_src, int kind, size_t len, u32 level,
+                         u32 slots, u32 sf_degree, u32 p_cnt) {
   init_encoder();
   if (slots == 0) slots = N / 2;
   if (level == 0) level = (u32)L;
+  tr(TR_ENCODE, level + p_cnt);
   if (len > slots || slots > N / 2 || (slots & (slots - 1)))
     throw std::runtime_error("encode: bad slot count");
   if (level > L || sf_degree < 1 || p_cnt > K) throw std::runtime_error("encode: bad level");
   u32 logslots = 0;
   while ((1u << logslots) < slots) logslots++;
-  cplx* hv = (cplx*)enc_host_;
   cplx* dv = (cplx*)enc_buf_;
-  ACE_CUDA(cudaStreamSynchronize(stream));  // enc_host_ may still feed a previous encode
-  if (cvals) {
-    for (size_t i = 0; i < slots; i++)
-      hv[i] = i < len ? cplx{cvals[i].real(), cvals[i].imag()} : cplx{0.0, 0.0};
-  } else {
-    for (size_t i = 0; i < slots; i++) hv[i] = cplx{i < len ? vals[i] : 0.0, 0.0};
-  }
-  ACE_CUDA(cudaMemcpyAsync(dv, hv, slots * sizeof(cplx), cudaMemcpyHostToDevice, stream));
   const cplx* tw = (const cplx*)enc_tw_;
-  for (u32 logm = logslots; logm > 0; logm--) {
-    u32 blocks = std::max<u32>(1, std::min<u32>(slots / 2 / 256, 1024));
-    emb_inv_stage_kernel<<<blocks, 256, 0, stream>>>(dv, tw, slots, logm);
+  const u32 logtile = logslots < kEmbTileLog ? logslots : kEmbTileLog;
+  const int sa = (int)(logslots - logtile);
+  if (sa > 0) {
+    dim3 grid(kEmbTile / 128);
+    switch (sa) {
+      case 1: emb_inv_strided<1><<<grid, 128, 0, stream>>>(dv, tw, dev_src, kind, (u32)len, logslots); break;
+      case 2: emb_inv_strided<2><<<grid, 128, 0, stream>>>(dv, tw, dev_src, kind, (u32)len, logslots); break;
+      case 3: emb_inv_strided<3><<<grid, 128, 0, stream>>>(dv, tw, dev_src, kind, (u32)len, logslots); break;
+      case 4: emb_inv_strided<4><<<grid, 128, 0, stream>>>(dv, tw, dev_src, kind, (u32)len, logslots); break;
+      default: throw std::runtime_error("encode: slot count too large");
+    }
+  }
+  {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(emb_inv_tile, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(kEmbTile * sizeof(cplx)));
+      attr = true;
+    }
+    const u32 tile = 1u << logtile;
+    emb_inv_tile<<<slots / tile, tile / 2 < 512 ? (tile / 2 ? tile / 2 : 1) : 512,
+                   tile * sizeof(cplx), stream>>>(dv, tw, dev_src, kind, (u32)len, logtile,
+                                                  sa == 0);
   }
   const double delta = (double)((u64)1 << params.scaling_mod_size);
   const u32 nl = level + p_cnt;
   LimbBatch b;
   b.base = out; b.src = nullptr; b.n = nl;
-  std::vector<u64> powp(nl, 0);
+  ScalarPack powp;
   for (u32 l = 0; l < nl; l++) {
     b.slot[l] = (uint16_t)l;
     b.g[l]    = (uint16_t)(l < level ? l : L + (l - level));
+    powp.v[l] = 0;
     if (sf_degree > 1 && l < level) {
       u64 q = mod[l], p = (u64)delta % q;
       for (u32 d = 2; d < sf_degree; d++) p = hm::mulmod(p, (u64)delta % q, q);
-      powp[l] = p;
+      powp.v[l] = p;
     }
   }
-  const u64* dpow = nullptr;
-  if (sf_degree > 1) {
-    ACE_CUDA(cudaMemcpyAsync(enc_pow_, powp.data(), nl * sizeof(u64), cudaMemcpyHostToDevice,
-                             stream));
-    dpow = enc_pow_;
-  }
   emb_round_rns_kernel<<<grid_for(N, nl), 256, 0, stream>>>(T, b, dv, slots, logslots, delta,
-                                                           dpow);
+                                                           powp, sf_degree > 1 ? 1 : 0);
   launch_ntt(T, b, stream);
-  launches += logslots + 1 + ((logN > 12) ? 2 : 1);
+  launches += (sa > 0 ? 1 : 0) + 2 + ((logN > 12) ? 2 : 1);
 }
 
 // Encode_val_at_level (ckks_encoder.c:464-528): constant plaintext, every coefficient of limb
@@ -437,11 +516,10 @@ void Context::encode_value(u64* out, double value, u32 level, u32 sf_degree) {
   init_encoder();
   if (level == 0) level = (u32)L;
   std::vector<u64> res = value_residues(value, level, sf_degree);
-  ACE_CUDA(cudaStreamSynchronize(stream));
-  ACE_CUDA(cudaMemcpyAsync(enc_pow_, res.data(), level * sizeof(u64), cudaMemcpyHostToDevice,
-                           stream));
+  ScalarPack sp;
+  for (u32 i = 0; i < level; i++) sp.v[i] = res[i];
   LimbBatch b = all_limbs(out, 0, level);
-  fill_limb_kernel<<<grid_for(N, level), 256, 0, stream>>>(T, b, enc_pow_);
+  fill_limb_kernel<<<grid_for(N, level), 256, 0, stream>>>(T, b, sp);
   launches++;
 }
 

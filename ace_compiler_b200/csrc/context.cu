@@ -213,7 +213,8 @@ static void copy_limbs(u64* dst, const u64* src, size_t n_limbs, u32 N, cudaStre
 }
 
 // ---------------------------------------------------------------------------- transforms
-void Context::ntt(u64* data, u32 g0, u32 n) {
+void Context::ntt(u64* data, u32 g0, u32 n, bool standalone) {
+  if (standalone) tr(TR_LIMB_NTT, 0, n);
   for (u32 done = 0; done < n; done += kMaxBatch) {
     LimbBatch b;
     b.base = data; b.src = nullptr;
@@ -223,7 +224,8 @@ void Context::ntt(u64* data, u32 g0, u32 n) {
     launches += (logN > 12) ? 2 : 1;
   }
 }
-void Context::intt(u64* data, u32 g0, u32 n) {
+void Context::intt(u64* data, u32 g0, u32 n, bool standalone) {
+  if (standalone) tr(TR_LIMB_NTT, 0, n);
   for (u32 done = 0; done < n; done += kMaxBatch) {
     LimbBatch b;
     b.base = data; b.src = nullptr;
@@ -307,6 +309,7 @@ void Context::decomp_modup(u64* out, const u64* in, u32 num_q, u32 part) {
 // Mod_up (poly_eval.c:19-26): `digit` holds only the digit's own limbs (output of Decomp)
 void Context::modup_from(u64* out, const u64* digit, u32 num_q, u32 part) {
   const ModUpTab& t = modup_tab(num_q, part);
+  tr(TR_MODUP_DIGIT, num_q);
   u64* coef = alloc_limbs(t.n_in, false);
   copy_limbs(out + (size_t)t.start * N, digit, t.n_in, N, stream);
   intt_from(coef, digit, t.start, t.n_in);
@@ -323,6 +326,7 @@ void Context::modup_from(u64* out, const u64* digit, u32 num_q, u32 part) {
 
 // Mod_down (poly_eval.c:36-41).  Unlike the reference the P part of `in` is left intact.
 void Context::mod_down(u64* out, const u64* in, u32 num_q) {
+  tr(TR_MODDOWN_POLY, num_q);
   u64* pc   = alloc_limbs(K, false);
   u64* conv = alloc_limbs(num_q, false);
   intt_from(pc, in + (size_t)num_q * N, (u32)L, (u32)K);
@@ -333,7 +337,7 @@ void Context::mod_down(u64* out, const u64* in, u32 num_q) {
   for (u32 i = 0; i < K; i++) d.g_in[i] = (u16)(L + i);
   for (u32 o = 0; o < num_q; o++) { d.g_out[o] = (u16)o; d.out_slot[o] = (u16)o; }
   launch_base_conv(T, &d, 1, stream);
-  ntt(conv, 0, num_q);
+  ntt(conv, 0, num_q, false);
   launch_moddown_tail(T, out, in, conv, nullptr, pinv_mod_q_, pinv_mod_q_sh_, num_q, stream);
   launches += 2;
   free_limbs(pc);
@@ -343,13 +347,14 @@ void Context::mod_down(u64* out, const u64* in, u32 num_q) {
 // Rescale (poly_eval.c:43-49): out gets num_q - 1 limbs
 void Context::rescale(u64* out, const u64* in, u32 num_q) {
   if (num_q < 2) throw std::runtime_error("Rescale: level not enough");
+  tr(TR_RESCALE_POLY, num_q);
   const u32 l = num_q - 1;
   u64* last = alloc_limbs(1, false);
   u64* tmp  = alloc_limbs(l, false);
   intt_from(last, in + (size_t)l * N, l, 1);
   launch_rescale_pre(T, tmp, last, l, negqlinv_ + (size_t)l * L, negqlinv_sh_ + (size_t)l * L,
                      stream);
-  ntt(tmp, 0, l);
+  ntt(tmp, 0, l, false);
   launch_rescale_post(T, out, in, tmp, qlinv_ + (size_t)l * L, qlinv_sh_ + (size_t)l * L, l,
                       stream);
   launches += 2;
@@ -398,6 +403,7 @@ void Context::import_key_limbs(SwitchKey& key, u32 part, int which, const u64* h
 // themselves and ksw_acc reads them from there.
 void Context::modup_all(u64* ext, const u64* d, u32 num_q) {
   const u32 beta = (u32)num_decomp(num_q), W = num_q + (u32)K;
+  tr(TR_MODUP_DIGIT, num_q, beta);
   u64* coef = alloc_limbs(num_q, false);
   intt_from(coef, d, 0, num_q);
   ConvDesc  descs[6];
@@ -432,6 +438,11 @@ void Context::modup_all(u64* ext, const u64* d, u32 num_q) {
 void Context::ksw_acc(u64* acc0, u64* acc1, const u64* ext, const u64* d, u32 num_q,
                       const SwitchKey& key) {
   if (!key.k0 || !key.k1) throw std::runtime_error("switch key not loaded");
+  {  // the emitted loop: per digit and limb 2 Hw_modmul + 2 Hw_modadd (GEN20:7005-7032)
+    const uint64_t n = 2ull * num_decomp(num_q) * (num_q + K);
+    tr(TR_LIMB_MUL, 0, n);
+    tr(TR_LIMB_ADD, 0, n);
+  }
   launch_ksw_inner(T, acc0, acc1, ext, d, (u32)part_size, key.k0, key.k1,
                    (u32)num_decomp(num_q), num_q, (u32)L, (u32)K, stream);
   launches++;
@@ -442,6 +453,8 @@ void Context::ksw_acc(u64* acc0, u64* acc1, const u64* ext, const u64* d, u32 nu
 void Context::mod_down_pair(u64* out0, u64* out1, const u64* a0, const u64* a1, u32 num_q,
                             const u64* add0) {
   const u32 np = a1 ? 2 : 1;
+  tr(TR_MODDOWN_POLY, num_q, np);
+  if (add0) tr(TR_LIMB_ADD, 0, num_q);
   u64* pc   = alloc_limbs(np * K, false);
   u64* conv = alloc_limbs(np * (size_t)num_q, false);
   ConvDesc md[2];
@@ -494,6 +507,7 @@ void Context::ct_rotate(u64* r0, u64* r1, const u64* c0, const u64* c1, u32 num_
   key_switch(s0, s1, c1, num_q, rot_keys_[k], c0);
   launch_gather(T, r0, s0, order, 0, num_q, stream);
   launch_gather(T, r1, s1, order, 0, num_q, stream);
+  tr(TR_LIMB_ROT, 0, 2 * num_q);
   launches += 2;
   free_limbs(s);
 }
@@ -512,6 +526,8 @@ void Context::ct_mul_relin(u64* r0, u64* r1, const u64* a0, const u64* a1, const
   launch_ew(T, EW_ADD, r1, d1, s1, 0, num_q, stream);
   launch_ew(T, EW_MUL, d2, a0, b0, 0, num_q, stream);
   launch_ew(T, EW_ADD, r0, d2, s0, 0, num_q, stream);
+  tr(TR_LIMB_MUL, 0, 4 * num_q);
+  tr(TR_LIMB_ADD, 0, 3 * num_q);
   launches += 7;
   free_limbs(t);
 }

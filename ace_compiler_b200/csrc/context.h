@@ -76,8 +76,9 @@ class Context {
   u32 gidx(u32 o, u32 num_q) const { return o < num_q ? o : (u32)L + (o - num_q); }
 
   // ---- transforms on `n` consecutive limbs starting at modulus g0
-  void ntt(u64* data, u32 g0, u32 n);
-  void intt(u64* data, u32 g0, u32 n);
+  // standalone = false: part of a larger primitive that the op trace already counts
+  void ntt(u64* data, u32 g0, u32 n, bool standalone = true);
+  void intt(u64* data, u32 g0, u32 n, bool standalone = true);
   void intt_from(u64* dst, const u64* src, u32 g0, u32 n);
 
   // ---- reference polynomial-level API (a5, a6, a8)
@@ -135,6 +136,16 @@ class Context {
 
   size_t launches = 0;  // kernels launched so far (bench.py reports the delta)
 
+  // Op trace: how many reference-granularity primitives the work so far corresponds to, by
+  // class and (where the cost depends on it) by number of Q limbs.  Control flow of emitted
+  // programs is data independent, so the trace of one image is a constant of the model; bench.py
+  // multiplies it with the reference's unit costs measured on the host for the CPU baseline.
+  enum TraceClass { TR_MODUP_DIGIT, TR_MODDOWN_POLY, TR_RESCALE_POLY, TR_ENCODE, TR_LIMB_MUL,
+                    TR_LIMB_ADD, TR_LIMB_ROT, TR_LIMB_NTT, TR_CLASSES };
+  static constexpr int kTraceLevels = 72;
+  uint64_t trace[TR_CLASSES][kTraceLevels] = {};
+  void tr(TraceClass c, u32 level, uint64_t n = 1) { trace[c][level < kTraceLevels ? level : 0] += n; }
+
  private:
   typedef uint16_t u16;
   struct ModUpTab {
@@ -159,6 +170,8 @@ class Context {
                    u32 slots, u32 sf_degree, u32 p_cnt);
   void encode_any(u64* out, const double* vals, const std::complex<double>* cvals, size_t len,
                   u32 level, u32 slots, u32 sf_degree, u32 p_cnt);
+  void encode_dev(u64* out, const void* dev_src, int kind, size_t len, u32 level, u32 slots,
+                  u32 sf_degree, u32 p_cnt);
  private:
   // Rescale tables, row l (dropping q_l), column i < l
   u64 *qlinv_, *qlinv_sh_, *negqlinv_, *negqlinv_sh_;  // [L][L]

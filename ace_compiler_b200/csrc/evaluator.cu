@@ -77,6 +77,7 @@ void Evaluator::add(Ct& res, Ct& a, Ct& b) {
   Basis bs{level, a.np, (u32)c->L};
   launch_ew_basis(c->T, EW_ADD, res.c0, a.c0, b.c0, bs, c->stream);
   launch_ew_basis(c->T, EW_ADD, res.c1, a.c1, b.c1, bs, c->stream);
+  c->tr(Context::TR_LIMB_ADD, 0, 2 * bs.width());
   c->launches += 2;
   res.nq = level;
 }
@@ -88,6 +89,7 @@ void Evaluator::sub(Ct& res, Ct& a, Ct& b) {
   Basis bs{level, 0, (u32)c->L};
   launch_ew_basis(c->T, EW_SUB, res.c0, a.c0, b.c0, bs, c->stream);
   launch_ew_basis(c->T, EW_SUB, res.c1, a.c1, b.c1, bs, c->stream);
+  c->tr(Context::TR_LIMB_ADD, 0, 2 * bs.width());
   c->launches += 2;
   res.nq = level;
 }
@@ -113,6 +115,7 @@ void Evaluator::add_const_sfd(Ct& res, Ct& a, double v, u32 sfd) {
                              cudaMemcpyDeviceToDevice, c->stream));
   }
   launch_add_scalar(c->T, res.c0, a.c0, sp, 0, a.nq, c->stream);
+  c->tr(Context::TR_LIMB_ADD, 0, a.nq);
   c->launches++;
 }
 
@@ -129,6 +132,7 @@ void Evaluator::mul_const(Ct& res, Ct& a, double v) {
   Basis bs{nq, 0, (u32)c->L};
   launch_mul_scalar_pack(c->T, res.c0, a.c0, sp, bs, c->stream);
   launch_mul_scalar_pack(c->T, res.c1, a.c1, sp, bs, c->stream);
+  c->tr(Context::TR_LIMB_MUL, 0, 2 * bs.width());
   c->launches += 2;
   res.sf = sf; res.sfd = sfd; res.slots = slots;
 }
@@ -147,6 +151,7 @@ void Evaluator::mul_integer(Ct& res, Ct& a, u32 power) {
   }
   launch_mul_scalar_pack(c->T, res.c0, a.c0, sp, bs, c->stream);
   launch_mul_scalar_pack(c->T, res.c1, a.c1, sp, bs, c->stream);
+  c->tr(Context::TR_LIMB_MUL, 0, 2 * bs.width());
   c->launches += 2;
 }
 
@@ -164,6 +169,7 @@ void Evaluator::mul_monomial(Ct& res, Ct& a, u32 power) {
   }
   launch_ew(c->T, EW_MUL, res.c0, a.c0, mono, 0, nq, c->stream);
   launch_ew(c->T, EW_MUL, res.c1, a.c1, mono, 0, nq, c->stream);
+  c->tr(Context::TR_LIMB_MUL, 0, 2 * nq);
   c->launches += 3;
   c->free_limbs(mono);
 }

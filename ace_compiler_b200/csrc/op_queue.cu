@@ -54,6 +54,7 @@ void OpQueue::touch(const void* p, int k) {
 void OpQueue::push_ew(EwOp op, u64* r, const u64* a, const u64* b, u32 g) {
   if (gather_mode_ || items_.size() == (size_t)kQueueCap) flush();
   gather_mode_ = false;
+  (op == EW_MUL ? *n_mul_ : *n_add_)++;
   int k = (int)items_.size();
   items_.push_back(EwItem{r, a, b, g, (u32)op});
   parent_.push_back(k);
@@ -69,6 +70,7 @@ void OpQueue::push_gather(u64* r, const u64* a, const int64_t* order, u32 g) {
   // of an earlier gather in the batch, and no destination may be an earlier source
   for (const EwItem& e : items_)
     if (e.r == a || e.r == r || e.a == r) { flush(); gather_mode_ = true; break; }
+  (*n_rot_)++;
   items_.push_back(EwItem{r, a, reinterpret_cast<const u64*>(order), g, 3u});
 }
 

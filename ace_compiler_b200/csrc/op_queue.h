@@ -40,8 +40,10 @@ struct EwPack {
 
 class OpQueue {
  public:
-  OpQueue(const DeviceTables* T, cudaStream_t s, size_t* launch_counter)
-      : T_(T), stream_(s), launches_(launch_counter) {}
+  OpQueue(const DeviceTables* T, cudaStream_t s, size_t* launch_counter, uint64_t* n_mul,
+          uint64_t* n_add, uint64_t* n_rot)
+      : T_(T), stream_(s), launches_(launch_counter), n_mul_(n_mul), n_add_(n_add),
+        n_rot_(n_rot) {}
   void push_ew(EwOp op, u64* r, const u64* a, const u64* b, u32 g);
   void push_gather(u64* r, const u64* a, const int64_t* order, u32 g);
   void flush();
@@ -52,6 +54,7 @@ class OpQueue {
   const DeviceTables* T_;
   cudaStream_t        stream_;
   size_t*             launches_;
+  uint64_t *          n_mul_, *n_add_, *n_rot_;  // op-trace counters of the context
   std::vector<EwItem> items_;
   bool                gather_mode_ = false;
   std::unordered_map<const void*, int> owner_;  // limb pointer -> an item that touches it

@@ -63,6 +63,13 @@ Stat g_stats[] = {{"Hw_modadd", 0, 0}, {"Hw_modmul", 0, 0}, {"Hw_rotate", 0, 0},
                   {"Free", 0, 0}, {"Copy/Set_coeffs", 0, 0}};
 enum { ST_ADD, ST_MUL, ST_ROT, ST_MODUP, ST_MODDOWN, ST_RESCALE, ST_ENCODE, ST_BTS, ST_ALLOC,
        ST_FREE, ST_COPY, ST_COUNT };
+// ACE_B200_QUIET=1: no [RT_STAT] lines and, more importantly, no stream synchronisation at
+// every layer boundary (the emitted code calls Tm_taken ~65 times per image)
+bool quiet() {
+  static int q = -1;
+  if (q < 0) q = (getenv("ACE_B200_QUIET") && getenv("ACE_B200_QUIET")[0] == '1') ? 1 : 0;
+  return q == 1;
+}
 bool g_no_batch = false;
 bool g_stats_on = false, g_stats_sync = false;  // =2: sync around every scope (true GPU time)
 void stats_sync();
@@ -270,6 +277,7 @@ struct LutEntry {
   uint64_t ent_ofst;
 };
 std::vector<char> g_wfile;
+char*             g_wfile_dev = nullptr;  // the same bytes in HBM: Pt_from_msg encodes from there
 const LutEntry*   g_lut   = nullptr;
 uint64_t          g_nent  = 0;
 uint32_t          g_etype = 0;
@@ -279,6 +287,32 @@ uint32_t          g_etype = 0;
 // =========================================================================== context
 API void Ace_set_device(int device) { g_device = device; }
 API void* Ace_context(void) { return g_ctx; }
+
+// ---- B200 extensions used by bench.py / tests: device-side timing and counters
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+API void Ace_timer_start(void) {
+  Context* c = ctx();
+  if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
+  cudaEventRecord(g_ev0, c->stream);
+}
+API float Ace_timer_stop_ms(void) {
+  Context* c = ctx();
+  float ms = 0;
+  cudaEventRecord(g_ev1, c->stream);
+  cudaEventSynchronize(g_ev1);
+  cudaEventElapsedTime(&ms, g_ev0, g_ev1);
+  return ms;
+}
+API uint64_t Ace_launch_count(void) { return ctx()->launches; }
+// op trace so far: out[class * 72 + level], classes in the order of Context::TraceClass
+// (modup digit, moddown poly, rescale poly, encode, limb mul, limb add, limb rotate, limb ntt)
+API int Ace_trace(uint64_t* out, size_t cap) {
+  Context* c = ctx();
+  size_t n = (size_t)Context::TR_CLASSES * Context::kTraceLevels;
+  if (cap < n) return -1;
+  memcpy(out, c->trace, n * sizeof(uint64_t));
+  return (int)n;
+}
 
 API void Prepare_context(void) {
   if (g_ctx) return;
@@ -298,13 +332,16 @@ API void Prepare_context(void) {
       g_mod[g]._br_k = g_mod[g]._br_m = 0;
       g_mod[g]._prec128 = ~(unsigned __int128)0 / g_ctx->mod[g];
     }
-    printf("ckks_param: _provider = %d, _poly_degree = %d, _sec_level = %ld, mul_depth = %ld, "
+    if (!quiet()) printf("ckks_param: _provider = %d, _poly_degree = %d, _sec_level = %ld, mul_depth = %ld, "
            "_first_mod_size = %ld, _scaling_mod_size = %ld, _num_q_parts = %ld, _num_p = %ld, "
            "_num_rot_idx = %ld,_hamming_wieght = %ld\n",
            p->_provider, p->_poly_degree, p->_sec_level, p->_mul_depth, p->_first_mod_size,
            p->_scaling_mod_size, parts, g_ctx->K, p->_num_rot_idx, p->_hamming_weight);
     g_ev = new Evaluator(g_ctx);
-    g_queue = new OpQueue(&g_ctx->T, g_ctx->stream, &g_ctx->launches);
+    g_queue = new OpQueue(&g_ctx->T, g_ctx->stream, &g_ctx->launches,
+                          &g_ctx->trace[Context::TR_LIMB_MUL][0],
+                          &g_ctx->trace[Context::TR_LIMB_ADD][0],
+                          &g_ctx->trace[Context::TR_LIMB_ROT][0]);
     g_no_batch = getenv("ACE_B200_NO_BATCH") && getenv("ACE_B200_NO_BATCH")[0] == '1';
     const char* no_keys = getenv("ACE_B200_NO_KEYGEN");  // parity runs import the oracle's keys
     const bool  own_keys = !(no_keys && no_keys[0] == '1');
@@ -470,10 +507,12 @@ API void Run_main_graph(void) {  // common/src/rt_lib.c:16-20
 
 API void Tm_start(const char* msg) {
   (void)msg;
+  if (quiet()) return;
   guard([&] { ctx()->sync(); });
   g_tm_stamp = clock();
 }
 API void Tm_taken(const char* msg) {  // rt_stat.c:23-28; a stream sync makes it device-accurate
+  if (quiet()) return;
   guard([&] { ctx()->sync(); });
   clock_t cur = clock();
   fprintf(stdout, "[RT_STAT] %s takes %.3f seconds.\n", msg,
@@ -944,22 +983,41 @@ API bool Pt_mgr_init(const char* fname) {  // pt_mgr.c:35-110 (message files onl
   g_nent  = h->ent_count;
   g_lut   = reinterpret_cast<const LutEntry*>(g_wfile.data() + h->lut_ofst);
   if (g_etype != DE_MSG_F32 && g_etype != DE_MSG_F64) die("only message data files are supported");
+  guard([&] {
+    Context* c = ctx();
+    ACE_CUDA(cudaMalloc(&g_wfile_dev, g_wfile.size()));
+    c->h2d_sync(g_wfile_dev, g_wfile.data(), g_wfile.size());
+  });
   return true;
 }
 API void Pt_mgr_fini(void) {
+  if (g_wfile_dev) cudaFree(g_wfile_dev);
+  g_wfile_dev = nullptr;
   g_wfile.clear();
   g_wfile.shrink_to_fit();
   g_lut = nullptr;
   g_nent = 0;
 }
-// Pt_from_msg (pt_mgr.c:182-191): look the message up and encode it at run time
+// Pt_from_msg (pt_mgr.c:182-191): look the message up and encode it at run time.  The message
+// is read from the HBM copy of the weight file: no host->device copy, no synchronisation.
 API void Pt_from_msg(void* pt, uint32_t index, size_t len, uint32_t scale, uint32_t level) {
   if (!g_lut || index >= g_nent) die("Pt_from_msg: index out of range");
   const LutEntry& e = g_lut[index];
+  const size_t esz = g_etype == DE_MSG_F32 ? sizeof(float) : sizeof(double);
+  if (e.size < len * esz) die("Pt_from_msg: entry size too small");
   const char* data = g_wfile.data() + e.ent_ofst;
-  if (g_etype == DE_MSG_F32) {
-    Encode_plain_from_float((PLAIN)pt, (float*)data, len, scale, level);
-  } else {
-    Encode_plain_from_double((PLAIN)pt, (double*)data, len, scale, level);
+  if (len == 1) {  // constant fast path of Encode_plain_from_float (plain_eval.c:28-34)
+    if (g_etype == DE_MSG_F32) Encode_plain_from_float((PLAIN)pt, (float*)data, len, scale, level);
+    else Encode_plain_from_double((PLAIN)pt, (double*)data, len, scale, level);
+    return;
   }
+  StatScope ss(ST_ENCODE);
+  PLAIN plain = (PLAIN)pt;
+  Context* c = ctx();
+  if (level == 0) level = (uint32_t)c->L;
+  init_plain(plain, c->N / 2, level, pow(Get_default_sc(), scale), scale);
+  guard([&] {
+    c->encode_dev(U(plain->_poly._data), g_wfile_dev + e.ent_ofst, g_etype == DE_MSG_F32 ? 0 : 1,
+                  len, level, 0, scale, 0);
+  });
 }

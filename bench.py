@@ -1,21 +1,27 @@
 #!/usr/bin/env python
-"""bench.py -- CKKS primitive micro-benchmark at ACE's ResNet-20 parameter set.
+"""bench.py -- ResNet-20 / CIFAR-10 encrypted inference (BASELINE.json headline metric).
 
-Workload (BASELINE.json configs[1]): N = 2^16, L = 34 Q limbs (51/50 bit), K = 11 P limbs
-(60 bit), dnum = 3.  One *chain* = HMult + relinearise -> rescale -> rotation (hybrid key
-switch) on one ciphertext at the top level, i.e. the three key-switch-bearing primitives
-that make up >95 % of an ACE-generated ResNet.  One *step* = CHAINS
-independent ciphertexts pushed through the chain on one GPU.
+Workload (BASELINE.json configs[0]): the reference's checked-in,
+unmodified ACE output `resnet20_cifar10_pre.onnx.inc` (N = 2^16, 34 Q limbs of 51/50 bit, 11 P
+limbs of 60 bit, dnum = 3, 19 bootstraps) compiled against this repo's rt_ant header tree and
+executed by the B200 runtime; synthetic weight file and image (no network): tools/make_weights.py
+and ace_compiler_b200.model_runner.synthetic_image.  One *step* = one encrypted image through
+Main_graph on every GPU (images are independent -> one image per rank, no collective).
 
-  value  : chains/s, whole job, inputs already resident in HBM (device-timed, CUDA events)
-  e2e    : chains/s through the C ABI with HOST buffers (pinned), H2D + D2H inside the timing
-  roofline: dominant kernel (batched NTT tile kernel), algorithmic bytes = 1 MiB per limb
-  cpu_baseline / --impl reference: the reference rtlib (oracle/_ref, built from
-            /root/reference) running the same chain on the host cores.
-
-Multi-GPU: ciphertexts (images) are independent -> sharded across ranks, no collective on the
-data path ("scaling": "weak"); torch.distributed is only used for the barrier and the
-max-over-ranks timing.
+  value   : images/s, whole job; timed region = Run_main_graph() with the encrypted input already
+            resident in HBM (the reference's RTM_MAIN_GRAPH region), CUDA events, max over ranks
+  e2e     : images/s through the reference's driver API with HOST data: Prepare_input (host image
+            -> encode + encrypt on the GPU) + Run_main_graph + Handle_output (decrypt, decode,
+            logits back on the host) all inside the timed region
+  roofline: batched forward NTT (the dominant kernel family), timed live
+  cpu_baseline / --impl reference: the unmodified reference rtlib (oracle/_ref/libace_ref.so)
+            on the host cores.  One reference image takes ~20 min and its context ~6 min to
+            build, so the CPU figure is composed: the reference's unit cost of every primitive
+            the image consists of (Decomp_modup, Mod_down, Rescale, limb mul/add/rotate, NTT,
+            encode; measured live at several levels, a bounded sample) times the model's op trace
+            (tests/emitted/<model>.trace.json, recorded by the GPU runtime; control flow of an
+            emitted program is data independent).  DESIGN.md section 5 compares this estimate
+            with a real end-to-end reference run.
 """
 import argparse
 import ctypes as C
@@ -31,12 +37,16 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N, DEPTH, Q0, SF, PARTS = 65536, 33, 51, 50, 3
-LEVEL = 34
-CHAINS = 4            # ciphertexts per step per GPU
-ROTS = [1, 2, 3, 4]   # one distinct rotation key per chain slot (defeats L2 reuse of keys)
-METRIC = "ckks_chain_throughput(HMult+relin+rescale+rotate, N=2^16, L=34)"
-UNIT = "chains/s"
+MODEL = "resnet20_cifar10_pre"
+N, DEPTH, Q0, SF, PARTS, HW = 65536, 33, 51, 50, 3, 192
+METRIC = "resnet20_cifar10_encrypted_inference_throughput"
+UNIT = "images/s"
+WORKLOAD = ("ResNet-20 CIFAR-10 single-image encrypted inference: ACE-emitted "
+            "resnet20_cifar10_pre.onnx.inc (N=2^16, L=34, K=11, dnum=3, 19 bootstraps), "
+            "synthetic weights/image")
+TRACE_CLASSES = ["modup_digit", "moddown_poly", "rescale_poly", "encode", "limb_mul", "limb_add",
+                 "limb_rot", "limb_ntt"]
+TRACE_LEVELS = 72
 
 
 def read_peaks():
@@ -45,6 +55,18 @@ def read_peaks():
             return float(json.load(f)["hbm_gbs"]), "measured"
     except Exception:
         return 6650.0, "fallback"
+
+
+def weight_file(model):
+    path = "/tmp/ace_b200_%s.msg" % model
+    if not os.path.exists(path):
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import make_weights
+        ent = [tuple(e) for e in json.load(open(os.path.join(ROOT, "tests", "emitted",
+                                                             model + ".entries.json")))]
+        make_weights.write_file(path + ".tmp%d" % os.getpid(), ent, 0.05, 1)
+        os.replace(path + ".tmp%d" % os.getpid(), path)
+    return path
 
 
 class ClockSampler(threading.Thread):
@@ -72,14 +94,14 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.5)
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def dist_setup(n_gpus):
+def dist_setup():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -109,89 +131,95 @@ def max_over_ranks(dist, local, x):
     return float(t.item())
 
 
+def read_trace(model_obj):
+    buf = (C.c_uint64 * (len(TRACE_CLASSES) * TRACE_LEVELS))()
+    n = model_obj.lib.Ace_trace(buf, len(buf))
+    assert n == len(buf)
+    return np.array(buf, dtype=np.uint64).reshape(len(TRACE_CLASSES), TRACE_LEVELS)
+
+
+def trace_to_json(t):
+    return {c: {str(l): int(t[i, l]) for l in range(TRACE_LEVELS) if t[i, l]}
+            for i, c in enumerate(TRACE_CLASSES)}
+
+
+def load_trace(model):
+    with open(os.path.join(ROOT, "tests", "emitted", model + ".trace.json")) as f:
+        return json.load(f)["per_image"]
+
+
 # --------------------------------------------------------------------------------- ours
 def run_ours(args):
-    import ace_compiler_b200 as ace
-    rank, world, local, dist = dist_setup(args.gpus)
-    ctx = ace.Context(N, DEPTH, Q0, SF, PARTS, device=local)
-    lib, h = ctx.lib, ctx.h
-    rng = np.random.default_rng(1234 + rank)
-    mods = np.concatenate([ctx.q, ctx.p])
-
-    def rand_limbs(gs):
-        return np.stack([rng.integers(0, mods[g], N, dtype=np.int64) for g in gs])
-
-    # synthetic evaluation keys: uniformly random residues (the integer pipeline does the
-    # same work for any key material); one relin key + one rotation key per chain slot
-    G = ctx.L + ctx.K
-    for is_rot, rot in [(False, 0)] + [(True, r) for r in ROTS[:CHAINS]]:
-        k0 = np.stack([rand_limbs(range(G)) for _ in range(ctx.parts)])
-        k1 = np.stack([rand_limbs(range(G)) for _ in range(ctx.parts)])
-        ctx.import_switch_key(is_rot, rot, k0, k1)
-        del k0, k1
-    # synthetic ciphertexts (uniform residues), resident in HBM, plus pinned host copies
+    from ace_compiler_b200.model_runner import EmittedModel, synthetic_image
+    rank, world, local, dist = dist_setup()
+    msg = weight_file(MODEL)
+    t0 = time.time()
+    m = EmittedModel(MODEL, msg, device=local)
+    t_ctx = time.time() - t0
     import torch
-    host_in = [torch.from_numpy(rand_limbs(list(range(LEVEL)) * 2)).pin_memory()
-               for _ in range(CHAINS)]
-    host_out = [torch.empty((2 * (LEVEL - 1), N), dtype=torch.int64).pin_memory()
-                for _ in range(CHAINS)]
-    cts = [ctx.put(hi.numpy()) for hi in host_in]
-    mul = [ctx.empty(2 * LEVEL) for _ in range(CHAINS)]
-    rs = [ctx.empty(2 * (LEVEL - 1)) for _ in range(CHAINS)]
-    out = [ctx.empty(2 * (LEVEL - 1)) for _ in range(CHAINS)]
-    NB = N * 8
+    images = [torch.from_numpy(synthetic_image(rank * 1000 + i)).pin_memory() for i in range(4)]
+    warm = max(3, args.warmup)
 
-    def chain(i):
-        c0, c1 = cts[i].ptr, cts[i].ptr + LEVEL * NB
-        m0, m1 = mul[i].ptr, mul[i].ptr + LEVEL * NB
-        s0, s1 = rs[i].ptr, rs[i].ptr + (LEVEL - 1) * NB
-        o0, o1 = out[i].ptr, out[i].ptr + (LEVEL - 1) * NB
-        ctx._ck(lib.ace_ct_mul_relin(h, m0, m1, c0, c1, c0, c1, LEVEL))
-        ctx._ck(lib.ace_ct_rescale(h, s0, s1, m0, m1, LEVEL))
-        ctx._ck(lib.ace_ct_rotate(h, o0, o1, s0, s1, LEVEL - 1, ROTS[i]))
+    def step_e2e(i):
+        m.prepare_input(images[i % len(images)].numpy())
+        m.run()
+        return m.handle_output(10)
 
-    def step():
-        for i in range(CHAINS):
-            chain(i)
+    t0 = time.time()
+    logits = step_e2e(0)
+    t_first = time.time() - t0
+    for i in range(1, warm):
+        logits = step_e2e(i)
 
-    def step_e2e():
-        for i in range(CHAINS):
-            ctx._ck(lib.ace_upload(h, cts[i].ptr, host_in[i].data_ptr(), 2 * LEVEL))
-            chain(i)
-            ctx._ck(lib.ace_download(h, host_out[i].data_ptr(), out[i].ptr, 2 * (LEVEL - 1)))
-
-    def timed(fn, steps):
-        ctx.sync()
-        barrier(dist, local)
-        lib.ace_timer_start(h)
-        for _ in range(steps):
-            fn()
-        ms = C.c_float()
-        ctx._ck(lib.ace_timer_stop_ms(h, C.byref(ms)))
-        ctx.sync()
-        barrier(dist, local)
-        return max_over_ranks(dist, local, ms.value)
-
-    for _ in range(max(3, args.warmup)):
-        step()
-    ctx.sync()
+    # ---- value: Main_graph with the input ciphertext resident, device-timed per step
     sampler = ClockSampler(local)
     sampler.start()
-    l0 = ctx.launch_count()
-    ms = timed(step, args.steps)
-    launches = ctx.launch_count() - l0
+    tr0, l0 = read_trace(m), m.launch_count()
+    barrier(dist, local)
+    ms = 0.0
+    for i in range(args.steps):
+        m.prepare_input(images[i % len(images)].numpy())
+        m.timer_start()
+        m.run()
+        ms += m.timer_stop_ms()
+    barrier(dist, local)
+    ms = max_over_ranks(dist, local, ms)
+    launches = m.launch_count() - l0
+    trace = (read_trace(m) - tr0) // max(1, args.steps)
     sampler.stop_flag = True
-    step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
 
-    # ---- roofline of the dominant kernel: batched forward NTT over all L+K limbs
+    # ---- e2e: host image in, logits out, everything inside the timed region
+    barrier(dist, local)
+    m.timer_start()
+    for i in range(args.steps):
+        logits = step_e2e(i)
+    ms_e2e = m.timer_stop_ms()
+    barrier(dist, local)
+    ms_e2e = max_over_ranks(dist, local, ms_e2e)
+    out_level_bytes = 2 * N * 8  # Handle_output downloads the decrypted plaintext (2 limbs)
+
+    if args.record_trace and rank == 0:
+        path = os.path.join(ROOT, "tests", "emitted", MODEL + ".trace.json")
+        json.dump({"model": MODEL, "classes": TRACE_CLASSES, "per_image": trace_to_json(trace)},
+                  open(path, "w"), indent=0)
+        print("trace written to", path, file=sys.stderr)
+    m.close()
+
+    # ---- roofline of the dominant kernel family: batched forward NTT over all L+K limbs
     roof = None
     if rank == 0:
-        buf = ctx.put(rand_limbs(list(range(G)) * 3))
-        reps = 20
-        for _ in range(3):
-            for k in range(3):
-                lib.ace_ntt(h, buf.ptr + k * G * NB, 0, G)
+        import ace_compiler_b200 as ace
+        ctx = ace.Context(N, DEPTH, Q0, SF, PARTS, device=local)
+        lib, h = ctx.lib, ctx.h
+        G = ctx.L + ctx.K
+        NB = N * 8
+        rng = np.random.default_rng(7)
+        mods = np.concatenate([ctx.q, ctx.p])
+        buf = ctx.put(np.stack([rng.integers(0, mods[g % G], N, dtype=np.int64)
+                                for g in range(3 * G)]))
+        reps = 30
+        for k in range(6):
+            lib.ace_ntt(h, buf.ptr + (k % 3) * G * NB, 0, G)
         ctx.sync()
         lib.ace_timer_start(h)
         for r in range(reps):
@@ -199,77 +227,137 @@ def run_ours(args):
         t = C.c_float()
         lib.ace_timer_stop_ms(h, C.byref(t))
         per_launch_s = t.value / reps / 1e3
-        alg_bytes = G * N * 8 * 2  # read + write each limb once
+        alg_bytes = G * N * 8 * 2  # read + write each limb once (1 MiB per limb)
         peak, how = read_peaks()
         ach = alg_bytes / per_launch_s / 1e9
-        roof = {"bound": "hbm", "kernel": "ntt (strided+tile kernels, %d limbs/launch)" % G,
+        roof = {"bound": "hbm", "kernel": "ntt_fwd_strided<4> + ntt_fwd_tile8 (%d limbs/launch)" % G,
                 "achieved": round(ach, 1), "peak": peak, "peak_source": how, "unit": "GB/s",
                 "frac": round(ach / peak, 4), "traffic": None,
                 "alg_bytes_per_launch": alg_bytes, "launch_us": round(per_launch_s * 1e6, 2),
-                "note": "NTT is INT32-multiply bound; HBM fraction reported for reference"}
+                "note": "two passes over each limb (2 MiB moved per 1 MiB algorithmic); the butterflies "
+                        "are INT32-multiply bound, see profiles/"}
         buf.free()
+        ctx.close()
     sampler.join(timeout=2)
 
-    total_chains = CHAINS * world * args.steps
+    total = world * args.steps
     line = {
-        "metric": METRIC, "value": round(total_chains / (ms / 1e3), 3), "unit": UNIT,
-        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": round(total / (ms / 1e3), 4), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": round(ms / args.steps, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": "CKKS primitive microbench at ACE ResNet-20 params: "
-                               "HMult+relin+rescale+rotate chain",
-                   "N": N, "L": LEVEL, "K": int(ctx.K), "dnum": PARTS,
-                   "chains_per_step_per_gpu": CHAINS,
-                   "l2": "working set per step (4 ct x 5 keys ~ 1 GB) exceeds the 126 MB L2",
-                   "parallelism": "ciphertexts sharded across GPUs, no collective"},
+        "config": {"workload": WORKLOAD, "model": MODEL, "N": N, "L": DEPTH + 1, "dnum": PARTS,
+                   "images_per_step_per_gpu": 1, "s_per_image": round(ms / args.steps / 1e3, 4),
+                   "first_image_s": round(t_first, 3), "prepare_context_s": round(t_ctx, 2),
+                   "l2": "working set per image (30 GB of switch keys, 225 MB of weights, "
+                         "ciphertexts of 34 MB) exceeds the 126 MB L2",
+                   "parallelism": "one image per GPU, full key replica per GPU, no collective",
+                   "logits0": [float(x) for x in logits[:3]]},
         "clocks": sampler.summary(),
-        "e2e": {"value": round(total_chains / (ms_e2e / 1e3), 3), "unit": UNIT,
-                "h2d_bytes_per_step": CHAINS * 2 * LEVEL * NB,
-                "d2h_bytes_per_step": CHAINS * 2 * (LEVEL - 1) * NB},
+        "e2e": {"value": round(total / (ms_e2e / 1e3), 4), "unit": UNIT,
+                "h2d_bytes_per_step": 3 * 32 * 32 * 8, "d2h_bytes_per_step": out_level_bytes},
         "gpu_launches": int(launches),
     }
     if rank == 0:
         line["roofline"] = roof
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(threads=1, iters=2)
+            line["cpu_baseline"] = cpu_baseline(trace_to_json(trace), threads=1)
         print(json.dumps(line), flush=True)
-    ctx.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------- reference
-def cpu_baseline(threads, iters):
-    """times the compiled reference rtlib (oracle/_ref) on the host cores"""
+def _interp(levels, costs, l):
+    return float(np.interp(l, levels, costs))
+
+
+def cpu_baseline(trace, threads):
+    """seconds per image of the reference rtlib on the host = sum over the op trace of
+    count(class, level) * unit cost(class, level) measured live on oracle/_ref (1 thread);
+    with threads > 1 the images/s figure is scaled by the measured parallel efficiency of
+    `threads` independent ciphertext chains (the reference parallelises over images with
+    OpenMP, ant/dataset/resnet_cifar.main.inc:81)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_bindings import RefLib, C as _C, u32, i32
-    ref = RefLib(N, DEPTH, Q0, SF, PARTS, 192, [1], with_bootstrap=False)
-    f = ref.lib.ref_bench_chain
-    f.restype, f.argtypes = _C.c_double, [_C.c_int, _C.c_int, u32, i32]
-    secs = f(threads, iters, LEVEL, 1)
-    return {"value": round(threads * iters / secs, 4), "unit": UNIT, "cores": threads,
+    t_start = time.time()
+    ref = RefLib(N, DEPTH, Q0, SF, PARTS, HW, [1], with_bootstrap=False)
+    rng = np.random.default_rng(3)
+    mods = np.concatenate([ref.q, ref.p])
+    L, K = ref.L, ref.K
+
+    def poly(nq, ext=False):
+        idx = list(range(nq)) + ([L + i for i in range(K)] if ext else [])
+        return np.stack([rng.integers(0, mods[g], N, dtype=np.int64) for g in idx])
+
+    def clock(fn, reps=1):
+        best = 1e30
+        for _ in range(reps):
+            t = time.perf_counter()
+            fn()
+            best = min(best, time.perf_counter() - t)
+        return best
+
+    levels = [2, 12, 23, 34]
+    unit = {c: [] for c in ("modup_digit", "moddown_poly", "rescale_poly", "encode")}
+    msg = rng.uniform(-0.05, 0.05, 16384).astype(np.float32)
+    for l in levels:
+        a = poly(l)
+        beta = min(PARTS, -(-l // ref.part_size))
+        unit["modup_digit"].append(sum(clock(lambda j=j: ref.decomp_modup(a, j)) for j in range(beta)) / beta)
+        e = poly(l, ext=True)
+        unit["moddown_poly"].append(clock(lambda: ref.mod_down(e)))
+        unit["rescale_poly"].append(clock(lambda: ref.rescale(a)))
+        unit["encode"].append(clock(lambda: ref.encode_float(msg, 1, l)))
+    x, y = poly(1)[0], poly(1)[0]
+    order = ref.auto_order(1)[1] if isinstance(ref.auto_order(1), tuple) else ref.auto_order(1)
+    limb = {"limb_mul": clock(lambda: ref.hw("modmul", 0, x, y), 5),
+            "limb_add": clock(lambda: ref.hw("modadd", 0, x, y), 5),
+            "limb_rot": clock(lambda: ref.hw("rotate", 0, x, order), 5),
+            "limb_ntt": clock(lambda: ref.ntt(0, x), 5)}
+    secs, parts = 0.0, {}
+    for cls, by_level in trace.items():
+        s = 0.0
+        for lvl, cnt in by_level.items():
+            s += cnt * (limb[cls] if cls in limb else _interp(levels, unit[cls], int(lvl)))
+        parts[cls] = round(s, 1)
+        secs += s
+    eff = 1.0
+    if threads > 1:
+        f = ref.lib.ref_bench_chain
+        f.restype, f.argtypes = _C.c_double, [_C.c_int, _C.c_int, u32, i32]
+        t1 = f(1, 1, 17, 1)
+        tn = f(threads, 1, 17, 1)
+        eff = min(1.0, t1 / tn)
+    return {"value": round(threads * eff / secs, 6), "unit": UNIT, "cores": threads,
             "kind": "reference",
-            "sample": "%d thread(s) x %d chain(s) at L=%d, reference rtlib -O3" % (
-                threads, iters, LEVEL), "seconds": round(secs, 2)}
+            "s_per_image_1thread": round(secs, 1), "parallel_efficiency": round(eff, 3),
+            "sample": "unit costs of Decomp_modup/Mod_down/Rescale/encode at levels %s and of a limb "
+                      "mul/add/rotate/NTT on oracle/_ref (-O3), x the op trace of one image "
+                      "(tests/emitted/%s.trace.json)" % (levels, MODEL),
+            "seconds_by_class": parts, "sample_seconds": round(time.time() - t_start, 1)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    # each in-flight chain needs ~0.5 GB; cap threads so small boxes do not swap
-    threads = max(1, min(threads, 64))
-    iters = max(1, args.steps)
+    threads = max(1, min(os.cpu_count() or 1, 64))
+    # every concurrent image needs its own working set (~8 GB) next to the shared 35 GB of keys
+    try:
+        mem_gb = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES") / 2**30
+        threads = max(1, min(threads, int((mem_gb - 40) // 8)))
+    except Exception:
+        pass
     t0 = time.time()
-    base = cpu_baseline(threads, iters)
+    base = cpu_baseline(load_trace(MODEL), threads)
+    s_img = base["s_per_image_1thread"]
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(base["seconds"] * 1e3 / iters, 1), "higher_is_better": True,
+            "ms_per_step": round(1e3 / base["value"], 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": "CKKS primitive microbench at ACE ResNet-20 params: "
-                                   "HMult+relin+rescale+rotate chain", "N": N, "L": LEVEL,
-                       "dnum": PARTS},
+            "config": {"workload": WORKLOAD, "model": MODEL, "N": N, "L": DEPTH + 1, "dnum": PARTS,
+                       "s_per_image_1thread": s_img, "threads": threads},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
@@ -280,10 +368,12 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--record-trace", action="store_true",
+                    help="write tests/emitted/<model>.trace.json from this run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

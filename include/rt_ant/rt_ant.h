@@ -272,6 +272,10 @@ void  Ace_import_switch_key(bool is_rot, int32_t rot_idx, uint32_t part, int whi
 void  Ace_set_input(const char* name, size_t idx, const int64_t* c0, const int64_t* c1,
                     uint32_t level, uint32_t slots, double scale, uint32_t sf_degree);
 CIPHER Ace_get_output(const char* name, size_t idx);
+void     Ace_timer_start(void);    /* CUDA event on the runtime's stream */
+float    Ace_timer_stop_ms(void);  /* ms since Ace_timer_start, device time */
+uint64_t Ace_launch_count(void);   /* kernels launched so far */
+int      Ace_trace(uint64_t* out, size_t cap); /* op trace [8 classes][72 levels], see rt_shim.cu */
 
 #ifdef __cplusplus
 }

@@ -60,10 +60,24 @@ def build_models(verbose=False, models=MODELS):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             print("FAILED", m, r.stderr[:2000])
+            continue
+        built.append(exe)
+        # the same unit as a shared object (ace_compiler_b200/models/lib<model>.so) for in-process
+        # drivers: bench.py and the whole-model parity test load it with RTLD_GLOBAL
+        mdir = os.path.join(ROOT, "ace_compiler_b200", "models")
+        os.makedirs(mdir, exist_ok=True)
+        so = os.path.join(mdir, "lib%s.so" % m)
+        cmd = ["gcc", "-O1", "-w", "-std=gnu11", "-fPIC", "-shared", "-include", "common/rtlib.h",
+               "-x", "c", inc, "-I", os.path.join(ROOT, "include"), "-o", so, "-L",
+               os.path.join(ROOT, "ace_compiler_b200"), "-lace_b200", "-Wl,-rpath,$ORIGIN/..",
+               "-lm"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            print("FAILED", so, r.stderr[:2000])
         else:
-            built.append(exe)
-            if verbose:
-                print("built", exe)
+            built.append(so)
+        if verbose:
+            print("built", exe, so)
     return built
 
 
