@@ -304,6 +304,15 @@ API float Ace_timer_stop_ms(void) {
   return ms;
 }
 API uint64_t Ace_launch_count(void) { return ctx()->launches; }
+// rotation indices whose keys Bootstrap_keygen would generate for `slots` (0 = N/2); the
+// conjugation key is rotation index 2N-1.  Returns the count.
+API int Ace_bootstrap_rot_indices(uint32_t slots, int32_t* out, size_t cap) {
+  ctx();
+  if (!g_ev->bootstrap_supported()) return 0;
+  std::vector<int32_t> v = g_ev->bootstrap_rot_indices(slots);
+  for (size_t i = 0; i < v.size() && i < cap; i++) out[i] = v[i];
+  return (int)v.size();
+}
 // op trace so far: out[class * 72 + level], classes in the order of Context::TraceClass
 // (modup digit, moddown poly, rescale poly, encode, limb mul, limb add, limb rotate, limb ntt)
 API int Ace_trace(uint64_t* out, size_t cap) {

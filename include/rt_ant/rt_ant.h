@@ -275,6 +275,7 @@ CIPHER Ace_get_output(const char* name, size_t idx);
 void     Ace_timer_start(void);    /* CUDA event on the runtime's stream */
 float    Ace_timer_stop_ms(void);  /* ms since Ace_timer_start, device time */
 uint64_t Ace_launch_count(void);   /* kernels launched so far */
+int      Ace_bootstrap_rot_indices(uint32_t slots, int32_t* out, size_t cap);
 int      Ace_trace(uint64_t* out, size_t cap); /* op trace [8 classes][72 levels], see rt_shim.cu */
 
 #ifdef __cplusplus

@@ -270,8 +270,11 @@ class RefModel:
     encrypted input and every output limb are reproducible."""
 
     def __init__(self, model, data_file):
-        self.lib = L = C.CDLL(REF_SO, mode=C.RTLD_GLOBAL)
-        self.unit = C.CDLL(os.path.join(os.path.dirname(REF_SO), model + "_ref.so"))
+        # RTLD_LOCAL + RTLD_NOW: every symbol of the reference pair is bound now and stays private,
+        # so the B200 runtime (same function names) can be loaded into the same process later
+        self.lib = L = C.CDLL(REF_SO, mode=os.RTLD_LOCAL | os.RTLD_NOW)
+        self.unit = C.CDLL(os.path.join(os.path.dirname(REF_SO), model + "_ref.so"),
+                           mode=os.RTLD_LOCAL | os.RTLD_NOW)
         L.ref_set_callbacks.argtypes = [vp] * 5
         self.unit.model_register.argtypes = [vp]
         self.unit.model_register(C.cast(L.ref_set_callbacks, vp))

@@ -1,0 +1,50 @@
+"""GPU parity of a whole ACE-emitted model (SURVEY section 8(c) parity protocol): the reference's
+unmodified resnet20_cifar10_pre.onnx.inc on the B200 runtime against the golden run of the same
+unit on the reference rtlib (tests/golden/resnet20_cifar10_pre.json, made by
+tests/golden/make_model_golden.py: 1925 s of Main_graph on the CPU).
+
+* test_resnet20_logits: own keys; decrypted logits within 1e-5 of the reference's (always runs).
+* test_resnet20_bit_exact: the reference library regenerates the golden run's keys on the host
+  (minutes, ~40 GB of RAM), the GPU imports them and must reproduce the output ciphertext bit for
+  bit (~3 min).  Runs when the host has >= 64 GB of RAM; ACE_MODEL_PARITY=0 skips it, =1 forces
+  it (log of the last run: profiles/r1_model_parity.log)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+MODEL = "resnet20_cifar10_pre"
+
+
+def _run(*extra, timeout=600):
+    if not os.path.exists(os.path.join(ROOT, "ace_compiler_b200", "models", "lib%s.so" % MODEL)):
+        pytest.skip("model unit not built (needs the reference tree at build time)")
+    r = subprocess.run([sys.executable, os.path.join(HERE, "model_case.py"), MODEL, *extra],
+                       capture_output=True, text=True, timeout=timeout)
+    sys.stdout.write(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + "\n" + r.stderr[-4000:]
+    assert "MODEL PARITY OK" in r.stdout
+
+
+def test_resnet20_logits():
+    _run()
+
+
+def _enough_ram():
+    try:
+        return os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES") >= 64 * 2**30
+    except Exception:
+        return False
+
+
+def test_resnet20_bit_exact():
+    flag = os.environ.get("ACE_MODEL_PARITY")
+    if flag == "0" or (flag != "1" and not _enough_ram()):
+        pytest.skip("needs ~40 GB of host RAM for the reference's keys (ACE_MODEL_PARITY=1 forces it)")
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", MODEL + "_ref.so")):
+        pytest.skip("oracle/_ref/%s_ref.so not built (needs the reference tree at build time)" % MODEL)
+    _run("exact", timeout=3000)
