@@ -14,6 +14,7 @@
 #include <random>
 
 #include "context.h"
+#include "prof.h"
 #include "host_math.h"
 
 namespace ace {
@@ -429,6 +430,8 @@ void Context::encode_dev(u64* out, const void* dev_src, int kind, size_t len, u3
   while ((1u << logslots) < slots) logslots++;
   cplx* dv = (cplx*)enc_buf_;
   const cplx* tw = (const cplx*)enc_tw_;
+  prof::Scope prof_scope_("encode(total)", stream);
+  int prof_fft_ = prof::on ? prof::begin("encode_fft", stream) : -1;
   const u32 logtile = logslots < kEmbTileLog ? logslots : kEmbTileLog;
   const int sa = (int)(logslots - logtile);
   if (sa > 0) {
@@ -453,6 +456,7 @@ void Context::encode_dev(u64* out, const void* dev_src, int kind, size_t len, u3
                    tile * sizeof(cplx), stream>>>(dv, tw, dev_src, kind, (u32)len, logtile,
                                                   sa == 0);
   }
+  if (prof_fft_ >= 0) prof::end(prof_fft_, stream);
   const double delta = (double)((u64)1 << params.scaling_mod_size);
   const u32 nl = level + p_cnt;
   LimbBatch b;
@@ -468,8 +472,11 @@ void Context::encode_dev(u64* out, const void* dev_src, int kind, size_t len, u3
       powp.v[l] = p;
     }
   }
-  emb_round_rns_kernel<<<grid_for(N, nl), 256, 0, stream>>>(T, b, dv, slots, logslots, delta,
-                                                           powp, sf_degree > 1 ? 1 : 0);
+  {
+    prof::Scope ps("encode_round_rns", stream);
+    emb_round_rns_kernel<<<grid_for(N, nl), 256, 0, stream>>>(T, b, dv, slots, logslots, delta,
+                                                             powp, sf_degree > 1 ? 1 : 0);
+  }
   launch_ntt(T, b, stream);
   launches += (sa > 0 ? 1 : 0) + 2 + ((logN > 12) ? 2 : 1);
 }

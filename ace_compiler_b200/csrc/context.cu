@@ -9,6 +9,7 @@
 //   Decompose_modup / Reduce_rns_base / Rescale_poly  src/util/polynomial.c:1241-1335, 928-967, 1097-1161
 //   emitted Rotate()/Relinearize()  dataset/resnet20_cifar10_pre.onnx.inc:6972-7146
 #include "context.h"
+#include "prof.h"
 
 #include <cstring>
 
@@ -193,7 +194,10 @@ u64* Context::alloc_limbs(size_t n_limbs, bool zero) {
   u64*   p     = nullptr;
   size_t bytes = std::max<size_t>(n_limbs, 1) * N * sizeof(u64);
   ACE_CUDA(cudaMallocAsync(&p, bytes, stream));
-  if (zero) ACE_CUDA(cudaMemsetAsync(p, 0, bytes, stream));
+  if (zero) {
+    prof::Scope ps("memset(alloc)", stream);
+    ACE_CUDA(cudaMemsetAsync(p, 0, bytes, stream));
+  }
   return p;
 }
 void Context::free_limbs(u64* p) {
@@ -209,6 +213,7 @@ void Context::download(u64* dst, const u64* src, size_t n_limbs) {
 void Context::sync() { ACE_CUDA(cudaStreamSynchronize(stream)); }
 
 static void copy_limbs(u64* dst, const u64* src, size_t n_limbs, u32 N, cudaStream_t s) {
+  prof::Scope ps("memcpy_d2d", s);
   ACE_CUDA(cudaMemcpyAsync(dst, src, n_limbs * N * sizeof(u64), cudaMemcpyDeviceToDevice, s));
 }
 

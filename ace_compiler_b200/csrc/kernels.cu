@@ -12,6 +12,7 @@
 // All of these are integer kernels: NTT and base conversion are bound by the INT32 multiply
 // pipe (IMAD), the rest by HBM bandwidth.  No tensor-core path is used.
 #include "kernels.cuh"
+#include "prof.h"
 
 namespace ace {
 
@@ -356,6 +357,7 @@ static void launch_strided_any(bool fwd, const DeviceTables& T, const LimbBatch&
 }
 
 void launch_ntt(const DeviceTables& T, const LimbBatch& b, cudaStream_t s) {
+  prof::Scope prof_scope_("ntt", s);
   if (b.n == 0) return;
   const u32 tile = T.N < (u32)kTile ? T.N : (u32)kTile;
   if (T.logN > (u32)kTileLog) launch_strided_any(true, T, b, s);
@@ -375,6 +377,7 @@ void launch_ntt(const DeviceTables& T, const LimbBatch& b, cudaStream_t s) {
 }
 
 void launch_intt(const DeviceTables& T, const LimbBatch& b, cudaStream_t s) {
+  prof::Scope prof_scope_("intt", s);
   if (b.n == 0) return;
   const u32 tile = T.N < (u32)kTile ? T.N : (u32)kTile;
   dim3 grid(T.N / tile, b.n);
@@ -419,6 +422,7 @@ static inline dim3 ew_grid(const DeviceTables& T, u32 n_limbs) {
 
 void launch_ew(const DeviceTables& T, EwOp op, u64* r, const u64* a, const u64* b, u32 g0,
                u32 n_limbs, cudaStream_t s) {
+  prof::Scope prof_scope_("ew", s);
   if (n_limbs == 0) return;
   dim3 grid = ew_grid(T, n_limbs);
   switch (op) {
@@ -443,6 +447,7 @@ __global__ void __launch_bounds__(256) gather_kernel(DeviceTables T, u64* __rest
 
 void launch_gather(const DeviceTables& T, u64* r, const u64* a, const int64_t* order, u32 g0,
                    u32 n_limbs, cudaStream_t s) {
+  prof::Scope prof_scope_("gather", s);
   if (n_limbs == 0) return;
   gather_kernel<<<ew_grid(T, n_limbs), 256, 0, s>>>(T, r, a, order, g0);
 }
@@ -461,6 +466,7 @@ __global__ void __launch_bounds__(256) mul_scalar_kernel(DeviceTables T, u64* __
 
 void launch_mul_scalar(const DeviceTables& T, u64* r, const u64* a, const u64* sc,
                        const u64* sc_sh, u32 g0, u32 n_limbs, cudaStream_t s) {
+  prof::Scope prof_scope_("mul_scalar", s);
   if (n_limbs == 0) return;
   mul_scalar_kernel<<<ew_grid(T, n_limbs), 256, 0, s>>>(T, r, a, sc, sc_sh, g0);
 }
@@ -505,6 +511,7 @@ __global__ void __launch_bounds__(128) base_conv_kernel(DeviceTables T, ConvDesc
 
 void launch_base_conv(const DeviceTables& T, const ConvDesc* descs, u32 n_desc,
                       cudaStream_t s) {
+  prof::Scope prof_scope_("base_conv", s);
   if (n_desc == 0) return;
   ConvDescPack P;
   u32 max_in = 0, max_sh = 0;
@@ -561,6 +568,7 @@ __global__ void __launch_bounds__(256) ksw_inner_kernel(DeviceTables T, u64* __r
 void launch_ksw_inner(const DeviceTables& T, u64* acc0, u64* acc1, const u64* ext,
                       const u64* own, u32 part_size, const u64* key0, const u64* key1,
                       u32 beta, u32 num_q, u32 L, u32 K, cudaStream_t s) {
+  prof::Scope prof_scope_("ksw_inner", s);
   dim3 grid((T.N + 255) / 256, num_q + K);
   ksw_inner_kernel<<<grid, 256, 0, s>>>(T, acc0, acc1, ext, own, part_size, key0, key1, beta,
                                         num_q, L, K);
@@ -584,6 +592,7 @@ __global__ void __launch_bounds__(256) moddown_tail_kernel(
 void launch_moddown_tail(const DeviceTables& T, u64* out, const u64* old, const u64* conv,
                          const u64* add, const u64* pinv, const u64* pinv_sh, u32 n_limbs,
                          cudaStream_t s) {
+  prof::Scope prof_scope_("moddown_tail", s);
   if (n_limbs == 0) return;
   moddown_tail_kernel<<<ew_grid(T, n_limbs), 256, 0, s>>>(T, out, old, conv, add, pinv,
                                                           pinv_sh);
@@ -603,6 +612,7 @@ __global__ void __launch_bounds__(256) rescale_pre_kernel(DeviceTables T, u64* _
 
 void launch_rescale_pre(const DeviceTables& T, u64* tmp, const u64* last, u32 l,
                         const u64* negqlinv, const u64* negqlinv_sh, cudaStream_t s) {
+  prof::Scope prof_scope_("rescale_pre", s);
   if (l == 0) return;
   rescale_pre_kernel<<<ew_grid(T, l), 256, 0, s>>>(T, tmp, last, l, negqlinv, negqlinv_sh);
 }
@@ -622,6 +632,7 @@ __global__ void __launch_bounds__(256) rescale_post_kernel(DeviceTables T, u64* 
 
 void launch_rescale_post(const DeviceTables& T, u64* out, const u64* c, const u64* tmp,
                          const u64* qlinv, const u64* qlinv_sh, u32 n_limbs, cudaStream_t s) {
+  prof::Scope prof_scope_("rescale_post", s);
   if (n_limbs == 0) return;
   rescale_post_kernel<<<ew_grid(T, n_limbs), 256, 0, s>>>(T, out, c, tmp, qlinv, qlinv_sh);
 }

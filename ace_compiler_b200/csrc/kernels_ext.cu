@@ -2,6 +2,7 @@
 // CKKS bootstrap needs (ModRaise, scalar add, plaintext inner product).  All HBM-bound: one
 // thread per coefficient, grid.y = limb, every output limb written exactly once.
 #include "kernels.cuh"
+#include "prof.h"
 
 namespace ace {
 
@@ -26,6 +27,7 @@ __global__ void __launch_bounds__(256) ew_basis_kernel(DeviceTables T, u64* __re
 
 void launch_ew_basis(const DeviceTables& T, EwOp op, u64* r, const u64* a, const u64* b,
                      Basis bs, cudaStream_t s) {
+  prof::Scope prof_scope_("ew_basis", s);
   if (bs.width() == 0) return;
   dim3 grid = grid_for(T, bs.width());
   switch (op) {
@@ -49,6 +51,7 @@ __global__ void __launch_bounds__(256) gather_basis_kernel(DeviceTables T, u64* 
 
 void launch_gather_basis(const DeviceTables& T, u64* r, const u64* a, const int64_t* order,
                          Basis bs, cudaStream_t s) {
+  prof::Scope prof_scope_("gather_basis", s);
   if (bs.width() == 0) return;
   gather_basis_kernel<<<grid_for(T, bs.width()), 256, 0, s>>>(T, r, a, order, bs);
 }
@@ -65,6 +68,7 @@ __global__ void __launch_bounds__(256) add_scalar_kernel(DeviceTables T, u64* __
 
 void launch_add_scalar(const DeviceTables& T, u64* r, const u64* a, const ScalarPack& sc,
                        u32 g0, u32 n_limbs, cudaStream_t s) {
+  prof::Scope prof_scope_("add_scalar", s);
   if (n_limbs == 0) return;
   add_scalar_kernel<<<grid_for(T, n_limbs), 256, 0, s>>>(T, r, a, sc, g0);
 }
@@ -82,6 +86,7 @@ __global__ void __launch_bounds__(256) mul_scalar_pack_kernel(DeviceTables T,
 
 void launch_mul_scalar_pack(const DeviceTables& T, u64* r, const u64* a, const ScalarPack& sc,
                             Basis bs, cudaStream_t s) {
+  prof::Scope prof_scope_("mul_scalar_pack", s);
   if (bs.width() == 0) return;
   mul_scalar_pack_kernel<<<grid_for(T, bs.width()), 256, 0, s>>>(T, r, a, sc, bs);
 }
@@ -99,6 +104,7 @@ __global__ void __launch_bounds__(256) mod_raise_kernel(DeviceTables T, u64* __r
 
 void launch_mod_raise(const DeviceTables& T, u64* out, const u64* in, u32 n_limbs,
                       cudaStream_t s) {
+  prof::Scope prof_scope_("mod_raise", s);
   if (n_limbs == 0) return;
   mod_raise_kernel<<<grid_for(T, n_limbs), 256, 0, s>>>(T, out, in);
 }
@@ -113,6 +119,7 @@ __global__ void __launch_bounds__(256) monomial_kernel(DeviceTables T, u64* __re
 
 void launch_monomial(const DeviceTables& T, u64* out, u32 index, bool negative, u32 n_limbs,
                      cudaStream_t s) {
+  prof::Scope prof_scope_("monomial", s);
   if (n_limbs == 0) return;
   monomial_kernel<<<grid_for(T, n_limbs), 256, 0, s>>>(T, out, index, negative ? 1u : 0u);
 }
@@ -138,6 +145,7 @@ __global__ void __launch_bounds__(256) pt_dot_kernel(DeviceTables T, u64* __rest
 
 void launch_pt_dot(const DeviceTables& T, u64* out0, u64* out1, const DotArgs& args, Basis bs,
                    cudaStream_t s) {
+  prof::Scope prof_scope_("pt_dot", s);
   if (bs.width() == 0 || args.n == 0) return;
   pt_dot_kernel<<<grid_for(T, bs.width()), 256, 0, s>>>(T, out0, out1, args, bs);
 }
@@ -154,6 +162,7 @@ __global__ void __launch_bounds__(256) mul_scalar_add_kernel(
 
 void launch_mul_scalar_add(const DeviceTables& T, u64* r, const u64* acc, const u64* c,
                            const u64* sc, const u64* sc_sh, u32 n_limbs, cudaStream_t s) {
+  prof::Scope prof_scope_("mul_scalar_add", s);
   if (n_limbs == 0) return;
   mul_scalar_add_kernel<<<grid_for(T, n_limbs), 256, 0, s>>>(T, r, acc, c, sc, sc_sh);
 }

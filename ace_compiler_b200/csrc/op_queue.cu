@@ -1,5 +1,6 @@
 // op_queue.cu -- see op_queue.h
 #include "op_queue.h"
+#include "prof.h"
 
 #include <algorithm>
 
@@ -79,6 +80,7 @@ void OpQueue::flush() {
   static thread_local EwPack pack;
   const u32 n = (u32)items_.size();
   dim3 grid((T_->N + 255) / 256, 1);
+  prof::Scope prof_scope_(gather_mode_ ? "gather_batch" : "ew_chain", stream_);
   if (gather_mode_) {
     for (u32 k = 0; k < n; k++) pack.it[k] = items_[k];
     pack.n_chains = n;

@@ -22,6 +22,7 @@
 #include "../../include/rt_ant/rt_ant.h"
 #include "evaluator.h"
 #include "op_queue.h"
+#include "prof.h"
 
 using namespace ace;
 
@@ -73,19 +74,30 @@ bool quiet() {
 bool g_no_batch = false;
 bool g_stats_on = false, g_stats_sync = false;  // =2: sync around every scope (true GPU time)
 void stats_sync();
+void stats_flush();
 inline double wall() {
   struct timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
   return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
+const char* const kApiScope[] = {nullptr, nullptr, nullptr, "api.Decomp_modup", "api.Mod_down",
+                                 "api.Rescale", "api.Encode", "api.Bootstrap", nullptr, nullptr,
+                                 "api.Copy/Set_coeffs"};
+cudaStream_t prof_stream();
 struct StatScope {
   int id; double t0;
+  int pslot = -1;
   explicit StatScope(int i) : id(i), t0(0) {
+    if (prof::on && kApiScope[i]) {
+      stats_flush();
+      pslot = prof::begin(kApiScope[i], prof_stream());
+    }
     if (!g_stats_on) return;
     if (g_stats_sync) stats_sync();
     t0 = wall();
   }
   ~StatScope() {
+    if (pslot >= 0) prof::end(pslot, prof_stream());
     if (!g_stats_on) return;
     if (g_stats_sync) stats_sync();
     g_stats[id].calls++;
@@ -98,6 +110,10 @@ struct StatScope {
   abort();  // FMT_ASSERT semantics (rtlib/include/common/error.h:23-29)
 }
 
+cudaStream_t prof_stream() { return g_ctx ? g_ctx->stream : nullptr; }
+void stats_flush() {
+  if (g_queue) g_queue->flush();
+}
 void stats_sync() {
   if (!g_ctx) return;
   if (g_queue) g_queue->flush();
@@ -162,9 +178,11 @@ void init_poly(POLYNOMIAL* res, const POLYNOMIAL* poly) {
     alloc_poly_data(res, poly->_ring_degree, poly->_num_primes, poly->_num_primes_p);
   } else {
     guard([&] {
+      Context* c = ctx();
+      prof::Scope ps("memset(init_poly)", c->stream);
       ACE_CUDA(cudaMemsetAsync(res->_data, 0,
                                res->_num_alloc_primes * (size_t)res->_ring_degree * 8,
-                               ctx()->stream));
+                               c->stream));
     });
     res->_ring_degree  = poly->_ring_degree;
     res->_num_primes   = poly->_num_primes;
@@ -327,6 +345,7 @@ API void Prepare_context(void) {
   if (g_ctx) return;
   g_stats_on   = getenv("ACE_B200_STATS") && getenv("ACE_B200_STATS")[0] >= '1';
   g_stats_sync = g_stats_on && getenv("ACE_B200_STATS")[0] == '2';
+  prof::enable(getenv("ACE_B200_PROF") && getenv("ACE_B200_PROF")[0] == '1');
   if (!Get_context_params) die("Get_context_params() not linked (emitted unit missing)");
   CKKS_PARAMS* p = Get_context_params();
   size_t parts = p->_num_q_parts;
@@ -510,8 +529,10 @@ API void Print_cipher_msg(FILE* fp, const char* name, CIPHER ciph, uint32_t len)
 
 API void Run_main_graph(void) {  // common/src/rt_lib.c:16-20
   if (!Main_graph) die("Main_graph() not linked");
+  if (prof::on) { ctx(); prof::reset(); }
   if (!Main_graph()) die("Main_graph failed");
   guard([&] { ctx()->sync(); });
+  if (prof::on) prof::report("Main_graph");
 }
 
 API void Tm_start(const char* msg) {
