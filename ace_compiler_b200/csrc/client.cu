@@ -8,6 +8,7 @@
 //   encrypt    src/util/ckks_encryptor.c:20-95        decrypt  src/util/ckks_decryptor.c:19-65
 //   encode     src/util/ckks_encoder.c:199-299 (+464-528 for constants), src/util/ntt.c:713-753
 //   decode     src/util/ckks_encoder.c:649-703, src/util/polynomial.c:467-497, ntt.c:672-711
+#include <algorithm>
 #include <cmath>
 #include <complex>
 #include <cstring>
@@ -272,14 +273,39 @@ __device__ __forceinline__ void emb_butterfly(cplx& a, cplx& b, const cplx w) {
 
 constexpr u32 kEmbTileLog = 12, kEmbTile = 1u << kEmbTileLog;
 
+// Messages of one batch: job j reads len[j] values of type kind[j] from src[j]; its N/2-slot
+// work vector is v + j * slots.
+constexpr int kMaxEnc = 64;
+struct EncSrcBatch {
+  u32         n;
+  const void* src[kMaxEnc];
+  u32         len[kMaxEnc];
+  uint8_t     kind[kMaxEnc];
+};
+// Output limbs of one batch: limb y belongs to job[y], uses modulus g[y], is multiplied by
+// pw[y] (Delta^(sf_degree-1) mod q, 0 = no factor) and written to out[y].
+constexpr int kMaxEncLimbs = 160;
+struct EncLimbBatch {
+  u32      n;
+  u64*     out[kMaxEncLimbs];
+  u64      pw[kMaxEncLimbs];
+  uint16_t g[kMaxEncLimbs];
+  uint16_t job[kMaxEncLimbs];
+};
+
 template <int SA>
-__global__ void __launch_bounds__(128) emb_inv_strided(cplx* __restrict__ v,
+__global__ void __launch_bounds__(128) emb_inv_strided(cplx* __restrict__ vall,
                                                        const cplx* __restrict__ tw,
-                                                       const void* __restrict__ src, int kind,
-                                                       u32 len, u32 logslots) {
+                                                       const __grid_constant__ EncSrcBatch B,
+                                                       u32 logslots) {
   constexpr int R = 1 << SA;
   const u32 stride = kEmbTile, col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= stride) return;
+  const u32   job  = blockIdx.y;
+  cplx*       v    = vall + ((size_t)job << logslots);
+  const void* src  = B.src[job];
+  const int   kind = B.kind[job];
+  const u32   len  = B.len[job];
   cplx x[R];
 #pragma unroll
   for (int r = 0; r < R; r++) x[r] = emb_load(src, kind, r * stride + col, len);
@@ -299,12 +325,17 @@ __global__ void __launch_bounds__(128) emb_inv_strided(cplx* __restrict__ v,
 }
 
 // tile = min(slots, 4096) elements; from_src: no strided phase ran, convert the input here
-__global__ void __launch_bounds__(512) emb_inv_tile(cplx* __restrict__ v,
+__global__ void __launch_bounds__(512) emb_inv_tile(cplx* __restrict__ vall,
                                                     const cplx* __restrict__ tw,
-                                                    const void* __restrict__ src, int kind,
-                                                    u32 len, u32 logtile, int from_src) {
+                                                    const __grid_constant__ EncSrcBatch B,
+                                                    u32 logtile, u32 logslots, int from_src) {
   extern __shared__ double emb_sm[];
   cplx* t = reinterpret_cast<cplx*>(emb_sm);
+  const u32   job  = blockIdx.y;
+  cplx*       v    = vall + ((size_t)job << logslots);
+  const void* src  = B.src[job];
+  const int   kind = B.kind[job];
+  const u32   len  = B.len[job];
   const u32 tile = 1u << logtile, base = blockIdx.x * tile;
   for (u32 e = threadIdx.x; e < tile; e += blockDim.x)
     t[e] = from_src ? emb_load(src, kind, base + e, len) : v[base + e];
@@ -322,15 +353,17 @@ __global__ void __launch_bounds__(512) emb_inv_tile(cplx* __restrict__ v,
 }
 
 // bit-reverse, divide by slots, scale by Delta, round, spread with `gap`, reduce into every limb
-// (ckks_encoder.c:247-263 + polynomial.c:362-392); powp[l] = Delta^(sf_degree-1) mod q_l or 0
-__global__ void emb_round_rns_kernel(DeviceTables T, LimbBatch b, const cplx* __restrict__ v,
-                                     u32 slots, u32 logslots, double delta,
-                                     const ScalarPack powp, int use_pow) {
+// (ckks_encoder.c:247-263 + polynomial.c:362-392)
+__global__ void __launch_bounds__(256) emb_round_rns_kernel(DeviceTables T,
+                                                            const __grid_constant__ EncLimbBatch B,
+                                                            const cplx* __restrict__ vall,
+                                                            u32 slots, u32 logslots, double delta) {
   const u32     limb = blockIdx.y;
-  const Modulus m    = T.mod[b.g[limb]];
-  u64*          out  = b.base + (size_t)b.slot[limb] * T.N;
+  const Modulus m    = T.mod[B.g[limb]];
+  u64*          out  = B.out[limb];
+  const cplx*   v    = vall + ((size_t)B.job[limb] << logslots);
   const u32     gap  = T.N / (2 * slots);
-  const u64     pw   = use_pow ? powp.v[limb] : 0;
+  const u64     pw   = B.pw[limb];
   for (u32 n = blockIdx.x * blockDim.x + threadIdx.x; n < T.N; n += gridDim.x * blockDim.x) {
     u64 res = 0;
     if (n % gap == 0) {
@@ -419,66 +452,112 @@ void Context::encode_any(u64* out, const double* vals, const std::complex<double
 // Encode_impl on a message that already lives in HBM (kind: 0 float32, 1 float64, 2 complex)
 void Context::encode_dev(u64* out, const void* dev_src, int kind, size_t len, u32 level,
                          u32 slots, u32 sf_degree, u32 p_cnt) {
+  EncodeJob j{out, dev_src, kind, (u32)len, level, slots, sf_degree, p_cnt};
+  encode_batch(&j, 1);
+}
+
+// Encode_impl for a group of messages: the special IFFT of all of them in two launches, one
+// rounding / RNS launch and one NTT launch over all their output limbs.
+void Context::encode_batch(const EncodeJob* jobs_in, size_t n_jobs) {
+  if (n_jobs == 0) return;
   init_encoder();
-  if (slots == 0) slots = N / 2;
-  if (level == 0) level = (u32)L;
-  tr(TR_ENCODE, level + p_cnt);
-  if (len > slots || slots > N / 2 || (slots & (slots - 1)))
-    throw std::runtime_error("encode: bad slot count");
-  if (level > L || sf_degree < 1 || p_cnt > K) throw std::runtime_error("encode: bad level");
-  u32 logslots = 0;
-  while ((1u << logslots) < slots) logslots++;
-  cplx* dv = (cplx*)enc_buf_;
-  const cplx* tw = (const cplx*)enc_tw_;
-  prof::Scope prof_scope_("encode(total)", stream);
-  int prof_fft_ = prof::on ? prof::begin("encode_fft", stream) : -1;
-  const u32 logtile = logslots < kEmbTileLog ? logslots : kEmbTileLog;
-  const int sa = (int)(logslots - logtile);
-  if (sa > 0) {
-    dim3 grid(kEmbTile / 128);
-    switch (sa) {
-      case 1: emb_inv_strided<1><<<grid, 128, 0, stream>>>(dv, tw, dev_src, kind, (u32)len, logslots); break;
-      case 2: emb_inv_strided<2><<<grid, 128, 0, stream>>>(dv, tw, dev_src, kind, (u32)len, logslots); break;
-      case 3: emb_inv_strided<3><<<grid, 128, 0, stream>>>(dv, tw, dev_src, kind, (u32)len, logslots); break;
-      case 4: emb_inv_strided<4><<<grid, 128, 0, stream>>>(dv, tw, dev_src, kind, (u32)len, logslots); break;
-      default: throw std::runtime_error("encode: slot count too large");
-    }
+  std::vector<EncodeJob> jobs(jobs_in, jobs_in + n_jobs);
+  for (EncodeJob& j : jobs) {
+    if (j.slots == 0) j.slots = N / 2;
+    if (j.level == 0) j.level = (u32)L;
+    if (j.len > j.slots || j.slots > N / 2 || (j.slots & (j.slots - 1)))
+      throw std::runtime_error("encode: bad slot count");
+    if (j.level > L || j.sf_degree < 1 || j.p_cnt > K) throw std::runtime_error("encode: bad level");
+    tr(TR_ENCODE, j.level + j.p_cnt);
   }
-  {
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(emb_inv_tile, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(kEmbTile * sizeof(cplx)));
-      attr = true;
-    }
-    const u32 tile = 1u << logtile;
-    emb_inv_tile<<<slots / tile, tile / 2 < 512 ? (tile / 2 ? tile / 2 : 1) : 512,
-                   tile * sizeof(cplx), stream>>>(dv, tw, dev_src, kind, (u32)len, logtile,
-                                                  sa == 0);
-  }
-  if (prof_fft_ >= 0) prof::end(prof_fft_, stream);
+  // jobs of one launch share the slot count; emitted programs use N/2 throughout
+  std::stable_sort(jobs.begin(), jobs.end(),
+                   [](const EncodeJob& a, const EncodeJob& b) { return a.slots < b.slots; });
+  const cplx*  tw    = (const cplx*)enc_tw_;
   const double delta = (double)((u64)1 << params.scaling_mod_size);
-  const u32 nl = level + p_cnt;
-  LimbBatch b;
-  b.base = out; b.src = nullptr; b.n = nl;
-  ScalarPack powp;
-  for (u32 l = 0; l < nl; l++) {
-    b.slot[l] = (uint16_t)l;
-    b.g[l]    = (uint16_t)(l < level ? l : L + (l - level));
-    powp.v[l] = 0;
-    if (sf_degree > 1 && l < level) {
-      u64 q = mod[l], p = (u64)delta % q;
-      for (u32 d = 2; d < sf_degree; d++) p = hm::mulmod(p, (u64)delta % q, q);
-      powp.v[l] = p;
+  prof::Scope  prof_scope_("encode(total)", stream);
+  size_t at = 0;
+  while (at < jobs.size()) {
+    const u32 slots = jobs[at].slots;
+    size_t    cnt   = 1;
+    while (at + cnt < jobs.size() && jobs[at + cnt].slots == slots && cnt < (size_t)kMaxEnc) cnt++;
+    u32 logslots = 0;
+    while ((1u << logslots) < slots) logslots++;
+    // work vectors: slots complex doubles per job (at most one limb's worth of bytes each)
+    cplx* dv = cnt == 1 ? (cplx*)enc_buf_
+                        : (cplx*)alloc_limbs((cnt * slots * sizeof(cplx) + (size_t)N * 8 - 1) / ((size_t)N * 8), false);
+    EncSrcBatch sb;
+    sb.n = (u32)cnt;
+    for (size_t k = 0; k < cnt; k++) {
+      sb.src[k] = jobs[at + k].src; sb.len[k] = jobs[at + k].len; sb.kind[k] = (uint8_t)jobs[at + k].kind;
     }
+    const u32 logtile = logslots < kEmbTileLog ? logslots : kEmbTileLog;
+    const int sa = (int)(logslots - logtile);
+    {
+      prof::Scope ps("encode_fft", stream);
+      if (sa > 0) {
+        dim3 grid(kEmbTile / 128, (u32)cnt);
+        switch (sa) {
+          case 1: emb_inv_strided<1><<<grid, 128, 0, stream>>>(dv, tw, sb, logslots); break;
+          case 2: emb_inv_strided<2><<<grid, 128, 0, stream>>>(dv, tw, sb, logslots); break;
+          case 3: emb_inv_strided<3><<<grid, 128, 0, stream>>>(dv, tw, sb, logslots); break;
+          case 4: emb_inv_strided<4><<<grid, 128, 0, stream>>>(dv, tw, sb, logslots); break;
+          default: throw std::runtime_error("encode: slot count too large");
+        }
+        launches++;
+      }
+      static bool attr = false;
+      if (!attr) {
+        cudaFuncSetAttribute(emb_inv_tile, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(kEmbTile * sizeof(cplx)));
+        attr = true;
+      }
+      const u32 tile = 1u << logtile;
+      emb_inv_tile<<<dim3(slots / tile, (u32)cnt), tile / 2 < 512 ? (tile / 2 ? tile / 2 : 1) : 512,
+                     tile * sizeof(cplx), stream>>>(dv, tw, sb, logtile, logslots, sa == 0);
+      launches++;
+    }
+    // rounding + RNS and the forward NTT over the output limbs of all jobs of the group
+    EncLimbBatch lb;
+    LimbPtrBatch nb;
+    lb.n = 0; nb.n = 0;
+    auto flush_round = [&] {
+      if (lb.n == 0) return;
+      prof::Scope ps("encode_round_rns", stream);
+      emb_round_rns_kernel<<<grid_for(N, lb.n), 256, 0, stream>>>(T, lb, dv, slots, logslots, delta);
+      launches++;
+      lb.n = 0;
+    };
+    auto flush_ntt = [&] {
+      if (nb.n == 0) return;
+      launch_ntt(T, nb, stream);
+      launches += (logN > 12) ? 2 : 1;
+      nb.n = 0;
+    };
+    for (size_t k = 0; k < cnt; k++) {
+      const EncodeJob& j = jobs[at + k];
+      const u32 nl = j.level + j.p_cnt;
+      for (u32 l = 0; l < nl; l++) {
+        if (lb.n == (u32)kMaxEncLimbs) { flush_round(); flush_ntt(); }
+        const u32 g = l < j.level ? l : (u32)L + (l - j.level);
+        u64 pw = 0;
+        if (j.sf_degree > 1 && l < j.level) {
+          u64 q = mod[l];
+          pw = (u64)delta % q;
+          for (u32 d = 2; d < j.sf_degree; d++) pw = hm::mulmod(pw, (u64)delta % q, q);
+        }
+        u64* o = j.out + (size_t)l * N;
+        lb.out[lb.n] = o; lb.pw[lb.n] = pw; lb.g[lb.n] = (uint16_t)g; lb.job[lb.n] = (uint16_t)k;
+        lb.n++;
+        nb.dst[nb.n] = o; nb.src[nb.n] = o; nb.g[nb.n] = (uint16_t)g;
+        nb.n++;
+      }
+    }
+    flush_round();
+    flush_ntt();
+    if (cnt > 1) free_limbs((u64*)dv);
+    at += cnt;
   }
-  {
-    prof::Scope ps("encode_round_rns", stream);
-    emb_round_rns_kernel<<<grid_for(N, nl), 256, 0, stream>>>(T, b, dv, slots, logslots, delta,
-                                                             powp, sf_degree > 1 ? 1 : 0);
-  }
-  launch_ntt(T, b, stream);
-  launches += (sa > 0 ? 1 : 0) + 2 + ((logN > 12) ? 2 : 1);
 }
 
 // Encode_val_at_level (ckks_encoder.c:464-528): constant plaintext, every coefficient of limb

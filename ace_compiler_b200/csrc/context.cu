@@ -186,14 +186,35 @@ Context::~Context() {
   if (enc_host_) cudaFreeHost(enc_host_);
   for (auto& kv : auto_orders_) cudaFree(kv.second);
   for (void* p : owned_) cudaFree(p);
+  cudaStreamSynchronize(stream);
+  for (auto& kv : block_limbs_) cudaFreeAsync(const_cast<u64*>(kv.first), stream);
+  cudaStreamSynchronize(stream);
   cudaStreamDestroy(stream);
 }
 
 // ---------------------------------------------------------------------------- memory
 u64* Context::alloc_limbs(size_t n_limbs, bool zero) {
-  u64*   p     = nullptr;
-  size_t bytes = std::max<size_t>(n_limbs, 1) * N * sizeof(u64);
-  ACE_CUDA(cudaMallocAsync(&p, bytes, stream));
+  n_limbs = std::max<size_t>(n_limbs, 1);
+  const size_t bytes = n_limbs * N * sizeof(u64);
+  u64* p = nullptr;
+  auto it = free_lists_.find(n_limbs);
+  if (it != free_lists_.end() && !it->second.empty()) {
+    p = it->second.back();
+    it->second.pop_back();
+    cached_bytes -= bytes;
+  } else {
+    // new blocks come from the driver's stream-ordered pool (no device synchronisation)
+    cudaError_t e = cudaMallocAsync(&p, bytes, stream);
+    if (e != cudaSuccess) {  // out of memory: give the cached blocks back and retry once
+      cudaGetLastError();
+      ACE_CUDA(cudaStreamSynchronize(stream));
+      trim_cache();
+      ACE_CUDA(cudaMallocAsync(&p, bytes, stream));
+    }
+    block_limbs_[p] = n_limbs;
+  }
+  live_bytes += bytes;
+  if (live_bytes > peak_bytes) peak_bytes = live_bytes;
   if (zero) {
     prof::Scope ps("memset(alloc)", stream);
     ACE_CUDA(cudaMemsetAsync(p, 0, bytes, stream));
@@ -201,7 +222,23 @@ u64* Context::alloc_limbs(size_t n_limbs, bool zero) {
   return p;
 }
 void Context::free_limbs(u64* p) {
-  if (p) ACE_CUDA(cudaFreeAsync(p, stream));
+  if (!p) return;
+  auto it = block_limbs_.find(p);
+  if (it == block_limbs_.end()) throw std::runtime_error("free_limbs: unknown block");
+  const size_t bytes = it->second * N * sizeof(u64);
+  free_lists_[it->second].push_back(p);
+  cached_bytes += bytes;
+  live_bytes -= bytes;
+}
+void Context::trim_cache() {
+  for (auto& kv : free_lists_) {
+    for (u64* p : kv.second) {
+      block_limbs_.erase(p);
+      cudaFreeAsync(p, stream);
+    }
+    kv.second.clear();
+  }
+  cached_bytes = 0;
 }
 void Context::upload(u64* dst, const u64* src, size_t n_limbs) {
   ACE_CUDA(cudaMemcpyAsync(dst, src, n_limbs * N * sizeof(u64), cudaMemcpyHostToDevice, stream));

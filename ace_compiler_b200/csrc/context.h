@@ -40,6 +40,15 @@ struct SwitchKey {
                                " at " __FILE__ ":" + std::to_string(__LINE__));           \
   } while (0)
 
+// Jobs of the batched polynomial-level primitives (batch.cu): what one reference call
+// (Decomp_modup / Mod_down / Rescale / Encode_plain_from_float) asks for.  The scheduler
+// (sched.h) collects independent calls and hands them over together, so that each step of the
+// primitive is one launch over the limbs of all of them.
+struct ModupJob   { u64* out; const u64* digit; u32 num_q, part; };  // digit: the part's own limbs
+struct ModdownJob { u64* out; const u64* in; u32 num_q; };            // in: [num_q | K]
+struct RescaleJob { u64* out; const u64* in; u32 num_q; };
+struct EncodeJob  { u64* out; const void* src; int kind; u32 len, level, slots, sf_degree, p_cnt; };
+
 class Context {
  public:
   Context(const Params& p, int device);
@@ -56,8 +65,17 @@ class Context {
   DeviceTables     T;
 
   // ---- memory: limb arrays in HBM, stream-ordered
+  // Blocks are recycled through per-size free lists: every consumer runs on `stream`, so a
+  // block handed out again is only touched after the work queued on it before the free.
   u64* alloc_limbs(size_t n_limbs, bool zero);
   void free_limbs(u64* p);
+  void trim_cache();  // return every cached block to the driver
+  size_t block_limbs(const u64* p) const {
+    auto it = block_limbs_.find(p);
+    if (it == block_limbs_.end()) throw std::runtime_error("unknown limb block");
+    return it->second;
+  }
+  size_t cached_bytes = 0, live_bytes = 0, peak_bytes = 0;
   void upload(u64* dst, const u64* src, size_t n_limbs);
   void download(u64* dst, const u64* src, size_t n_limbs);
   void sync();
@@ -91,6 +109,11 @@ class Context {
   }
   void mod_down(u64* out, const u64* in, u32 num_q);
   void rescale(u64* out, const u64* in, u32 num_q);
+  // the same primitives over many independent polynomials at once (batch.cu)
+  void modup_batch(const ModupJob* jobs, size_t n);
+  void moddown_batch(const ModdownJob* jobs, size_t n);
+  void rescale_batch(const RescaleJob* jobs, size_t n);
+  void encode_batch(const EncodeJob* jobs, size_t n);
 
   // ---- keys and automorphisms
   u32            auto_index(int32_t rot_idx) const;
@@ -160,6 +183,8 @@ class Context {
   std::unordered_map<u32, int64_t*>        auto_orders_;
   std::unordered_map<u32, SwitchKey>       rot_keys_;
   std::vector<void*>                       owned_;  // device tables freed in the destructor
+  std::unordered_map<size_t, std::vector<u64*>> free_lists_;  // by size in limbs
+  std::unordered_map<const u64*, size_t>        block_limbs_;
   // ModDown tables
   u64 *phat_inv_, *phat_inv_sh_, *phat_mod_q_;  // [K], [K], [L][K]
   u64 *pinv_mod_q_, *pinv_mod_q_sh_;            // [L]

@@ -30,6 +30,20 @@ constexpr int kTileLog   = 12;
 constexpr int kTile      = 1 << kTileLog;
 constexpr int kNttThreads = 512;
 
+// limb i of a batch: where it is read from and where the result goes (see kernels.cuh)
+__device__ __forceinline__ u64* batch_dst(const LimbBatch& b, u32 i, u32 N) {
+  return b.base + (size_t)b.slot[i] * N;
+}
+__device__ __forceinline__ const u64* batch_src(const LimbBatch& b, u32 i, u32 N) {
+  return b.src ? b.src + (size_t)b.src_slot[i] * N : b.base + (size_t)b.slot[i] * N;
+}
+__device__ __forceinline__ bool batch_has_src(const LimbBatch& b) { return b.src != nullptr; }
+__device__ __forceinline__ u64* batch_dst(const LimbPtrBatch& b, u32 i, u32) { return b.dst[i]; }
+__device__ __forceinline__ const u64* batch_src(const LimbPtrBatch& b, u32 i, u32) {
+  return b.src[i];
+}
+__device__ __forceinline__ bool batch_has_src(const LimbPtrBatch&) { return true; }
+
 // Harvey-style lazy butterflies: values stay in [0, 4q) (forward) / [0, 2q) (inverse) between
 // stages, one conditional subtraction per butterfly; the final pass normalises to [0, q), so
 // the stored result is the same canonical residue the reference produces (ntt.c:206-263).
@@ -53,14 +67,14 @@ __device__ __forceinline__ void gs_butterfly(u64& u, u64& v, u64 w, u64 wsh, u64
 __device__ __forceinline__ u64 normalize4(u64 a, u64 q) { return csub(csub(a, 2 * q), q); }
 
 // ---- strided phase, forward: stages 0 .. SA-1, R = 2^SA rows at stride N/R -------------
-template <int SA>
-__global__ void __launch_bounds__(128) ntt_fwd_strided(DeviceTables T, LimbBatch b) {
+template <int SA, class B>
+__global__ void __launch_bounds__(128) ntt_fwd_strided(DeviceTables T, const __grid_constant__ B b) {
   constexpr int R = 1 << SA;
   const u32 limb  = blockIdx.y;
   const u32 g     = b.g[limb];
   const u64 q     = T.mod[g].q;
-  u64*      data  = b.base + (size_t)b.slot[limb] * T.N;
-  const u64* in   = b.src ? b.src + (size_t)b.src_slot[limb] * T.N : data;
+  u64*      data  = batch_dst(b, limb, T.N);
+  const u64* in   = batch_src(b, limb, T.N);
   const u64* tw   = T.tw + (size_t)g * T.N;
   const u64* twsh = T.tw_sh + (size_t)g * T.N;
   const u32 stride = T.N >> SA;  // = 4096
@@ -85,13 +99,13 @@ __global__ void __launch_bounds__(128) ntt_fwd_strided(DeviceTables T, LimbBatch
 }
 
 // ---- strided phase, inverse: stages with t = N/R .. N/2, then * N^-1 --------------------
-template <int SA>
-__global__ void __launch_bounds__(128) ntt_inv_strided(DeviceTables T, LimbBatch b) {
+template <int SA, class B>
+__global__ void __launch_bounds__(128) ntt_inv_strided(DeviceTables T, const __grid_constant__ B b) {
   constexpr int R = 1 << SA;
   const u32 limb  = blockIdx.y;
   const u32 g     = b.g[limb];
   const u64 q     = T.mod[g].q;
-  u64*      data  = b.base + (size_t)b.slot[limb] * T.N;
+  u64*      data  = batch_dst(b, limb, T.N);
   const u64* tw   = T.itw + (size_t)g * T.N;
   const u64* twsh = T.itw_sh + (size_t)g * T.N;
   const u64 ninv = T.n_inv[g], ninv_sh = T.n_inv_sh[g];
@@ -118,7 +132,8 @@ __global__ void __launch_bounds__(128) ntt_inv_strided(DeviceTables T, LimbBatch
 }
 
 // ---- tile phase, forward: stages s0 .. logN-1 on a contiguous tile in shared memory ----
-__global__ void __launch_bounds__(kNttThreads) ntt_fwd_tile(DeviceTables T, LimbBatch b) {
+template <class B>
+__global__ void __launch_bounds__(kNttThreads) ntt_fwd_tile(DeviceTables T, const __grid_constant__ B b) {
   extern __shared__ u64 sm[];
   const u32 limb   = blockIdx.y;
   const u32 g      = b.g[limb];
@@ -126,10 +141,10 @@ __global__ void __launch_bounds__(kNttThreads) ntt_fwd_tile(DeviceTables T, Limb
   const u32 tile   = T.N < (u32)kTile ? T.N : (u32)kTile;
   const u32 tlog   = T.logN < (u32)kTileLog ? T.logN : (u32)kTileLog;
   const u32 tbase  = blockIdx.x * tile;
-  u64*      data   = b.base + (size_t)b.slot[limb] * T.N + tbase;
+  u64*      data   = batch_dst(b, limb, T.N) + tbase;
   const u64* tw    = T.tw + (size_t)g * T.N;
   const u64* twsh  = T.tw_sh + (size_t)g * T.N;
-  const u64* in    = b.src ? b.src + (size_t)b.src_slot[limb] * T.N + tbase : data;
+  const u64* in    = batch_src(b, limb, T.N) + tbase;
   for (u32 i = threadIdx.x; i < tile; i += blockDim.x) sm[i] = in[i];
   __syncthreads();
   const u32 s0 = T.logN - tlog;
@@ -151,7 +166,8 @@ __global__ void __launch_bounds__(kNttThreads) ntt_fwd_tile(DeviceTables T, Limb
 }
 
 // ---- tile phase, inverse: stages with t = 1 .. tile/2; folds N^-1 when it is the only phase
-__global__ void __launch_bounds__(kNttThreads) ntt_inv_tile(DeviceTables T, LimbBatch b) {
+template <class B>
+__global__ void __launch_bounds__(kNttThreads) ntt_inv_tile(DeviceTables T, const __grid_constant__ B b) {
   extern __shared__ u64 sm[];
   const u32 limb   = blockIdx.y;
   const u32 g      = b.g[limb];
@@ -159,10 +175,10 @@ __global__ void __launch_bounds__(kNttThreads) ntt_inv_tile(DeviceTables T, Limb
   const u32 tile   = T.N < (u32)kTile ? T.N : (u32)kTile;
   const u32 tlog   = T.logN < (u32)kTileLog ? T.logN : (u32)kTileLog;
   const u32 tbase  = blockIdx.x * tile;
-  u64*      data   = b.base + (size_t)b.slot[limb] * T.N + tbase;
+  u64*      data   = batch_dst(b, limb, T.N) + tbase;
   const u64* tw    = T.itw + (size_t)g * T.N;
   const u64* twsh  = T.itw_sh + (size_t)g * T.N;
-  const u64* in    = b.src ? b.src + (size_t)b.src_slot[limb] * T.N + tbase : data;
+  const u64* in    = batch_src(b, limb, T.N) + tbase;
   for (u32 i = threadIdx.x; i < tile; i += blockDim.x) sm[i] = in[i];
   __syncthreads();
   for (u32 lt = 0; lt < tlog; lt++) {
@@ -249,21 +265,21 @@ __device__ __forceinline__ void gs_radix8(u64 (&x)[8], const u64* __restrict__ t
   }
 }
 
-__global__ void __launch_bounds__(512, 2) ntt_fwd_tile8(DeviceTables T, LimbBatch b) {
+template <class B>
+__global__ void __launch_bounds__(512, 2) ntt_fwd_tile8(DeviceTables T, const __grid_constant__ B b) {
   extern __shared__ u64 sm[];
   u64* buf[2] = {sm, sm + kTileSm};
   const u32 limb  = blockIdx.y;
   const u32 g     = b.g[limb];
   const u64 q     = T.mod[g].q;
   const u32 tbase = blockIdx.x * kTile;
-  u64*      data  = b.base + (size_t)b.slot[limb] * T.N + tbase;
+  u64*      data  = batch_dst(b, limb, T.N) + tbase;
   const u64* tw   = T.tw + (size_t)g * T.N;
   const u64* twsh = T.tw_sh + (size_t)g * T.N;
   const u32 tid   = threadIdx.x;
   const u32 m0    = T.N >> kTileLog;  // groups of the first tile stage (stride 2048)
   // the strided phase (if any) already moved the limb to its destination
-  const u64* in = (b.src && T.logN == (u32)kTileLog)
-                      ? b.src + (size_t)b.src_slot[limb] * T.N + tbase : data;
+  const u64* in = T.logN == (u32)kTileLog ? batch_src(b, limb, T.N) + tbase : data;
   u64 x[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) x[k] = in[tid + 512 * k];
@@ -288,20 +304,21 @@ __global__ void __launch_bounds__(512, 2) ntt_fwd_tile8(DeviceTables T, LimbBatc
     out[k] = make_ulonglong2(normalize4(x[2 * k], q), normalize4(x[2 * k + 1], q));
 }
 
-__global__ void __launch_bounds__(512, 2) ntt_inv_tile8(DeviceTables T, LimbBatch b) {
+template <class B>
+__global__ void __launch_bounds__(512, 2) ntt_inv_tile8(DeviceTables T, const __grid_constant__ B b) {
   extern __shared__ u64 sm[];
   u64* buf[2] = {sm, sm + kTileSm};
   const u32 limb  = blockIdx.y;
   const u32 g     = b.g[limb];
   const u64 q     = T.mod[g].q;
   const u32 tbase = blockIdx.x * kTile;
-  u64*      data  = b.base + (size_t)b.slot[limb] * T.N + tbase;
+  u64*      data  = batch_dst(b, limb, T.N) + tbase;
   const u64* tw   = T.itw + (size_t)g * T.N;
   const u64* twsh = T.itw_sh + (size_t)g * T.N;
   const u32 tid   = threadIdx.x;
   u64 x[8];
   {
-    const u64* src = b.src ? b.src + (size_t)b.src_slot[limb] * T.N + tbase : data;
+    const u64* src = batch_src(b, limb, T.N) + tbase;
     const ulonglong2* in = reinterpret_cast<const ulonglong2*>(src + 8 * tid);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -333,68 +350,74 @@ __global__ void __launch_bounds__(512, 2) ntt_inv_tile8(DeviceTables T, LimbBatc
   for (int k = 0; k < 8; k++) data[tid + 512 * k] = x[k];
 }
 
-template <int SA>
-static void launch_strided(bool fwd, const DeviceTables& T, const LimbBatch& b,
-                           cudaStream_t s) {
+template <int SA, class B>
+static void launch_strided(bool fwd, const DeviceTables& T, const B& b, cudaStream_t s) {
   dim3 grid((T.N >> SA) / 128, b.n);
   if (fwd) {
-    ntt_fwd_strided<SA><<<grid, 128, 0, s>>>(T, b);
+    ntt_fwd_strided<SA, B><<<grid, 128, 0, s>>>(T, b);
   } else {
-    ntt_inv_strided<SA><<<grid, 128, 0, s>>>(T, b);
+    ntt_inv_strided<SA, B><<<grid, 128, 0, s>>>(T, b);
   }
 }
 
-static void launch_strided_any(bool fwd, const DeviceTables& T, const LimbBatch& b,
-                               cudaStream_t s) {
+template <class B>
+static void launch_strided_any(bool fwd, const DeviceTables& T, const B& b, cudaStream_t s) {
   switch (T.logN - kTileLog) {
-    case 1: launch_strided<1>(fwd, T, b, s); break;
-    case 2: launch_strided<2>(fwd, T, b, s); break;
-    case 3: launch_strided<3>(fwd, T, b, s); break;
-    case 4: launch_strided<4>(fwd, T, b, s); break;
-    case 5: launch_strided<5>(fwd, T, b, s); break;
+    case 1: launch_strided<1, B>(fwd, T, b, s); break;
+    case 2: launch_strided<2, B>(fwd, T, b, s); break;
+    case 3: launch_strided<3, B>(fwd, T, b, s); break;
+    case 4: launch_strided<4, B>(fwd, T, b, s); break;
+    case 5: launch_strided<5, B>(fwd, T, b, s); break;
     default: break;
   }
 }
 
-void launch_ntt(const DeviceTables& T, const LimbBatch& b, cudaStream_t s) {
-  prof::Scope prof_scope_("ntt", s);
+template <class B>
+static void launch_ntt_impl(const DeviceTables& T, const B& b, cudaStream_t s) {
   if (b.n == 0) return;
+  prof::Scope prof_scope_("ntt", s);
   const u32 tile = T.N < (u32)kTile ? T.N : (u32)kTile;
-  if (T.logN > (u32)kTileLog) launch_strided_any(true, T, b, s);
+  if (T.logN > (u32)kTileLog) launch_strided_any<B>(true, T, b, s);
   dim3 grid(T.N / tile, b.n);
   if (T.logN >= (u32)kTileLog) {
     static bool attr = false;
     if (!attr) {
-      cudaFuncSetAttribute(ntt_fwd_tile8, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaFuncSetAttribute(ntt_fwd_tile8<B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            2 * kTileSm * (int)sizeof(u64));
       attr = true;
     }
-    ntt_fwd_tile8<<<grid, 512, 2 * kTileSm * sizeof(u64), s>>>(T, b);
+    ntt_fwd_tile8<B><<<grid, 512, 2 * kTileSm * sizeof(u64), s>>>(T, b);
     return;
   }
   u32  threads = tile / 2 < (u32)kNttThreads ? tile / 2 : (u32)kNttThreads;
-  ntt_fwd_tile<<<grid, threads, tile * sizeof(u64), s>>>(T, b);
+  ntt_fwd_tile<B><<<grid, threads, tile * sizeof(u64), s>>>(T, b);
 }
 
-void launch_intt(const DeviceTables& T, const LimbBatch& b, cudaStream_t s) {
-  prof::Scope prof_scope_("intt", s);
+template <class B>
+static void launch_intt_impl(const DeviceTables& T, const B& b, cudaStream_t s) {
   if (b.n == 0) return;
+  prof::Scope prof_scope_("intt", s);
   const u32 tile = T.N < (u32)kTile ? T.N : (u32)kTile;
   dim3 grid(T.N / tile, b.n);
   if (T.logN >= (u32)kTileLog) {
     static bool attr = false;
     if (!attr) {
-      cudaFuncSetAttribute(ntt_inv_tile8, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaFuncSetAttribute(ntt_inv_tile8<B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            2 * kTileSm * (int)sizeof(u64));
       attr = true;
     }
-    ntt_inv_tile8<<<grid, 512, 2 * kTileSm * sizeof(u64), s>>>(T, b);
+    ntt_inv_tile8<B><<<grid, 512, 2 * kTileSm * sizeof(u64), s>>>(T, b);
   } else {
     u32 threads = tile / 2 < (u32)kNttThreads ? tile / 2 : (u32)kNttThreads;
-    ntt_inv_tile<<<grid, threads, tile * sizeof(u64), s>>>(T, b);
+    ntt_inv_tile<B><<<grid, threads, tile * sizeof(u64), s>>>(T, b);
   }
-  if (T.logN > (u32)kTileLog) launch_strided_any(false, T, b, s);
+  if (T.logN > (u32)kTileLog) launch_strided_any<B>(false, T, b, s);
 }
+
+void launch_ntt(const DeviceTables& T, const LimbBatch& b, cudaStream_t s) { launch_ntt_impl(T, b, s); }
+void launch_intt(const DeviceTables& T, const LimbBatch& b, cudaStream_t s) { launch_intt_impl(T, b, s); }
+void launch_ntt(const DeviceTables& T, const LimbPtrBatch& b, cudaStream_t s) { launch_ntt_impl(T, b, s); }
+void launch_intt(const DeviceTables& T, const LimbPtrBatch& b, cudaStream_t s) { launch_intt_impl(T, b, s); }
 
 // ------------------------------------------------------------------------------------
 // Element-wise kernels (HBM-bound): one thread per coefficient, grid.y = limb.
@@ -477,7 +500,7 @@ void launch_mul_scalar(const DeviceTables& T, u64* r, const u64* a, const u64* s
 // (n_in + n_out) limbs; the work is n_in*n_out 64x64->128 MACs per coefficient (INT-bound).
 // ------------------------------------------------------------------------------------
 struct ConvDescPack {
-  ConvDesc d[6];
+  ConvDesc d[kMaxConvPack];
 };
 
 template <int MAXIN>
@@ -635,6 +658,63 @@ void launch_rescale_post(const DeviceTables& T, u64* out, const u64* c, const u6
   prof::Scope prof_scope_("rescale_post", s);
   if (n_limbs == 0) return;
   rescale_post_kernel<<<ew_grid(T, n_limbs), 256, 0, s>>>(T, out, c, tmp, qlinv, qlinv_sh);
+}
+
+// ------------------------------------------------------------------------------------
+// Batched tails for polynomials that live in different allocations (scheduler path): one
+// descriptor per output limb, blockIdx.y = descriptor.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) moddown_tail_batch_kernel(
+    DeviceTables T, const __grid_constant__ Ptr3Batch P, const u64* __restrict__ pinv,
+    const u64* __restrict__ pinv_sh) {
+  const u32  y = blockIdx.y, l = P.g[y];
+  const u64  q = T.mod[l].q, w = pinv[l], wsh = pinv_sh[l];
+  u64*       out = P.r[y];
+  const u64 *old = P.a[y], *conv = P.b[y];
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x)
+    out[i] = mul_shoup(sub_mod(old[i], conv[i], q), w, wsh, q);
+}
+void launch_moddown_tail_batch(const DeviceTables& T, const Ptr3Batch& P, const u64* pinv,
+                               const u64* pinv_sh, cudaStream_t s) {
+  if (P.n == 0) return;
+  prof::Scope prof_scope_("moddown_tail", s);
+  moddown_tail_batch_kernel<<<ew_grid(T, P.n), 256, 0, s>>>(T, P, pinv, pinv_sh);
+}
+
+__global__ void __launch_bounds__(256) rescale_pre_batch_kernel(
+    DeviceTables T, const __grid_constant__ Ptr3Batch P, const u64* __restrict__ negqlinv,
+    const u64* __restrict__ negqlinv_sh, u32 L) {
+  const u32  y = blockIdx.y, i = P.g[y], l = P.aux[y];
+  const u64  qi = T.mod[i].q, ql = T.mod[l].q;
+  const u64  w = negqlinv[(size_t)l * L + i], wsh = negqlinv_sh[(size_t)l * L + i];
+  u64*       tmp  = P.r[y];
+  const u64* last = P.a[y];
+  for (u32 n = blockIdx.x * blockDim.x + threadIdx.x; n < T.N; n += gridDim.x * blockDim.x)
+    tmp[n] = mul_shoup(switch_modulus(last[n], ql, qi), w, wsh, qi);
+}
+void launch_rescale_pre_batch(const DeviceTables& T, const Ptr3Batch& P, const u64* negqlinv,
+                              const u64* negqlinv_sh, u32 L, cudaStream_t s) {
+  if (P.n == 0) return;
+  prof::Scope prof_scope_("rescale_pre", s);
+  rescale_pre_batch_kernel<<<ew_grid(T, P.n), 256, 0, s>>>(T, P, negqlinv, negqlinv_sh, L);
+}
+
+__global__ void __launch_bounds__(256) rescale_post_batch_kernel(
+    DeviceTables T, const __grid_constant__ Ptr3Batch P, const u64* __restrict__ qlinv,
+    const u64* __restrict__ qlinv_sh, u32 L) {
+  const u32  y = blockIdx.y, i = P.g[y], l = P.aux[y];
+  const u64  qi = T.mod[i].q;
+  const u64  w = qlinv[(size_t)l * L + i], wsh = qlinv_sh[(size_t)l * L + i];
+  u64*       out = P.r[y];
+  const u64 *c = P.a[y], *tmp = P.b[y];
+  for (u32 n = blockIdx.x * blockDim.x + threadIdx.x; n < T.N; n += gridDim.x * blockDim.x)
+    out[n] = add_mod(mul_shoup(c[n], w, wsh, qi), tmp[n], qi);
+}
+void launch_rescale_post_batch(const DeviceTables& T, const Ptr3Batch& P, const u64* qlinv,
+                               const u64* qlinv_sh, u32 L, cudaStream_t s) {
+  if (P.n == 0) return;
+  prof::Scope prof_scope_("rescale_post", s);
+  rescale_post_batch_kernel<<<ew_grid(T, P.n), 256, 0, s>>>(T, P, qlinv, qlinv_sh, L);
 }
 
 }  // namespace ace

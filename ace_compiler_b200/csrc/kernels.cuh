@@ -38,6 +38,20 @@ struct DeviceTables {
 void launch_ntt(const DeviceTables& T, const LimbBatch& b, cudaStream_t s);
 void launch_intt(const DeviceTables& T, const LimbBatch& b, cudaStream_t s);
 
+// The same transforms over limbs that live in different allocations (the scheduler batches
+// the polynomials of many independent reference calls into one launch, sched.h): limb i is
+// read from src[i], transformed modulo modulus g[i] and written to dst[i] (src[i] == dst[i]
+// for an in-place transform).
+constexpr int kMaxPtrBatch = 192;
+struct LimbPtrBatch {
+  u32        n;
+  u64*       dst[kMaxPtrBatch];
+  const u64* src[kMaxPtrBatch];
+  uint16_t   g[kMaxPtrBatch];
+};
+void launch_ntt(const DeviceTables& T, const LimbPtrBatch& b, cudaStream_t s);
+void launch_intt(const DeviceTables& T, const LimbPtrBatch& b, cudaStream_t s);
+
 enum EwOp { EW_ADD = 0, EW_SUB = 1, EW_MUL = 2 };
 // r[i] = a[i] op b[i] over n_limbs consecutive limbs, limb i uses modulus g0 + i
 void launch_ew(const DeviceTables& T, EwOp op, u64* r, const u64* a, const u64* b, u32 g0,
@@ -65,6 +79,7 @@ struct ConvDesc {
   uint16_t   g_out[64];
   uint16_t   out_slot[64];
 };
+constexpr int kMaxConvPack = 8;  // descriptors per launch (n_desc <= kMaxConvPack)
 void launch_base_conv(const DeviceTables& T, const ConvDesc* descs, u32 n_desc,
                       cudaStream_t s);
 
@@ -89,6 +104,27 @@ void launch_rescale_pre(const DeviceTables& T, u64* tmp, const u64* last, u32 l,
                         const u64* negqlinv, const u64* negqlinv_sh, cudaStream_t s);
 void launch_rescale_post(const DeviceTables& T, u64* out, const u64* c, const u64* tmp,
                          const u64* qlinv, const u64* qlinv_sh, u32 n_limbs, cudaStream_t s);
+
+// Batched forms of the three tails above for polynomials in different allocations: one
+// descriptor per output limb y.
+//   moddown tail : r = (a - b) * pinv[g]                      (a = old limb, b = converted limb)
+//   rescale pre  : r = switch_modulus(a, q_aux, q_g) * negqlinv[aux][g]   (a = INTT of limb aux)
+//   rescale post : r = a * qlinv[aux][g] + b
+constexpr int kMaxP3 = 128;
+struct Ptr3Batch {
+  u32        n;
+  u64*       r[kMaxP3];
+  const u64* a[kMaxP3];
+  const u64* b[kMaxP3];
+  uint16_t   g[kMaxP3];
+  uint16_t   aux[kMaxP3];
+};
+void launch_moddown_tail_batch(const DeviceTables& T, const Ptr3Batch& P, const u64* pinv,
+                               const u64* pinv_sh, cudaStream_t s);
+void launch_rescale_pre_batch(const DeviceTables& T, const Ptr3Batch& P, const u64* negqlinv,
+                              const u64* negqlinv_sh, u32 L, cudaStream_t s);
+void launch_rescale_post_batch(const DeviceTables& T, const Ptr3Batch& P, const u64* qlinv,
+                               const u64* qlinv_sh, u32 L, cudaStream_t s);
 
 }  // namespace ace
 

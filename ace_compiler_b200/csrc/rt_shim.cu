@@ -21,7 +21,7 @@
 
 #include "../../include/rt_ant/rt_ant.h"
 #include "evaluator.h"
-#include "op_queue.h"
+#include "sched.h"
 #include "prof.h"
 
 using namespace ace;
@@ -47,7 +47,7 @@ namespace {
 
 Context*  g_ctx    = nullptr;
 Evaluator* g_ev    = nullptr;
-OpQueue*   g_queue = nullptr;  // deferred Hw_modadd / Hw_modmul / Hw_rotate calls
+Scheduler* g_queue = nullptr;  // deferred execution of the polynomial-level API (sched.h)
 MODULUS*  g_mod    = nullptr;  // [G] Q then P, contiguous like the reference's arrays
 int       g_device = 0;
 uint64_t  g_enc_seed = 1;
@@ -71,7 +71,6 @@ bool quiet() {
   if (q < 0) q = (getenv("ACE_B200_QUIET") && getenv("ACE_B200_QUIET")[0] == '1') ? 1 : 0;
   return q == 1;
 }
-bool g_no_batch = false;
 bool g_stats_on = false, g_stats_sync = false;  // =2: sync around every scope (true GPU time)
 void stats_sync();
 void stats_flush();
@@ -80,9 +79,9 @@ inline double wall() {
   clock_gettime(CLOCK_MONOTONIC, &ts);
   return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
-const char* const kApiScope[] = {nullptr, nullptr, nullptr, "api.Decomp_modup", "api.Mod_down",
-                                 "api.Rescale", "api.Encode", "api.Bootstrap", nullptr, nullptr,
-                                 "api.Copy/Set_coeffs"};
+// only Bootstrap executes inside its call; everything else is deferred (sched.h)
+const char* const kApiScope[] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                 "api.Bootstrap", nullptr, nullptr, nullptr};
 cudaStream_t prof_stream();
 struct StatScope {
   int id; double t0;
@@ -155,13 +154,13 @@ void alloc_poly_data(POLYNOMIAL* p, uint32_t degree, size_t nq, size_t np) {
   p->_num_alloc_primes = nq + np;
   p->_is_ntt           = false;
   // fresh memory: nothing recorded can refer to it, no flush needed
-  guard([&] { p->_data = reinterpret_cast<int64_t*>(ctx_nf()->alloc_limbs(nq + np, true)); });
+  guard([&] { ctx_nf(); p->_data = reinterpret_cast<int64_t*>(g_queue->alloc(nq + np, true)); });
 }
 
 void free_poly_data(POLYNOMIAL* p) {
   StatScope ss(ST_FREE);
   if (p->_data) {
-    guard([&] { ctx()->free_limbs(U(p->_data)); });
+    guard([&] { ctx_nf(); g_queue->free(U(p->_data)); });
     p->_data = nullptr;
   }
   p->_num_alloc_primes = 0;
@@ -177,13 +176,7 @@ void init_poly(POLYNOMIAL* res, const POLYNOMIAL* poly) {
     free_poly_data(res);
     alloc_poly_data(res, poly->_ring_degree, poly->_num_primes, poly->_num_primes_p);
   } else {
-    guard([&] {
-      Context* c = ctx();
-      prof::Scope ps("memset(init_poly)", c->stream);
-      ACE_CUDA(cudaMemsetAsync(res->_data, 0,
-                               res->_num_alloc_primes * (size_t)res->_ring_degree * 8,
-                               c->stream));
-    });
+    guard([&] { ctx_nf(); g_queue->zero(U(res->_data), res->_num_alloc_primes); });
     res->_ring_degree  = poly->_ring_degree;
     res->_num_primes   = poly->_num_primes;
     res->_num_primes_p = poly->_num_primes_p;
@@ -198,12 +191,9 @@ int64_t* p_coeffs(const POLYNOMIAL* p) {  // Get_p_coeffs (polynomial.h:214-217)
 void copy_polynomial(POLYNOMIAL* dst, const POLYNOMIAL* src) {  // polynomial.h:425-438
   StatScope ss(ST_COPY);
   guard([&] {
-    Context* c = ctx();
-    ACE_CUDA(cudaMemcpyAsync(dst->_data, src->_data, dst->_num_primes * (size_t)c->N * 8,
-                             cudaMemcpyDeviceToDevice, c->stream));
-    if (src->_num_primes_p)
-      ACE_CUDA(cudaMemcpyAsync(p_coeffs(dst), p_coeffs(src), dst->_num_primes_p * (size_t)c->N * 8,
-                               cudaMemcpyDeviceToDevice, c->stream));
+    ctx_nf();
+    g_queue->copy(U(dst->_data), U(src->_data), dst->_num_primes);
+    if (src->_num_primes_p) g_queue->copy(U(p_coeffs(dst)), U(p_coeffs(src)), dst->_num_primes_p);
   });
   dst->_is_ntt = src->_is_ntt;
 }
@@ -366,11 +356,9 @@ API void Prepare_context(void) {
            p->_provider, p->_poly_degree, p->_sec_level, p->_mul_depth, p->_first_mod_size,
            p->_scaling_mod_size, parts, g_ctx->K, p->_num_rot_idx, p->_hamming_weight);
     g_ev = new Evaluator(g_ctx);
-    g_queue = new OpQueue(&g_ctx->T, g_ctx->stream, &g_ctx->launches,
-                          &g_ctx->trace[Context::TR_LIMB_MUL][0],
-                          &g_ctx->trace[Context::TR_LIMB_ADD][0],
-                          &g_ctx->trace[Context::TR_LIMB_ROT][0]);
-    g_no_batch = getenv("ACE_B200_NO_BATCH") && getenv("ACE_B200_NO_BATCH")[0] == '1';
+    g_queue = new Scheduler(g_ctx);
+    // ACE_B200_EAGER=1: issue every call at once (no batching across calls)
+    g_queue->eager = getenv("ACE_B200_EAGER") && getenv("ACE_B200_EAGER")[0] == '1';
     const char* no_keys = getenv("ACE_B200_NO_KEYGEN");  // parity runs import the oracle's keys
     const bool  own_keys = !(no_keys && no_keys[0] == '1');
     const char* seed_env = getenv("ACE_B200_SEED");
@@ -391,8 +379,12 @@ API void Prepare_context(void) {
 API void Finalize_context(void) {
   if (!g_ctx) return;
   if (g_stats_on) {
-    printf("[ace_b200 stats] kernels launched: %zu; limb-op batches %zu for %zu ops\n",
-           g_ctx->launches, g_queue->batches, g_queue->ops);
+    printf("[ace_b200 stats] kernels launched: %zu; scheduler: %zu ops in %zu flushes / %zu waves, "
+           "%zu chain launches, %zu mul+add fused, %zu dead stores dropped; peak limb memory "
+           "%.1f GB\n",
+           g_ctx->launches, g_queue->n_ops, g_queue->n_flush, g_queue->n_waves,
+           g_queue->n_chain_launches, g_queue->n_fused, g_queue->n_dead,
+           g_ctx->peak_bytes / 1073741824.0);
     for (int i = 0; i < ST_COUNT; i++)
       printf("[ace_b200 stats] %-22s calls %9llu  host time %8.3f s\n", g_stats[i].name,
              (unsigned long long)g_stats[i].calls, g_stats[i].secs);
@@ -445,6 +437,7 @@ API void Prepare_input(TENSOR* input, const char* name) {
     c->encode(pt, input->_vals, len, (u32)c->L, 0, 1, 0);
     alloc_poly_data(&ct->_c0_poly, c->N, c->L, 0);
     alloc_poly_data(&ct->_c1_poly, c->N, c->L, 0);
+    ctx();  // the recorded zero fills go first
     c->encrypt(U(ct->_c0_poly._data), U(ct->_c1_poly._data), pt, (u32)c->L, g_enc_seed++);
     c->free_limbs(pt);
   });
@@ -461,6 +454,7 @@ API void Ace_set_input(const char* name, size_t idx, const int64_t* c0, const in
   CIPHERTEXT* ct = (CIPHERTEXT*)calloc(1, sizeof(CIPHERTEXT));
   alloc_poly_data(&ct->_c0_poly, c->N, level, 0);
   alloc_poly_data(&ct->_c1_poly, c->N, level, 0);
+  ctx();  // the recorded zero fills go first
   guard([&] {
     c->upload(U(ct->_c0_poly._data), U(c0), level);
     c->upload(U(ct->_c1_poly._data), U(c1), level);
@@ -566,10 +560,7 @@ API void Free_poly(POLY poly) {
 API void Copy_poly(POLY res, POLY poly) { copy_polynomial(res, poly); }
 API void Set_coeffs(POLY dst, uint32_t level, uint32_t degree, int64_t* src) {  // poly_eval.h:74-79
   StatScope ss(ST_COPY);
-  guard([&] {
-    ACE_CUDA(cudaMemcpyAsync(dst->_data + (size_t)level * degree, src, sizeof(int64_t) * degree,
-                             cudaMemcpyDeviceToDevice, ctx()->stream));
-  });
+  guard([&] { ctx_nf(); g_queue->copy(U(dst->_data + (size_t)level * degree), U(src), 1); });
 }
 API size_t Num_decomp(POLY poly) { return ctx_nf()->num_decomp(poly->_num_primes); }
 
@@ -588,22 +579,19 @@ API void Ace_upload_poly(POLY poly, const int64_t* host_src) {
 API int64_t* Hw_modadd(int64_t* res, int64_t* a, int64_t* b, MODULUS* m, uint32_t degree) {
   StatScope ss(ST_ADD);
   ctx_nf();
-  g_queue->push_ew(EW_ADD, U(res), U(a), U(b), mod_index(m));
-  if (g_no_batch) g_queue->flush();
+  guard([&] { g_queue->ew(OP_ADD, U(res), U(a), U(b), mod_index(m)); });
   return res + degree;
 }
 API int64_t* Hw_modmul(int64_t* res, int64_t* a, int64_t* b, MODULUS* m, uint32_t degree) {
   StatScope ss(ST_MUL);
   ctx_nf();
-  g_queue->push_ew(EW_MUL, U(res), U(a), U(b), mod_index(m));
-  if (g_no_batch) g_queue->flush();
+  guard([&] { g_queue->ew(OP_MUL, U(res), U(a), U(b), mod_index(m)); });
   return res + degree;
 }
 API int64_t* Hw_rotate(int64_t* res, int64_t* a, int64_t* order, MODULUS* m, uint32_t degree) {
   StatScope ss(ST_ROT);
   ctx_nf();
-  g_queue->push_gather(U(res), U(a), order, mod_index(m));
-  if (g_no_batch) g_queue->flush();
+  guard([&] { g_queue->gather(U(res), U(a), order, mod_index(m)); });
   return res + degree;
 }
 
@@ -617,10 +605,7 @@ API POLY Decomp(POLY res, POLY poly, uint32_t part) {  // Decompose_poly, polyno
     res->_num_primes = len;
     res->_num_primes_p = 0;
   }
-  guard([&] {
-    ACE_CUDA(cudaMemcpyAsync(res->_data, poly->_data + (size_t)st * c->N, (size_t)len * c->N * 8,
-                             cudaMemcpyDeviceToDevice, c->stream));
-  });
+  guard([&] { g_queue->copy(U(res->_data), U(poly->_data + (size_t)st * c->N), len); });
   res->_is_ntt = poly->_is_ntt;
   return res;
 }
@@ -631,19 +616,19 @@ API POLY Mod_up(POLY new_poly, POLY old_poly, uint32_t part) {  // poly_eval.c:1
 }
 API POLY Decomp_modup(POLY res, POLY poly, uint32_t part) {  // poly_eval.c:28-34
   StatScope ss(ST_MODUP);
-  guard([&] { ctx()->decomp_modup(U(res->_data), U(poly->_data), (u32)poly->_num_primes, part); });
+  guard([&] { ctx_nf(); g_queue->modup(U(res->_data), U(poly->_data), (u32)poly->_num_primes, part); });
   res->_is_ntt = true;
   return res;
 }
 API POLY Mod_down(POLY res, POLY poly) {  // poly_eval.c:36-41
   StatScope ss(ST_MODDOWN);
-  guard([&] { ctx()->mod_down(U(res->_data), U(poly->_data), (u32)res->_num_primes); });
+  guard([&] { ctx_nf(); g_queue->moddown(U(res->_data), U(poly->_data), (u32)res->_num_primes); });
   res->_is_ntt = poly->_is_ntt;
   return res;
 }
 API POLY Rescale(POLY res, POLY poly) {  // poly_eval.c:43-49
   StatScope ss(ST_RESCALE);
-  guard([&] { ctx()->rescale(U(res->_data), U(poly->_data), (u32)poly->_num_primes); });
+  guard([&] { ctx_nf(); g_queue->rescale(U(res->_data), U(poly->_data), (u32)poly->_num_primes); });
   res->_is_ntt     = true;
   res->_num_primes = res->_num_primes - 1;  // Mod_down_q_primes
   return res;
@@ -824,6 +809,7 @@ API CIPHER Relin(CIPHER res, CIPHER3 ciph) {  // ckks_evaluator.c:266-282
   res->_slots          = ciph->_slots;
   init_poly(&res->_c0_poly, &ciph->_c2_poly);
   init_poly(&res->_c1_poly, &ciph->_c2_poly);
+  ctx();  // issue what was recorded for these blocks (zero fills) before launching directly
   guard([&] {
     u64* t = c->alloc_limbs(2 * (size_t)level, false);
     c->key_switch(t, t + (size_t)level * c->N, U(ciph->_c2_poly._data), level, c->relin_key, nullptr);
@@ -846,6 +832,7 @@ API CIPHER Mul_ciph(CIPHER res, CIPHER a, CIPHER b) {  // ckks_evaluator.c:167-1
   memset(&tmp, 0, sizeof(tmp));
   alloc_poly_data(&tmp._c0_poly, c->N, level, 0);
   alloc_poly_data(&tmp._c1_poly, c->N, level, 0);
+  ctx();  // issue what was recorded for these blocks (zero fills) before launching directly
   guard([&] {
     c->ct_mul_relin(U(tmp._c0_poly._data), U(tmp._c1_poly._data), U(a->_c0_poly._data),
                     U(a->_c1_poly._data), U(b->_c0_poly._data), U(b->_c1_poly._data), level);
@@ -869,6 +856,7 @@ API CIPHER Rescale_ciph(CIPHER res, CIPHER ciph) {  // ckks_evaluator.c:324-343
   memset(&tmp, 0, sizeof(tmp));
   alloc_poly_data(&tmp._c0_poly, c->N, level, 0);
   alloc_poly_data(&tmp._c1_poly, c->N, level, 0);
+  ctx();  // issue what was recorded for these blocks (zero fills) before launching directly
   guard([&] {
     c->rescale(U(tmp._c0_poly._data), U(ciph->_c0_poly._data), level);
     c->rescale(U(tmp._c1_poly._data), U(ciph->_c1_poly._data), level);
@@ -890,6 +878,7 @@ API CIPHER Rotate_ciph(CIPHER res, CIPHER ciph, int32_t rotation) {  // cipher_e
   memset(&tmp, 0, sizeof(tmp));
   alloc_poly_data(&tmp._c0_poly, c->N, level, 0);
   alloc_poly_data(&tmp._c1_poly, c->N, level, 0);
+  ctx();  // issue what was recorded for these blocks (zero fills) before launching directly
   guard([&] {
     c->ct_rotate(U(tmp._c0_poly._data), U(tmp._c1_poly._data), U(ciph->_c0_poly._data),
                  U(ciph->_c1_poly._data), level, rotation);
@@ -913,6 +902,7 @@ API CIPHER Encrypt(CIPHER res, PLAIN plain) {  // cipher_eval.c:406-409
   res->_slots          = plain->_slots;
   init_poly(&res->_c0_poly, &plain->_poly);
   init_poly(&res->_c1_poly, &plain->_poly);
+  ctx();  // issue what was recorded for these blocks (zero fills) before launching directly
   guard([&] { c->encrypt(U(res->_c0_poly._data), U(res->_c1_poly._data), U(plain->_poly._data), level, g_enc_seed++); });
   res->_c0_poly._is_ntt = res->_c1_poly._is_ntt = true;
   return res;
@@ -950,30 +940,36 @@ API CIPHER Bootstrap(CIPHER res, CIPHER ciph, uint32_t level_after_bts) {
 
 // =========================================================================== plaintexts
 static void init_plain(PLAIN plain, uint32_t slots, size_t level, double sf, uint32_t deg) {
-  Context* c = ctx();
+  Context* c = ctx_nf();
   plain->_scaling_factor = sf;
   plain->_sf_degree      = deg;
   plain->_slots          = slots;
-  if (plain->_poly._data == nullptr || plain->_poly._num_primes != level ||
-      plain->_poly._num_primes_p != 0) {
-    free_poly_data(&plain->_poly);
-    alloc_poly_data(&plain->_poly, c->N, level, 0);
-  }
+  // always a fresh block: the encode that fills it is deferred (sched.h) and must not wait for
+  // the ops still reading the previous contents
+  free_poly_data(&plain->_poly);
+  plain->_poly._ring_degree = c->N; plain->_poly._num_primes = level; plain->_poly._num_primes_p = 0;
+  plain->_poly._num_alloc_primes = level;
+  guard([&] { plain->_poly._data = reinterpret_cast<int64_t*>(g_queue->alloc(level, false)); });
   plain->_poly._is_ntt = true;
 }
 
 static void encode_plain(PLAIN plain, const double* vals, size_t len, uint32_t sc_degree,
                          uint32_t level) {
   StatScope ss(ST_ENCODE);
-  Context* c = ctx();
+  Context* c = ctx_nf();
   if (level == 0) level = (uint32_t)c->L;
   double sf = Get_default_sc();
-  if (len == 1) {  // plain_eval.c:28-34: constant fast path
+  if (len == 1) {  // plain_eval.c:28-34: constant fast path; one recorded fill per limb
     init_plain(plain, c->N / 2, level, pow(sf, sc_degree), sc_degree);
-    guard([&] { c->encode_value(U(plain->_poly._data), vals[0], level, sc_degree); });
+    guard([&] {
+      std::vector<u64> res = c->value_residues(vals[0], level, sc_degree);
+      for (uint32_t l = 0; l < level; l++)
+        g_queue->fill(U(plain->_poly._data) + (size_t)l * c->N, res[l]);
+    });
     return;
   }
   init_plain(plain, c->N / 2, level, pow(sf, sc_degree), sc_degree);
+  ctx();  // the message is in host memory: staged and encoded at once
   guard([&] { c->encode(U(plain->_poly._data), vals, len, level, 0, sc_degree, 0); });
 }
 
@@ -1043,11 +1039,11 @@ API void Pt_from_msg(void* pt, uint32_t index, size_t len, uint32_t scale, uint3
   }
   StatScope ss(ST_ENCODE);
   PLAIN plain = (PLAIN)pt;
-  Context* c = ctx();
+  Context* c = ctx_nf();
   if (level == 0) level = (uint32_t)c->L;
   init_plain(plain, c->N / 2, level, pow(Get_default_sc(), scale), scale);
   guard([&] {
-    c->encode_dev(U(plain->_poly._data), g_wfile_dev + e.ent_ofst, g_etype == DE_MSG_F32 ? 0 : 1,
-                  len, level, 0, scale, 0);
+    g_queue->encode(EncodeJob{U(plain->_poly._data), g_wfile_dev + e.ent_ofst,
+                              g_etype == DE_MSG_F32 ? 0 : 1, (u32)len, level, 0, scale, 0});
   });
 }

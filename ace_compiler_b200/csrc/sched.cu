@@ -1,0 +1,565 @@
+// sched.cu -- see sched.h
+#include "sched.h"
+
+#include <algorithm>
+#include <cstring>
+
+#include "prof.h"
+
+namespace ace {
+
+// ---------------------------------------------------------------------------- kernels
+// one thread per coefficient, blockIdx.y = chain; the items of a chain run in program order.
+// Plain (non-restrict, non-ldg) accesses: a later item may read what an earlier one wrote.
+__global__ void __launch_bounds__(256) ew_chain_kernel(DeviceTables T,
+                                                       const __grid_constant__ ChainPack P) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T.N) return;
+  const u32 k0 = P.chain_start[blockIdx.y], k1 = P.chain_start[blockIdx.y + 1];
+  for (u32 k = k0; k < k1; k++) {
+    const ChainItem& it = P.it[k];
+    const u32 op = it.op;
+    if (op == OP_ZERO) { it.r[i] = 0; continue; }
+    if (op == OP_COPY) { it.r[i] = it.a[i]; continue; }
+    if (op == OP_FILL) { it.r[i] = (u64)(uintptr_t)it.a; continue; }
+    const Modulus m = T.mod[it.g];
+    const u64 x = it.a[i], y = it.b[i];
+    u64 z;
+    if (op == OP_ADD) z = add_mod(x, y, m.q);
+    else if (op == OP_SUB) z = sub_mod(x, y, m.q);
+    else {
+      z = mul_mod(x, y, m);
+      if (op == OP_MAC) {
+        if (it.t) it.t[i] = z;
+        if (it.c) z = add_mod(it.c[i], z, m.q);
+      }
+    }
+    it.r[i] = z;
+  }
+}
+
+// independent gathers (Hw_rotate): blockIdx.y = item, b = the int64 order table
+__global__ void __launch_bounds__(256) gather_batch_kernel(DeviceTables T,
+                                                           const __grid_constant__ ChainPack P) {
+  const ChainItem& it    = P.it[blockIdx.y];
+  const int64_t*   order = reinterpret_cast<const int64_t*>(it.b);
+  const u64        q     = T.mod[it.g].q;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
+    const int64_t k = order[i];
+    it.r[i] = k >= 0 ? it.a[k] : q - it.a[-k];
+  }
+}
+
+// ---------------------------------------------------------------------------- limb table
+static inline u32 hash_addr(const u64* p) {
+  return (u32)((((uint64_t)(uintptr_t)p) >> 9) * 0x9E3779B97F4A7C15ull >> 32);
+}
+
+Scheduler::Scheduler(Context* c) : c_(c) {
+  table_.resize(1u << 16);
+  memset(table_.data(), 0, table_.size() * sizeof(Limb));
+  mask_ = (u32)table_.size() - 1;
+  ops_.reserve(1 << 16);
+}
+Scheduler::~Scheduler() {}
+
+void Scheduler::grow() {
+  std::vector<Limb> old;
+  old.swap(table_);
+  table_.resize(old.size() * 2);
+  memset(table_.data(), 0, table_.size() * sizeof(Limb));
+  mask_ = (u32)table_.size() - 1;
+  for (const Limb& l : old) {
+    if (l.gen != gen_) continue;
+    u32 h = hash_addr((const u64*)(uintptr_t)l.addr) & mask_;
+    while (table_[h].gen == gen_) h = (h + 1) & mask_;
+    table_[h] = l;
+  }
+}
+
+// the entry of a limb, created on first sight.  References stay valid until the next limb()
+// call that inserts (callers look up all operands of an op first: grow() only runs at entry)
+Scheduler::Limb& Scheduler::limb(const u64* addr) {
+  u32 h = hash_addr(addr) & mask_;
+  for (;;) {
+    Limb& l = table_[h];
+    if (l.gen != gen_) {
+      memset(&l, 0, sizeof(l));
+      l.addr = (u64)(uintptr_t)addr;
+      l.gen  = gen_;
+      l.w_op = -1;
+      live_++;
+      return l;
+    }
+    if (l.addr == (u64)(uintptr_t)addr) return l;
+    h = (h + 1) & mask_;
+  }
+}
+
+// earliest wave of a reader / writer of limb l.  Chain ops may share a wave with the chain ops
+// they depend on (program order inside the chain does the rest); anything else is one later.
+u32 Scheduler::dep_read(Limb& l, bool heavy) const {
+  if (!l.has_w) return 0;
+  return (heavy || l.w_heavy) ? l.w_wave + 1 : l.w_wave;
+}
+u32 Scheduler::dep_write(Limb& l, bool heavy) const {
+  u32 w = dep_read(l, heavy);
+  if (l.has_r_chain) w = std::max(w, heavy ? l.r_wave_chain + 1 : l.r_wave_chain);
+  if (l.has_r_heavy) w = std::max(w, l.r_wave_heavy + 1);
+  return w;
+}
+void Scheduler::note_read(Limb& l, u32 wave, bool heavy) {
+  l.read_since = 1;
+  if (heavy) {
+    l.r_wave_heavy = l.has_r_heavy ? std::max(l.r_wave_heavy, wave) : wave;
+    l.has_r_heavy  = 1;
+  } else {
+    l.r_wave_chain = l.has_r_chain ? std::max(l.r_wave_chain, wave) : wave;
+    l.has_r_chain  = 1;
+  }
+}
+void Scheduler::note_write(Limb& l, u32 wave, bool heavy, int32_t op, bool as_t) {
+  l.w_op = heavy ? -1 : op;
+  l.has_w = 1;
+  l.w_wave = wave;
+  l.w_heavy = heavy ? 1 : 0;
+  l.w_is_t = as_t ? 1 : 0;
+  l.read_since = 0;
+  l.has_r_chain = l.has_r_heavy = 0;
+  l.is_zero = 0;
+}
+
+// the limb is about to be overwritten (or its block freed): if nothing read what the last
+// recorded chain op stored there, that store is dead
+void Scheduler::kill_if_unread(Limb& l) {
+  if (l.w_op < 0 || l.read_since) return;
+  Op& o = ops_[l.w_op];
+  if (l.w_is_t) {
+    if (o.kind == OP_MAC) o.t_live = 0;
+  } else if (o.kind == OP_MAC && o.t_live) {
+    // only the product is still wanted: r = a * b stored to t
+    o.kind = OP_MUL;
+    o.r = o.t;
+    o.t_live = 0;
+    Limb& lt = limb(o.t);  // exists already
+    lt.w_is_t = 0;
+  } else if (o.kind != OP_NOP) {
+    o.kind = OP_NOP;
+  }
+  n_dead++;
+  l.w_op = -1;
+}
+
+void Scheduler::maybe_flush() {
+  if (eager || ops_.size() > (1u << 18) || pending_free_bytes_ > ((size_t)40 << 30)) flush();
+}
+
+// ---------------------------------------------------------------------------- recording
+u64* Scheduler::alloc(size_t n_limbs, bool zeroed) {
+  u64* p = c_->alloc_limbs(n_limbs, false);
+  if (zeroed) zero(p, n_limbs);
+  return p;
+}
+
+void Scheduler::free(u64* block) {
+  if (!block) return;
+  const size_t n = c_->block_limbs(block);
+  for (size_t i = 0; i < n; i++) {
+    const u64* a = block + i * c_->N;
+    u32 h = hash_addr(a) & mask_;
+    while (table_[h].gen == gen_) {
+      if (table_[h].addr == (u64)(uintptr_t)a) { kill_if_unread(table_[h]); break; }
+      h = (h + 1) & mask_;
+    }
+  }
+  frees_.push_back(block);
+  pending_free_bytes_ += n * c_->N * sizeof(u64);
+  maybe_flush();
+}
+
+void Scheduler::zero(u64* r, size_t n_limbs) {
+  if (live_ + n_limbs + 8 > table_.size() / 2) grow();
+  for (size_t i = 0; i < n_limbs; i++) {
+    u64* p = r + i * c_->N;
+    Limb& l = limb(p);
+    kill_if_unread(l);
+    const u32 wave = dep_write(l, false);
+    Op o{};
+    o.kind = OP_ZERO; o.r = p; o.wave = wave;
+    ops_.push_back(o);
+    note_write(l, wave, false, (int32_t)ops_.size() - 1, false);
+    l.is_zero = 1;
+  }
+  n_ops += n_limbs;
+  maybe_flush();
+}
+
+void Scheduler::fill(u64* r, u64 value) {
+  if (value == 0) { zero(r, 1); return; }
+  if (live_ + 8 > table_.size() / 2) grow();
+  Limb& l = limb(r);
+  kill_if_unread(l);
+  const u32 wave = dep_write(l, false);
+  Op o{};
+  o.kind = OP_FILL; o.r = r; o.wave = wave;
+  o.a = reinterpret_cast<const u64*>((uintptr_t)value);
+  ops_.push_back(o);
+  note_write(l, wave, false, (int32_t)ops_.size() - 1, false);
+  n_ops++;
+  maybe_flush();
+}
+
+void Scheduler::copy(u64* r, const u64* a, size_t n_limbs) {
+  for (size_t i = 0; i < n_limbs; i++) {
+    u64* rp = r + i * c_->N;
+    const u64* ap = a + i * c_->N;
+    if (rp == ap) continue;
+    if (live_ + 8 > table_.size() / 2) grow();
+    Limb& la = limb(ap);
+    if (la.is_zero) { zero(rp, 1); continue; }
+    const u32 wa = dep_read(la, false);
+    note_read(la, wa, false);  // provisional; raised below if the write forces a later wave
+    Limb& lr = limb(rp);
+    kill_if_unread(lr);
+    const u32 wave = std::max(wa, dep_write(lr, false));
+    Op o{};
+    o.kind = OP_COPY; o.r = rp; o.a = ap; o.wave = wave;
+    ops_.push_back(o);
+    note_write(lr, wave, false, (int32_t)ops_.size() - 1, false);
+    if (wave != wa) note_read(limb(ap), wave, false);
+    n_ops++;
+  }
+  maybe_flush();
+}
+
+void Scheduler::ew(SchedOp op, u64* r, const u64* a, const u64* b, u32 g) {
+  if (live_ + 8 > table_.size() / 2) grow();
+  c_->tr(op == OP_MUL ? Context::TR_LIMB_MUL : Context::TR_LIMB_ADD, 0);
+  n_ops++;
+  const bool za = limb(a).is_zero, zb = limb(b).is_zero;
+  // ---- operands known to be zero: the op degenerates (0 + y = y, x * 0 = 0, x - 0 = x)
+  if (za || zb) {
+    if (op == OP_MUL || (za && zb)) { zero(r, 1); return; }
+    if (op == OP_ADD) { copy(r, za ? b : a, 1); return; }
+    if (op == OP_SUB && zb) { copy(r, a, 1); return; }
+  }
+  // ---- Hw_modmul(tmp, x, y) directly followed by Hw_modadd(r, acc, tmp): one multiply-add
+  if (op == OP_ADD && !ops_.empty()) {
+    Op& m = ops_.back();
+    if (m.kind == OP_MUL && m.r != r && ((b == m.r) != (a == m.r))) {
+      const u64* acc = (b == m.r) ? a : b;
+      u64*       tmp = m.r;
+      Limb& lt = limb(tmp);
+      if (lt.w_op == (int32_t)ops_.size() - 1 && !lt.read_since) {
+        Limb& lacc = limb(acc);
+        const bool acc_zero = lacc.is_zero;
+        u32 wave = m.wave;
+        if (!acc_zero) {
+          wave = std::max(wave, dep_read(lacc, false));
+          note_read(lacc, wave, false);
+        }
+        Limb& lr = limb(r);
+        kill_if_unread(lr);
+        wave = std::max(wave, dep_write(lr, false));
+        m.kind = OP_MAC; m.c = acc_zero ? nullptr : acc; m.t = tmp; m.t_live = 1; m.r = r;
+        m.wave = wave;
+        const int32_t idx = (int32_t)ops_.size() - 1;
+        note_write(lr, wave, false, idx, false);
+        Limb& lt2 = limb(tmp);
+        lt2.w_wave = wave; lt2.w_is_t = 1; lt2.w_op = idx;
+        // reads happen in the final wave (the value the destination held before is what is read)
+        if (m.a != r && m.a != tmp) note_read(limb(m.a), wave, false);
+        if (m.b != r && m.b != tmp) note_read(limb(m.b), wave, false);
+        if (!acc_zero && acc != r) note_read(limb(acc), wave, false);
+        n_fused++;
+        maybe_flush();
+        return;
+      }
+    }
+  }
+  Limb& la = limb(a);
+  u32 wave = dep_read(la, false);
+  Limb& lb = limb(b);
+  wave = std::max(wave, dep_read(lb, false));
+  note_read(limb(a), wave, false);
+  note_read(limb(b), wave, false);
+  Limb& lr = limb(r);
+  kill_if_unread(lr);
+  const u32 w2 = std::max(wave, dep_write(lr, false));
+  Op o{};
+  o.kind = op; o.r = r; o.a = a; o.b = b; o.g = (uint16_t)g; o.wave = w2;
+  ops_.push_back(o);
+  note_write(limb(r), w2, false, (int32_t)ops_.size() - 1, false);
+  if (w2 != wave) {
+    note_read(limb(a), w2, false);
+    note_read(limb(b), w2, false);
+    if (a == r || b == r) limb(r).read_since = 0;
+  }
+  // an op that reads its own destination: the read is of the OLD value and precedes the write
+  if (a == r || b == r) { Limb& l = limb(r); l.read_since = 0; l.has_r_chain = 0; }
+  maybe_flush();
+}
+
+void Scheduler::gather(u64* r, const u64* a, const int64_t* order, u32 g) {
+  if (live_ + 8 > table_.size() / 2) grow();
+  c_->tr(Context::TR_LIMB_ROT, 0);
+  n_ops++;
+  if (r == a) throw std::runtime_error("Hw_rotate in place is not supported");
+  Limb& la = limb(a);
+  u32 wave = dep_read(la, true);
+  Limb& lr = limb(r);
+  kill_if_unread(lr);
+  wave = std::max(wave, dep_write(lr, true));
+  note_read(limb(a), wave, true);
+  Op o{};
+  o.kind = OP_GATHER; o.r = r; o.a = a; o.b = reinterpret_cast<const u64*>(order);
+  o.g = (uint16_t)g; o.wave = wave;
+  ops_.push_back(o);
+  note_write(limb(r), wave, true, -1, false);
+  maybe_flush();
+}
+
+// a heavy op reading limbs [rd, rd + n_rd) and writing limbs [wr, wr + n_wr)
+static inline size_t limb_off(u32 N, size_t i) { return i * (size_t)N; }
+
+void Scheduler::encode(const EncodeJob& j) {
+  const size_t nw = j.level + j.p_cnt;
+  if (live_ + nw + 8 > table_.size() / 2) grow();
+  u32 wave = 0;
+  for (size_t i = 0; i < nw; i++) {
+    Limb& l = limb(j.out + limb_off(c_->N, i));
+    kill_if_unread(l);
+    wave = std::max(wave, dep_write(l, true));
+  }
+  for (size_t i = 0; i < nw; i++) note_write(limb(j.out + limb_off(c_->N, i)), wave, true, -1, false);
+  Op o{};
+  o.kind = OP_ENCODE; o.wave = wave; o.p0 = (u32)enc_jobs_.size();
+  enc_jobs_.push_back(j);
+  ops_.push_back(o);
+  n_ops++;
+  maybe_flush();
+}
+
+void Scheduler::modup(u64* out, const u64* in, u32 num_q, u32 part) {
+  const u32 N = c_->N, W = num_q + (u32)c_->K;
+  const u32 st = c_->digit_start(part), len = c_->digit_len(num_q, part);
+  if (live_ + W + len + 8 > table_.size() / 2) grow();
+  u32 wave = 0;
+  for (u32 i = 0; i < len; i++) wave = std::max(wave, dep_read(limb(in + limb_off(N, st + i)), true));
+  for (u32 i = 0; i < W; i++) {
+    Limb& l = limb(out + limb_off(N, i));
+    kill_if_unread(l);
+    wave = std::max(wave, dep_write(l, true));
+  }
+  for (u32 i = 0; i < len; i++) note_read(limb(in + limb_off(N, st + i)), wave, true);
+  for (u32 i = 0; i < W; i++) note_write(limb(out + limb_off(N, i)), wave, true, -1, false);
+  Op o{};
+  o.kind = OP_MODUP; o.r = out; o.a = in + limb_off(N, st); o.p0 = num_q; o.p1 = part; o.wave = wave;
+  ops_.push_back(o);
+  n_ops++;
+  maybe_flush();
+}
+
+void Scheduler::moddown(u64* out, const u64* in, u32 num_q) {
+  const u32 N = c_->N, W = num_q + (u32)c_->K;
+  if (live_ + W + num_q + 8 > table_.size() / 2) grow();
+  u32 wave = 0;
+  for (u32 i = 0; i < W; i++) wave = std::max(wave, dep_read(limb(in + limb_off(N, i)), true));
+  for (u32 i = 0; i < num_q; i++) {
+    Limb& l = limb(out + limb_off(N, i));
+    kill_if_unread(l);
+    wave = std::max(wave, dep_write(l, true));
+  }
+  for (u32 i = 0; i < W; i++) note_read(limb(in + limb_off(N, i)), wave, true);
+  for (u32 i = 0; i < num_q; i++) note_write(limb(out + limb_off(N, i)), wave, true, -1, false);
+  Op o{};
+  o.kind = OP_MODDOWN; o.r = out; o.a = in; o.p0 = num_q; o.wave = wave;
+  ops_.push_back(o);
+  n_ops++;
+  maybe_flush();
+}
+
+void Scheduler::rescale(u64* out, const u64* in, u32 num_q) {
+  const u32 N = c_->N;
+  if (num_q < 2) throw std::runtime_error("Rescale: level not enough");
+  if (live_ + 2 * num_q + 8 > table_.size() / 2) grow();
+  u32 wave = 0;
+  for (u32 i = 0; i < num_q; i++) wave = std::max(wave, dep_read(limb(in + limb_off(N, i)), true));
+  for (u32 i = 0; i + 1 < num_q; i++) {
+    Limb& l = limb(out + limb_off(N, i));
+    if (out != in) kill_if_unread(l);
+    wave = std::max(wave, dep_write(l, true));
+  }
+  for (u32 i = 0; i < num_q; i++) note_read(limb(in + limb_off(N, i)), wave, true);
+  for (u32 i = 0; i + 1 < num_q; i++) note_write(limb(out + limb_off(N, i)), wave, true, -1, false);
+  Op o{};
+  o.kind = OP_RESCALE; o.r = out; o.a = in; o.p0 = num_q; o.wave = wave;
+  ops_.push_back(o);
+  n_ops++;
+  maybe_flush();
+}
+
+// ---------------------------------------------------------------------------- issuing
+// chain ops of one wave: ops that touch a limb written in this wave belong to one chain
+void Scheduler::run_chains(std::vector<u32>& idx) {
+  const size_t n = idx.size();
+  if (n == 0) return;
+  // written limbs -> representative item (first writer), open addressing
+  size_t cap = 16;
+  while (cap < 4 * n) cap <<= 1;
+  static thread_local std::vector<std::pair<const u64*, u32>> wmap;
+  wmap.assign(cap, std::make_pair((const u64*)nullptr, 0u));
+  auto wfind = [&](const u64* p, bool insert, u32 k) -> int32_t {
+    size_t h = hash_addr(p) & (cap - 1);
+    for (;;) {
+      if (wmap[h].first == nullptr) {
+        if (!insert) return -1;
+        wmap[h] = std::make_pair(p, k);
+        return (int32_t)k;
+      }
+      if (wmap[h].first == p) return (int32_t)wmap[h].second;
+      h = (h + 1) & (cap - 1);
+    }
+  };
+  std::vector<u32> parent(n);
+  for (u32 k = 0; k < n; k++) parent[k] = k;
+  auto find = [&](u32 x) {
+    while (parent[x] != x) x = parent[x] = parent[parent[x]];
+    return x;
+  };
+  auto unite = [&](u32 a, u32 b) {
+    a = find(a); b = find(b);
+    if (a != b) parent[std::max(a, b)] = std::min(a, b);
+  };
+  for (u32 k = 0; k < n; k++) {
+    const Op& o = ops_[idx[k]];
+    unite(k, (u32)wfind(o.r, true, k));
+    if (o.kind == OP_MAC && o.t_live) unite(k, (u32)wfind(o.t, true, k));
+  }
+  for (u32 k = 0; k < n; k++) {
+    const Op& o = ops_[idx[k]];
+    const u64* rd[3] = {o.kind == OP_FILL ? nullptr : o.a, o.b, o.c};
+    for (const u64* p : rd) {
+      if (!p) continue;
+      int32_t w = wfind(p, false, 0);
+      if (w >= 0) unite(k, (u32)w);
+    }
+  }
+  // group by chain, program order inside a chain (idx is in program order already)
+  std::vector<int32_t> chain_id(n, -1);
+  std::vector<u32>     chain_of(n);
+  u32 n_chains = 0;
+  for (u32 k = 0; k < n; k++) {
+    u32 root = find(k);
+    if (chain_id[root] < 0) chain_id[root] = (int32_t)n_chains++;
+    chain_of[k] = (u32)chain_id[root];
+  }
+  std::vector<u32> cnt(n_chains + 1, 0);
+  for (u32 k = 0; k < n; k++) cnt[chain_of[k] + 1]++;
+  for (u32 ch = 0; ch < n_chains; ch++) cnt[ch + 1] += cnt[ch];
+  std::vector<u32> order(n), pos(cnt.begin(), cnt.end() - 1);
+  for (u32 k = 0; k < n; k++) order[pos[chain_of[k]]++] = k;
+  // pack whole chains into launches; a chain longer than a launch continues in the next one
+  static thread_local ChainPack pack;
+  u32 items = 0, chains = 0;
+  auto launch = [&] {
+    if (items == 0) return;
+    pack.chain_start[chains] = (uint16_t)items;
+    pack.n_chains = chains;
+    prof::Scope ps("ew_chain", c_->stream);
+    ew_chain_kernel<<<dim3((c_->N + 255) / 256, chains), 256, 0, c_->stream>>>(c_->T, pack);
+    c_->launches++;
+    n_chain_launches++;
+    items = chains = 0;
+  };
+  for (u32 ch = 0; ch < n_chains; ch++) {
+    u32 len = cnt[ch + 1] - cnt[ch], at = cnt[ch];
+    while (len > 0) {
+      if (items == (u32)kChainCap || (items > 0 && items + len > (u32)kChainCap && len <= (u32)kChainCap))
+        launch();
+      const u32 take = std::min<u32>(len, (u32)kChainCap - items);
+      pack.chain_start[chains++] = (uint16_t)items;
+      for (u32 q = 0; q < take; q++) {
+        const Op& o = ops_[idx[order[at + q]]];
+        ChainItem& it = pack.it[items++];
+        it.r = o.r; it.a = o.a; it.b = o.b; it.c = o.c;
+        it.t = (o.kind == OP_MAC && o.t_live) ? o.t : nullptr;
+        it.g = o.g; it.op = o.kind;
+      }
+      at += take; len -= take;
+      if (len > 0) launch();  // the rest of this chain must run after this launch
+    }
+  }
+  launch();
+}
+
+void Scheduler::flush() {
+  if (ops_.empty()) {
+    for (u64* p : frees_) c_->free_limbs(p);
+    frees_.clear();
+    pending_free_bytes_ = 0;
+    return;
+  }
+  n_flush++;
+  u32 max_wave = 0;
+  for (const Op& o : ops_) max_wave = std::max(max_wave, o.wave);
+  // counting sort of op indices by wave (stable: program order inside a wave)
+  std::vector<u32> start(max_wave + 2, 0);
+  for (const Op& o : ops_) if (o.kind != OP_NOP) start[o.wave + 1]++;
+  for (u32 w = 0; w <= max_wave; w++) start[w + 1] += start[w];
+  std::vector<u32> sorted(start[max_wave + 1]), pos(start.begin(), start.end() - 1);
+  for (u32 i = 0; i < ops_.size(); i++)
+    if (ops_[i].kind != OP_NOP) sorted[pos[ops_[i].wave]++] = i;
+  std::vector<u32>        chain_idx, gather_idx;
+  std::vector<EncodeJob>  enc;
+  std::vector<ModupJob>   mu;
+  std::vector<ModdownJob> md;
+  std::vector<RescaleJob> rs;
+  static thread_local ChainPack gpack;
+  for (u32 w = 0; w <= max_wave; w++) {
+    if (start[w] == start[w + 1]) continue;
+    n_waves++;
+    chain_idx.clear(); gather_idx.clear(); enc.clear(); mu.clear(); md.clear(); rs.clear();
+    for (u32 s = start[w]; s < start[w + 1]; s++) {
+      const Op& o = ops_[sorted[s]];
+      switch (o.kind) {
+        case OP_GATHER:  gather_idx.push_back(sorted[s]); break;
+        case OP_ENCODE:  enc.push_back(enc_jobs_[o.p0]); break;
+        case OP_MODUP:   mu.push_back(ModupJob{o.r, o.a, o.p0, o.p1}); break;
+        case OP_MODDOWN: md.push_back(ModdownJob{o.r, o.a, o.p0}); break;
+        case OP_RESCALE: rs.push_back(RescaleJob{o.r, o.a, o.p0}); break;
+        default:         chain_idx.push_back(sorted[s]); break;
+      }
+    }
+    run_chains(chain_idx);
+    for (size_t at = 0; at < gather_idx.size(); at += kChainCap) {
+      const u32 cnt = (u32)std::min<size_t>(kChainCap, gather_idx.size() - at);
+      for (u32 k = 0; k < cnt; k++) {
+        const Op& o = ops_[gather_idx[at + k]];
+        ChainItem& it = gpack.it[k];
+        it.r = o.r; it.a = o.a; it.b = o.b; it.c = nullptr; it.t = nullptr; it.g = o.g; it.op = OP_GATHER;
+      }
+      gpack.n_chains = cnt;
+      prof::Scope ps("gather_batch", c_->stream);
+      gather_batch_kernel<<<dim3((c_->N + 255) / 256, cnt), 256, 0, c_->stream>>>(c_->T, gpack);
+      c_->launches++;
+    }
+    if (!enc.empty()) c_->encode_batch(enc.data(), enc.size());
+    if (!mu.empty()) c_->modup_batch(mu.data(), mu.size());
+    if (!md.empty()) c_->moddown_batch(md.data(), md.size());
+    if (!rs.empty()) c_->rescale_batch(rs.data(), rs.size());
+  }
+  ops_.clear();
+  enc_jobs_.clear();
+  for (u64* p : frees_) c_->free_limbs(p);
+  frees_.clear();
+  pending_free_bytes_ = 0;
+  gen_++;
+  live_ = 0;
+  if (gen_ == 0) {  // generation counter wrapped: really clear the table
+    memset(table_.data(), 0, table_.size() * sizeof(Limb));
+    gen_ = 1;
+  }
+}
+
+}  // namespace ace

@@ -48,3 +48,27 @@ def test_resnet20_bit_exact():
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", MODEL + "_ref.so")):
         pytest.skip("oracle/_ref/%s_ref.so not built (needs the reference tree at build time)" % MODEL)
     _run("exact", timeout=3000)
+
+
+def _driver_logits(env_extra):
+    exe = os.path.join(ROOT, "tests", "_emitted_bin", MODEL)
+    if not os.path.exists(exe):
+        pytest.skip("model binary not built (needs the reference tree at build time)")
+    sys.path.insert(0, ROOT)
+    import bench
+    env = dict(os.environ, ACE_B200_DATA_FILE=bench.weight_file(MODEL), RTLIB_BTS_EVEN_POLY="1",
+               ACE_B200_QUIET="1", ACE_B200_SEED="777", **env_extra)
+    r = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("[driver] logits")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    return lines[0]
+
+
+def test_resnet20_deferred_equals_eager():
+    """the scheduler (csrc/sched.h: waves, batching, dead-store elimination, mul+add fusion) must
+    not change a single bit: same keys, same image, call-by-call execution (ACE_B200_EAGER=1)
+    against deferred execution; logits compared at full double precision (%.17g)"""
+    eager = _driver_logits({"ACE_B200_EAGER": "1"})
+    deferred = _driver_logits({})
+    assert eager == deferred, eager + "\n" + deferred
