@@ -436,16 +436,23 @@ void Evaluator::rotate_iteration(Ct& result, BtsPrecom& pc,
     u64 *r0 = rot + (size_t)j * 2 * WN, *r1 = r0 + WN;
     int32_t val = rin[step][j];
     if (val != 0) {
+      // Fast_rotate_ext in one pass: key inner product, + P*c0, automorphism (written through
+      // the inverse table)
       const SwitchKey& key = rot_key(val);
-      c->ksw_acc(acc, acc + WN, ext, result.c1, nq, key);
-      launch_mul_scalar_add(c->T, acc, acc, result.c0, c->pmodq_, c->pmodq_sh_, nq, c->stream);
-      const int64_t* order = c->auto_order(c->auto_index(val));
-      launch_gather_basis(c->T, r0, acc, order, ext_b, c->stream);
-      launch_gather_basis(c->T, r1, acc + WN, order, ext_b, c->stream);
+      if (!key.k0 || !key.k1) throw std::runtime_error("switch key not loaded");
+      const int64_t* inv = c->auto_order_inv(c->auto_index(val));
+      launch_ksw_inner_rot(c->T, r0, r1, ext, result.c1, (u32)c->part_size, key.k0, key.k1, beta, nq,
+                           (u32)c->L, K, result.c0, c->pmodq_, c->pmodq_sh_, inv, false, false,
+                           c->stream);
+      {
+        const uint64_t n = 2ull * beta * W;  // what ksw_acc counts
+        c->tr(Context::TR_LIMB_MUL, 0, n);
+        c->tr(Context::TR_LIMB_ADD, 0, n);
+      }
       c->tr(Context::TR_LIMB_MUL, 0, nq);
       c->tr(Context::TR_LIMB_ADD, 0, nq);
       c->tr(Context::TR_LIMB_ROT, 0, 2 * W);
-      c->launches += 3;
+      c->launches += 1;
     } else {  // Switch_key_ext: lift (c0, c1) by P, P limbs are zero
       launch_mul_scalar(c->T, r0, result.c0, c->pmodq_, c->pmodq_sh_, 0, nq, c->stream);
       launch_mul_scalar(c->T, r1, result.c1, c->pmodq_, c->pmodq_sh_, 0, nq, c->stream);
@@ -485,25 +492,27 @@ void Evaluator::rotate_iteration(Ct& result, BtsPrecom& pc,
     int32_t val = rout[step][i];
     if (val != 0) {
       const int64_t* order = c->auto_order(c->auto_index(val));
+      const int64_t* inv   = c->auto_order_inv(c->auto_index(val));
       // first += rot(inner.c0)
-      launch_gather_basis(c->T, tmp, inner, order, ext_b, c->stream);
-      launch_ew_basis(c->T, EW_ADD, first, first, tmp, ext_b, c->stream);
-      // inner.c1 -> Q basis -> digits -> key switch in the extended basis -> rotate -> outer
+      launch_gather_add_basis(c->T, first, inner, order, ext_b, c->stream);
+      // inner.c1 -> Q basis -> digits -> key switch in the extended basis -> rotate -> outer:
+      // the inner product writes through the inverse automorphism table and accumulates
       c->mod_down_pair(red, nullptr, inner + WN, nullptr, nq, nullptr);
       c->modup_all(ext, red, nq);
-      c->ksw_acc(acc, acc + WN, ext, red, nq, rot_key(val));
-      launch_gather_basis(c->T, tmp, acc, order, ext_b, c->stream);
-      launch_gather_basis(c->T, tmp + WN, acc + WN, order, ext_b, c->stream);
-      if (outer0_zero) {
-        ACE_CUDA(cudaMemcpyAsync(outer, tmp, WN * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
-        outer0_zero = false;
-      } else {
-        launch_ew_basis(c->T, EW_ADD, outer, outer, tmp, ext_b, c->stream);
+      const SwitchKey& key = rot_key(val);
+      if (!key.k0 || !key.k1) throw std::runtime_error("switch key not loaded");
+      launch_ksw_inner_rot(c->T, outer, outer + WN, ext, red, (u32)c->part_size, key.k0, key.k1, beta,
+                           nq, (u32)c->L, K, nullptr, nullptr, nullptr, inv, !outer0_zero, true,
+                           c->stream);
+      outer0_zero = false;
+      {
+        const uint64_t n = 2ull * beta * W;  // what ksw_acc counts
+        c->tr(Context::TR_LIMB_MUL, 0, n);
+        c->tr(Context::TR_LIMB_ADD, 0, n);
       }
-      launch_ew_basis(c->T, EW_ADD, outer + WN, outer + WN, tmp + WN, ext_b, c->stream);
       c->tr(Context::TR_LIMB_ROT, 0, 3 * W);
       c->tr(Context::TR_LIMB_ADD, 0, 3 * W);
-      c->launches += 6;
+      c->launches += 2;
     } else {
       launch_ew_basis(c->T, EW_ADD, first, first, inner, ext_b, c->stream);
       launch_ew_basis(c->T, EW_ADD, outer + WN, outer + WN, inner + WN, ext_b, c->stream);

@@ -116,10 +116,20 @@ Context::Context(const Params& p, int dev) : params(p), device(dev) {
   }
   T.N = N; T.logN = logN; T.G = (u32)G;
   T.mod    = to_device(mods);
-  T.tw     = to_device(tw);
-  T.tw_sh  = to_device(tw_sh);
-  T.itw    = to_device(itw);
-  T.itw_sh = to_device(itw_sh);
+  {  // the four twiddle tables in one block (one L2 access-policy window can cover them)
+    const size_t per = G * (size_t)N;
+    u64* blk = nullptr;
+    ACE_CUDA(cudaMalloc(&blk, 4 * per * sizeof(u64)));
+    owned_.push_back(blk);
+    h2d_sync(blk, tw.data(), per * sizeof(u64));
+    h2d_sync(blk + per, tw_sh.data(), per * sizeof(u64));
+    h2d_sync(blk + 2 * per, itw.data(), per * sizeof(u64));
+    h2d_sync(blk + 3 * per, itw_sh.data(), per * sizeof(u64));
+    T.tw = blk; T.tw_sh = blk + per; T.itw = blk + 2 * per; T.itw_sh = blk + 3 * per;
+    // (Pinning the tables in the persisting part of the L2 with an access-policy window was
+    // measured and rejected: key switch 553 -> 583 us, ResNet-20 1.12 -> 1.24 s/image -- the
+    // ciphertext intermediates that flow from one kernel to the next need the L2 more.)
+  }
   T.n_inv    = to_device(n_inv);
   T.n_inv_sh = to_device(n_inv_sh);
 
@@ -431,6 +441,15 @@ const int64_t* Context::auto_order(u32 k) {  // number_theory.c:201-214 (is_ntt 
   return d;
 }
 
+// the inverse permutation of auto_order(k) is the table of k^-1 mod 2N
+const int64_t* Context::auto_order_inv(u32 k) {
+  const u64 M = 2 * (u64)N;
+  u64 inv = k;  // Newton iteration for the inverse of an odd number modulo a power of two
+  for (int i = 0; i < 6; i++) inv = (inv * (2 + M - (k * inv) % M)) % M;
+  if ((inv * k) % M != 1) throw std::runtime_error("auto_order_inv: no inverse");
+  return auto_order((u32)inv);
+}
+
 void Context::import_key_limbs(SwitchKey& key, u32 part, int which, const u64* host) {
   if (part >= dnum) throw std::runtime_error("key part out of range");
   size_t per = G * (size_t)N;
@@ -493,10 +512,11 @@ void Context::ksw_acc(u64* acc0, u64* acc1, const u64* ext, const u64* d, u32 nu
 // Reduce_rns_base of two extended polynomials at once (polynomial.c:928-967); a0/a1 are laid
 // out [num_q | K]; add0 (optional) is added to out0.  a1 == nullptr: one polynomial only.
 void Context::mod_down_pair(u64* out0, u64* out1, const u64* a0, const u64* a1, u32 num_q,
-                            const u64* add0) {
+                            const u64* add0, const u64* add1) {
   const u32 np = a1 ? 2 : 1;
   tr(TR_MODDOWN_POLY, num_q, np);
   if (add0) tr(TR_LIMB_ADD, 0, num_q);
+  if (add1) tr(TR_LIMB_ADD, 0, num_q);
   u64* pc   = alloc_limbs(np * K, false);
   u64* conv = alloc_limbs(np * (size_t)num_q, false);
   ConvDesc md[2];
@@ -516,7 +536,7 @@ void Context::mod_down_pair(u64* out0, u64* out1, const u64* a0, const u64* a1, 
   launch_ntt(T, cb, stream);
   launch_moddown_tail(T, out0, a0, conv, add0, pinv_mod_q_, pinv_mod_q_sh_, num_q, stream);
   if (a1)
-    launch_moddown_tail(T, out1, a1, conv + (size_t)num_q * N, nullptr, pinv_mod_q_,
+    launch_moddown_tail(T, out1, a1, conv + (size_t)num_q * N, add1, pinv_mod_q_,
                         pinv_mod_q_sh_, num_q, stream);
   launches += 1 + np + ((logN > 12) ? 2 : 1);
   free_limbs(pc); free_limbs(conv);
@@ -527,14 +547,14 @@ void Context::mod_down_pair(u64* out0, u64* out1, const u64* a0, const u64* a1, 
 // all complement limbs, one inner-product launch that reads the key once, and one ModDown
 // for both output polynomials.
 void Context::key_switch(u64* out0, u64* out1, const u64* d, u32 num_q, const SwitchKey& key,
-                         const u64* add0) {
+                         const u64* add0, const u64* add1) {
   if (!key.k0 || !key.k1) throw std::runtime_error("switch key not loaded");
   const u32 beta = (u32)num_decomp(num_q), W = num_q + (u32)K;
   u64* ext = alloc_limbs((size_t)beta * W, false);
   u64* acc = alloc_limbs(2 * (size_t)W, false);
   modup_all(ext, d, num_q);
   ksw_acc(acc, acc + (size_t)W * N, ext, d, num_q, key);
-  mod_down_pair(out0, out1, acc, acc + (size_t)W * N, num_q, add0);
+  mod_down_pair(out0, out1, acc, acc + (size_t)W * N, num_q, add0, add1);
   free_limbs(ext); free_limbs(acc);
 }
 
@@ -557,20 +577,14 @@ void Context::ct_rotate(u64* r0, u64* r1, const u64* c0, const u64* c1, u32 num_
 // tensor product + emitted Relinearize(): r0 = a0 b0 + ks0(a1 b1), r1 = a0 b1 + a1 b0 + ks1
 void Context::ct_mul_relin(u64* r0, u64* r1, const u64* a0, const u64* a1, const u64* b0,
                            const u64* b1, u32 num_q) {
-  u64* t  = alloc_limbs(4 * (size_t)num_q, false);
-  u64 *d2 = t, *d1 = t + (size_t)num_q * N, *s0 = t + 2 * (size_t)num_q * N,
-      *s1 = t + 3 * (size_t)num_q * N;
-  launch_ew(T, EW_MUL, d2, a1, b1, 0, num_q, stream);
-  key_switch(s0, s1, d2, num_q, relin_key, nullptr);
-  launch_ew(T, EW_MUL, d1, a0, b1, 0, num_q, stream);
-  launch_ew(T, EW_MUL, d2, a1, b0, 0, num_q, stream);
-  launch_ew(T, EW_ADD, d1, d1, d2, 0, num_q, stream);
-  launch_ew(T, EW_ADD, r1, d1, s1, 0, num_q, stream);
-  launch_ew(T, EW_MUL, d2, a0, b0, 0, num_q, stream);
-  launch_ew(T, EW_ADD, r0, d2, s0, 0, num_q, stream);
+  u64* t  = alloc_limbs(3 * (size_t)num_q, false);
+  u64 *d0 = t, *d1 = t + (size_t)num_q * N, *d2 = t + 2 * (size_t)num_q * N;
+  launch_tensor(T, d0, d1, d2, a0, a1, b0, b1, num_q, stream);
+  // the two final additions ride on the ModDown tails of the key switch
+  key_switch(r0, r1, d2, num_q, relin_key, d0, d1);
   tr(TR_LIMB_MUL, 0, 4 * num_q);
-  tr(TR_LIMB_ADD, 0, 3 * num_q);
-  launches += 7;
+  tr(TR_LIMB_ADD, 0, 1 * num_q);  // d1 = a0 b1 + a1 b0; the other two are counted by mod_down_pair
+  launches += 1;
   free_limbs(t);
 }
 

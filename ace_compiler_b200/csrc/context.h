@@ -118,6 +118,7 @@ class Context {
   // ---- keys and automorphisms
   u32            auto_index(int32_t rot_idx) const;
   const int64_t* auto_order(u32 auto_idx);  // device table, built on first use
+  const int64_t* auto_order_inv(u32 auto_idx);  // table of the inverse automorphism (scatter form)
   SwitchKey&     rot_key(u32 auto_idx) { return rot_keys_[auto_idx]; }
   bool           has_rot_key(u32 auto_idx) const { return rot_keys_.count(auto_idx) != 0; }
   SwitchKey      relin_key;
@@ -127,12 +128,12 @@ class Context {
   // hybrid key switch of d (num_q limbs, NTT form); out0 += nothing, optional add0 is added
   // to out0 after ModDown (the c0 of a rotation).
   void key_switch(u64* out0, u64* out1, const u64* d, u32 num_q, const SwitchKey& key,
-                  const u64* add0);
+                  const u64* add0, const u64* add1 = nullptr);
   void modup_all(u64* ext, const u64* d, u32 num_q);
   void ksw_acc(u64* acc0, u64* acc1, const u64* ext, const u64* d, u32 num_q,
                const SwitchKey& key);
   void mod_down_pair(u64* out0, u64* out1, const u64* a0, const u64* a1, u32 num_q,
-                     const u64* add0);
+                     const u64* add0, const u64* add1 = nullptr);
   void ct_rotate(u64* r0, u64* r1, const u64* c0, const u64* c1, u32 num_q, int32_t rot_idx);
   void ct_mul_relin(u64* r0, u64* r1, const u64* a0, const u64* a1, const u64* b0,
                     const u64* b1, u32 num_q);

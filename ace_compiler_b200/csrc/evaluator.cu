@@ -196,8 +196,8 @@ void Evaluator::rescale(Ct& res, Ct& a) {
   u32 sfd = a.sfd - 1, slots = a.slots, nq = a.nq;
   Ct t;
   reserve(t, nq, 0);
-  c->rescale(t.c0, a.c0, nq);
-  c->rescale(t.c1, a.c1, nq);
+  RescaleJob jobs[2] = {{t.c0, a.c0, nq}, {t.c1, a.c1, nq}};
+  c->rescale_batch(jobs, 2);
   move(res, t);
   res.nq = nq - 1;
   res.sf = sf; res.sfd = sfd; res.slots = slots;

@@ -717,4 +717,28 @@ void launch_rescale_post_batch(const DeviceTables& T, const Ptr3Batch& P, const 
   rescale_post_batch_kernel<<<ew_grid(T, P.n), 256, 0, s>>>(T, P, qlinv, qlinv_sh, L);
 }
 
+// Tensor product of two ciphertexts in one pass (Mul_ciphertext3, ckks_evaluator.c:133-165):
+//   d0 = a0 b0,  d1 = a0 b1 + a1 b0,  d2 = a1 b1     -- 4 limbs read, 3 written per limb index
+__global__ void __launch_bounds__(256) tensor_kernel(DeviceTables T, u64* __restrict__ d0,
+                                                     u64* __restrict__ d1, u64* __restrict__ d2,
+                                                     const u64* __restrict__ a0,
+                                                     const u64* __restrict__ a1,
+                                                     const u64* __restrict__ b0,
+                                                     const u64* __restrict__ b1) {
+  const Modulus m   = T.mod[blockIdx.y];
+  const size_t  off = (size_t)blockIdx.y * T.N;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
+    const u64 x0 = a0[off + i], x1 = a1[off + i], y0 = b0[off + i], y1 = b1[off + i];
+    d0[off + i] = mul_mod(x0, y0, m);
+    d1[off + i] = add_mod(mul_mod(x0, y1, m), mul_mod(x1, y0, m), m.q);
+    d2[off + i] = mul_mod(x1, y1, m);
+  }
+}
+void launch_tensor(const DeviceTables& T, u64* d0, u64* d1, u64* d2, const u64* a0,
+                   const u64* a1, const u64* b0, const u64* b1, u32 n_limbs, cudaStream_t s) {
+  if (n_limbs == 0) return;
+  prof::Scope prof_scope_("tensor", s);
+  tensor_kernel<<<ew_grid(T, n_limbs), 256, 0, s>>>(T, d0, d1, d2, a0, a1, b0, b1);
+}
+
 }  // namespace ace

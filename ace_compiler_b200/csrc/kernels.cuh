@@ -97,6 +97,11 @@ void launch_moddown_tail(const DeviceTables& T, u64* out, const u64* old, const 
                          const u64* add, const u64* pinv, const u64* pinv_sh, u32 n_limbs,
                          cudaStream_t s);
 
+// d0 = a0 b0, d1 = a0 b1 + a1 b0, d2 = a1 b1 over n_limbs Q limbs (tensor product of two
+// ciphertexts, ckks_evaluator.c:133-165) in one pass
+void launch_tensor(const DeviceTables& T, u64* d0, u64* d1, u64* d2, const u64* a0,
+                   const u64* a1, const u64* b0, const u64* b1, u32 n_limbs, cudaStream_t s);
+
 // Rescale (polynomial.c:1097-1161):
 //  pre : tmp[i] = switch_modulus(last, q_l, q_i) * negqlinv[i]          (coefficient form)
 //  post: out[i] = c[i] * qlinv[i] + NTT(tmp)[i]
@@ -191,5 +196,16 @@ void launch_pt_dot(const DeviceTables& T, u64* out0, u64* out1, const DotArgs& a
 // Fast_rotate_ext (ckks_evaluator.c:566-573); r may alias acc.
 void launch_mul_scalar_add(const DeviceTables& T, u64* r, const u64* acc, const u64* c,
                            const u64* sc, const u64* sc_sh, u32 n_limbs, cudaStream_t s);
+
+// ksw inner product fused with the epilogue of a rotation in the extended basis; see
+// kernels_ext.cu.  c0 / scatter may be null; accN: add into outN instead of overwriting it.
+void launch_ksw_inner_rot(const DeviceTables& T, u64* out0, u64* out1, const u64* ext,
+                          const u64* own, u32 part_size, const u64* key0, const u64* key1,
+                          u32 beta, u32 num_q, u32 L, u32 K, const u64* c0, const u64* pmodq,
+                          const u64* pmodq_sh, const int64_t* scatter, bool acc0, bool acc1,
+                          cudaStream_t s);
+// r[y][i] += a[y][order[i]]
+void launch_gather_add_basis(const DeviceTables& T, u64* r, const u64* a, const int64_t* order,
+                             Basis bs, cudaStream_t s);
 
 }  // namespace ace

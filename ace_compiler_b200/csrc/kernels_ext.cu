@@ -167,4 +167,73 @@ void launch_mul_scalar_add(const DeviceTables& T, u64* r, const u64* acc, const 
   mul_scalar_add_kernel<<<grid_for(T, n_limbs), 256, 0, s>>>(T, r, acc, c, sc, sc_sh);
 }
 
+// Key inner product with the epilogue of a "fast" rotation in the extended basis
+// (Fast_rotate_ext, ckks_evaluator.c:537-577 = Fast_switch_key_ext + P*c0 + automorphism):
+//   v0[o] = sum_j ext_j[o] key0_j[g(o)]  (+ c0[o] * (P mod q_o) on the Q limbs)
+//   v1[o] = sum_j ext_j[o] key1_j[g(o)]
+//   out[o][scatter[n]] (+)= v[o][n]      scatter = the inverse automorphism table
+// One pass instead of inner product, scalar multiply-add, two gathers and two additions; every
+// value is the same canonical residue the separate kernels produce.
+__global__ void __launch_bounds__(256) ksw_inner_rot_kernel(
+    DeviceTables T, u64* __restrict__ out0, u64* __restrict__ out1, const u64* __restrict__ ext,
+    const u64* __restrict__ own, u32 part_size, const u64* __restrict__ key0,
+    const u64* __restrict__ key1, u32 beta, u32 num_q, u32 L, u32 K, const u64* __restrict__ c0,
+    const u64* __restrict__ pmodq, const u64* __restrict__ pmodq_sh,
+    const int64_t* __restrict__ scatter, int acc0_flag, int acc1_flag) {
+  const u32     o = blockIdx.y;
+  const u32     g = o < num_q ? o : L + (o - num_q);
+  const u32     W = num_q + K;
+  const Modulus m = T.mod[g];
+  const u32     n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= T.N) return;
+  u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+  for (u32 j = 0; j < beta; j++) {
+    const bool mine = own != nullptr && o < num_q && o / part_size == j;
+    const u64 e = mine ? own[(size_t)o * T.N + n] : ext[((size_t)j * W + o) * T.N + n];
+    const u64 k0 = key0[((size_t)j * (L + K) + g) * T.N + n];
+    const u64 k1 = key1[((size_t)j * (L + K) + g) * T.N + n];
+    mac128(lo0, hi0, e, k0);
+    mac128(lo1, hi1, e, k1);
+  }
+  u64 v0 = reduce128(lo0, hi0, m), v1 = reduce128(lo1, hi1, m);
+  if (c0 != nullptr && o < num_q)
+    v0 = add_mod(v0, mul_shoup(c0[(size_t)o * T.N + n], pmodq[o], pmodq_sh[o], m.q), m.q);
+  const size_t pos = (size_t)o * T.N + (scatter ? (u32)scatter[n] : n);
+  if (acc0_flag) v0 = add_mod(out0[pos], v0, m.q);
+  if (acc1_flag) v1 = add_mod(out1[pos], v1, m.q);
+  out0[pos] = v0;
+  out1[pos] = v1;
+}
+
+void launch_ksw_inner_rot(const DeviceTables& T, u64* out0, u64* out1, const u64* ext,
+                          const u64* own, u32 part_size, const u64* key0, const u64* key1,
+                          u32 beta, u32 num_q, u32 L, u32 K, const u64* c0, const u64* pmodq,
+                          const u64* pmodq_sh, const int64_t* scatter, bool acc0, bool acc1,
+                          cudaStream_t s) {
+  prof::Scope prof_scope_("ksw_inner_rot", s);
+  dim3 grid((T.N + 255) / 256, num_q + K);
+  ksw_inner_rot_kernel<<<grid, 256, 0, s>>>(T, out0, out1, ext, own, part_size, key0, key1, beta,
+                                            num_q, L, K, c0, pmodq, pmodq_sh, scatter,
+                                            acc0 ? 1 : 0, acc1 ? 1 : 0);
+}
+
+// r[y][i] += a[y][order[i]] over all limbs of the basis (automorphism + accumulate)
+__global__ void __launch_bounds__(256) gather_add_basis_kernel(DeviceTables T, u64* __restrict__ r,
+                                                               const u64* __restrict__ a,
+                                                               const int64_t* __restrict__ order,
+                                                               Basis bs) {
+  const u64    q   = T.mod[bs.g(blockIdx.y)].q;
+  const size_t off = (size_t)blockIdx.y * T.N;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
+    const int64_t k = order[i];
+    const u64 v = k >= 0 ? a[off + k] : q - a[off - k];
+    r[off + i] = add_mod(r[off + i], v, q);
+  }
+}
+void launch_gather_add_basis(const DeviceTables& T, u64* r, const u64* a, const int64_t* order,
+                             Basis bs, cudaStream_t s) {
+  prof::Scope prof_scope_("gather_add_basis", s);
+  gather_add_basis_kernel<<<grid_for(T, bs.width()), 256, 0, s>>>(T, r, a, order, bs);
+}
+
 }  // namespace ace

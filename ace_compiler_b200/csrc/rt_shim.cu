@@ -526,7 +526,7 @@ API void Run_main_graph(void) {  // common/src/rt_lib.c:16-20
   if (prof::on) { ctx(); prof::reset(); }
   if (!Main_graph()) die("Main_graph failed");
   guard([&] { ctx()->sync(); });
-  if (prof::on) prof::report("Main_graph");
+  if (prof::on) prof::report("emitted");
 }
 
 API void Tm_start(const char* msg) {
@@ -910,8 +910,9 @@ API CIPHER Encrypt(CIPHER res, PLAIN plain) {  // cipher_eval.c:406-409
 
 // Bootstrap (cipher_eval.c:366-404) -> Evaluator::bootstrap
 API CIPHER Bootstrap(CIPHER res, CIPHER ciph, uint32_t level_after_bts) {
-  StatScope ss(ST_BTS);
   Context* c = ctx();
+  if (prof::on) prof::report("emitted");  // device time since the previous bootstrap
+  StatScope ss(ST_BTS);
   if (ciph->_c0_poly._num_primes_p != 0) die("Bootstrap: extended ciphertext");
   guard([&] {
     Ct in;
@@ -935,6 +936,7 @@ API CIPHER Bootstrap(CIPHER res, CIPHER ciph, uint32_t level_after_bts) {
     }
     res->_scaling_factor = out.sf; res->_sf_degree = out.sfd; res->_slots = out.slots;
   });
+  if (prof::on) prof::report("bootstrap");
   return res;
 }
 

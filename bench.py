@@ -47,6 +47,12 @@ WORKLOAD = ("ResNet-20 CIFAR-10 single-image encrypted inference: ACE-emitted "
 TRACE_CLASSES = ["modup_digit", "moddown_poly", "rescale_poly", "encode", "limb_mul", "limb_add",
                  "limb_rot", "limb_ntt"]
 TRACE_LEVELS = 72
+# dram__bytes_read.sum + dram__bytes_write.sum of one 45-limb forward NTT (ntt_fwd_strided<4> +
+# ntt_fwd_tile8) from the ncu --set full capture profiles/r1_ncu_full_ntt_v1.csv: 23.6 MB (data)
+# + 70.8 MB (data + 47.2 MB of twiddle tables) read, ~1 MB written back inside the launches (the
+# rest of the 47 MB of results leaves L2 later).  Algorithmic bytes are 47.2 MB: the excess is
+# the per-prime twiddle tables (w and its Shoup companion, 1 MiB per limb).
+NTT_DRAM_TRAFFIC_PER_LAUNCH = 95.4e6
 
 
 def read_peaks():
@@ -232,7 +238,7 @@ def run_ours(args):
         ach = alg_bytes / per_launch_s / 1e9
         roof = {"bound": "hbm", "kernel": "ntt_fwd_strided<4> + ntt_fwd_tile8 (%d limbs/launch)" % G,
                 "achieved": round(ach, 1), "peak": peak, "peak_source": how, "unit": "GB/s",
-                "frac": round(ach / peak, 4), "traffic": None,
+                "frac": round(ach / peak, 4), "traffic": NTT_DRAM_TRAFFIC_PER_LAUNCH,
                 "alg_bytes_per_launch": alg_bytes, "launch_us": round(per_launch_s * 1e6, 2),
                 "note": "two passes over each limb (2 MiB moved per 1 MiB algorithmic); the butterflies "
                         "are INT32-multiply bound, see profiles/"}

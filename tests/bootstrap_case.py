@@ -1,6 +1,6 @@
 """One bootstrap parity case, run in its own process (the reference keeps one global context).
 
-    python tests/bootstrap_case.py N depth hamming_weight slots level_in level_after
+    python tests/bootstrap_case.py N depth hamming_weight slots level_in level_after [q0_bits sf_bits]
 
 The reference library (oracle/_ref/libace_ref.so) generates the keys -- including the bootstrap
 rotation keys and the conjugation key of Bootstrap_keygen -- encrypts a message and bootstraps it
@@ -20,12 +20,13 @@ sys.path.insert(0, HERE)
 
 def main():
     N, depth, hw, slots, level_in, level_after = (int(x) for x in sys.argv[1:7])
+    q0, sf = (int(sys.argv[7]), int(sys.argv[8])) if len(sys.argv) > 8 else (51, 50)
     import ace_compiler_b200 as ace
     from oracle_bindings import RefLib, build_oracles
     build_oracles()
     t = time.time()
-    ref = RefLib(N, depth, 51, 50, 3, hw, [1], with_bootstrap=True)
-    ctx = ace.Context(N, depth, 51, 50, 3, hamming_weight=hw)
+    ref = RefLib(N, depth, q0, sf, 3, hw, [1], with_bootstrap=True)
+    ctx = ace.Context(N, depth, q0, sf, 3, hamming_weight=hw)
     rots = ctx.bootstrap_rot_indices(slots)
     print("reference init %.1fs; %d bootstrap rotation keys, depth %d" %
           (time.time() - t, len(rots), ctx.bootstrap_depth()), flush=True)

@@ -20,16 +20,19 @@ CASES = [
     (2048, 18, 192, 256, 2, 3, 1),     # sparsely packed: partial sums + extra rotation
     (16384, 17, 192, 8192, 2, 3, 1),   # 5 collapsed FFT layers (b=4) + fixed-root table for the P primes
     (65536, 33, 192, 32768, 3, 15, 1), # ResNet-20's parameter set and call (GEN20:1577, 7148-7150)
+    # ResNet-110's scale (q0 = 2^51, Delta = 2^48: resnet110_cifar10_train.onnx.inc Get_context_params)
+    (1024, 17, 192, 512, 2, 3, 1, 51, 48),
+    (2048, 18, 192, 256, 2, 3, 1, 51, 48),
 ]
 
 
-@pytest.mark.parametrize("case", CASES, ids=lambda c: "N%d_d%d_hw%d_s%d_even%d" % (c[0], c[1], c[2], c[3], c[6]))
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "N%d_d%d_hw%d_s%d_even%d" % (c[0], c[1], c[2], c[3], c[6]) + ("_sf%d" % c[8] if len(c) > 8 else ""))
 def test_bootstrap_bit_exact(case):
-    N, depth, hw, slots, lin, lafter, even = case
+    N, depth, hw, slots, lin, lafter, even = case[:7]
     env = dict(os.environ)
     env["RTLIB_BTS_EVEN_POLY"] = str(even)
     r = subprocess.run([sys.executable, os.path.join(HERE, "bootstrap_case.py"), str(N), str(depth),
-                        str(hw), str(slots), str(lin), str(lafter)],
+                        str(hw), str(slots), str(lin), str(lafter)] + [str(x) for x in case[7:]],
                        env=env, capture_output=True, text=True, timeout=1500)
     sys.stdout.write(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-2000:] + "\n" + r.stderr[-4000:]

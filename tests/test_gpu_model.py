@@ -50,15 +50,17 @@ def test_resnet20_bit_exact():
     _run("exact", timeout=3000)
 
 
-def _driver_logits(env_extra):
-    exe = os.path.join(ROOT, "tests", "_emitted_bin", MODEL)
+def _driver_logits(env_extra, model=MODEL, n_classes=10):
+    exe = os.path.join(ROOT, "tests", "_emitted_bin", model)
     if not os.path.exists(exe):
         pytest.skip("model binary not built (needs the reference tree at build time)")
     sys.path.insert(0, ROOT)
     import bench
-    env = dict(os.environ, ACE_B200_DATA_FILE=bench.weight_file(MODEL), RTLIB_BTS_EVEN_POLY="1",
+    env = dict(os.environ, ACE_B200_DATA_FILE=bench.weight_file(model), RTLIB_BTS_EVEN_POLY="1",
                ACE_B200_QUIET="1", ACE_B200_SEED="777", **env_extra)
-    r = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=900, env=env)
+    r = subprocess.run([exe, "1", str(n_classes)], capture_output=True, text=True, timeout=1500,
+                       env=env)
+    sys.stdout.write("\n".join(l for l in r.stdout.splitlines() if "[driver]" in l)[-1500:] + "\n")
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("[driver] logits")]
     assert len(lines) == 1, r.stdout[-2000:]
@@ -72,3 +74,19 @@ def test_resnet20_deferred_equals_eager():
     eager = _driver_logits({"ACE_B200_EAGER": "1"})
     deferred = _driver_logits({})
     assert eager == deferred, eager + "\n" + deferred
+
+
+@pytest.mark.parametrize("model,n_classes", [("resnet32_cifar100_pre", 100),
+                                             ("resnet56_cifar10_pre", 10),
+                                             ("resnet110_cifar10_train", 10)])
+def test_other_emitted_resnets(model, n_classes):
+    """BASELINE.json configs 3-5: the reference's other checked-in emitted ResNets (unmodified
+    .inc files; 298 rotation keys for CIFAR-100, 55 / 109 bootstraps for ResNet-56 / -110, scale
+    2^48 for ResNet-110) run end to end on the B200 runtime with synthetic weights; deferred and
+    call-by-call execution must agree bit for bit, and the decrypted logits must be sane
+    (a diverged bootstrap gives |logit| >> 1 or NaN)."""
+    deferred = _driver_logits({}, model, n_classes)
+    vals = [float(x) for x in deferred.split(":", 1)[1].split()]
+    assert len(vals) == n_classes and all(abs(v) < 1.0 for v in vals), deferred
+    if model == "resnet32_cifar100_pre":  # the eager run of the two deep ones takes minutes
+        assert _driver_logits({"ACE_B200_EAGER": "1"}, model, n_classes) == deferred
