@@ -12,6 +12,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -664,6 +665,7 @@ API void Ace_import_switch_key(bool is_rot, int32_t rot_idx, uint32_t part, int 
 }
 
 // =========================================================================== ciphertexts
+static void dbg_range(const char* where, CIPHER ct);
 API void Init_ciph_same_scale(CIPHER res, CIPHER c1, CIPHER c2) {  // cipher_eval.c:32-43
   CIPHER ciph = c2 != nullptr ? lower_level(c1, c2) : c1;
   res->_scaling_factor = ciph->_scaling_factor;
@@ -683,10 +685,26 @@ API void Init_ciph_up_scale(CIPHER res, CIPHER c1, CIPHER c2) {
   init_cipher(res, ciph, c1->_scaling_factor * c2->_scaling_factor, c1->_sf_degree + c2->_sf_degree);
 }
 API void Init_ciph_up_scale_plain(CIPHER res, CIPHER ciph, PLAIN plain) {
+  dbg_range("mul_plain", ciph);
   init_cipher(res, ciph, ciph->_scaling_factor * plain->_scaling_factor,
               ciph->_sf_degree + plain->_sf_degree);
 }
+// ACE_B200_DEBUG_RANGE=<n> (own keys): decrypt the operand of the first n rescales / plaintext
+// multiplications and print its message range -- a trace of activation magnitudes
+static void dbg_range(const char* where, CIPHER ct) {
+  static int left = getenv("ACE_B200_DEBUG_RANGE") ? atoi(getenv("ACE_B200_DEBUG_RANGE")) : 0;
+  if (left <= 0 || ct->_c0_poly._data == nullptr || ct->_c0_poly._num_primes_p) return;
+  left--;
+  double* m = Get_msg(ct);
+  double mx = 0;
+  for (uint32_t i = 0; i < ct->_slots; i++) mx = std::max(mx, fabs(m[i]));
+  printf("[ace_b200 range] %-12s level %2zu sf_degree %u scale 2^%.2f  max|msg| %.5g\n", where,
+         (size_t)ct->_c0_poly._num_primes, ct->_sf_degree, log2(ct->_scaling_factor), mx);
+  free(m);
+}
+
 API void Init_ciph_down_scale(CIPHER res, CIPHER ciph) {
+  dbg_range("rescale", ciph);
   init_cipher(res, ciph, ciph->_scaling_factor / Get_default_sc(), ciph->_sf_degree - 1);
 }
 API void Init_ciph_same_scale_ciph3(CIPHER res, CIPHER3 ciph) {  // cipher_eval.c:65-75
@@ -912,6 +930,12 @@ API CIPHER Encrypt(CIPHER res, PLAIN plain) {  // cipher_eval.c:406-409
 API CIPHER Bootstrap(CIPHER res, CIPHER ciph, uint32_t level_after_bts) {
   Context* c = ctx();
   if (prof::on) prof::report("emitted");  // device time since the previous bootstrap
+  // ACE_B200_DEBUG_BTS=1 (own keys only): decrypt before and after, print the message range and
+  // how far the refreshed message is from the input -- tells a model whose activations leave the
+  // bootstrap's (-1, 1) input range from a runtime problem
+  static const bool dbg = getenv("ACE_B200_DEBUG_BTS") && getenv("ACE_B200_DEBUG_BTS")[0] == '1';
+  double* before = dbg ? Get_msg(ciph) : nullptr;
+  const uint32_t dbg_slots = ciph->_slots, dbg_level = (uint32_t)ciph->_c0_poly._num_primes;
   StatScope ss(ST_BTS);
   if (ciph->_c0_poly._num_primes_p != 0) die("Bootstrap: extended ciphertext");
   guard([&] {
@@ -937,6 +961,20 @@ API CIPHER Bootstrap(CIPHER res, CIPHER ciph, uint32_t level_after_bts) {
     res->_scaling_factor = out.sf; res->_sf_degree = out.sfd; res->_slots = out.slots;
   });
   if (prof::on) prof::report("bootstrap");
+  if (dbg) {
+    static int call = 0;
+    double* after = Get_msg(res);
+    double mx_in = 0, mx_out = 0, mx_diff = 0;
+    for (uint32_t i = 0; i < dbg_slots; i++) {
+      mx_in = std::max(mx_in, fabs(before[i]));
+      mx_out = std::max(mx_out, fabs(after[i]));
+      mx_diff = std::max(mx_diff, fabs(after[i] - before[i]));
+    }
+    printf("[ace_b200 bts %3d] level %u -> %zu, max|in| %.4g, max|out| %.4g, max|out-in| %.3g\n", call++,
+           dbg_level, (size_t)res->_c0_poly._num_primes, mx_in, mx_out, mx_diff);
+    free(before);
+    free(after);
+  }
   return res;
 }
 

@@ -63,14 +63,14 @@ def read_peaks():
         return 6650.0, "fallback"
 
 
-def weight_file(model):
-    path = "/tmp/ace_b200_%s.msg" % model
+def weight_file(model, amp=0.05):
+    path = "/tmp/ace_b200_%s%s.msg" % (model, "" if amp == 0.05 else "_amp%g" % amp)
     if not os.path.exists(path):
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import make_weights
         ent = [tuple(e) for e in json.load(open(os.path.join(ROOT, "tests", "emitted",
                                                              model + ".entries.json")))]
-        make_weights.write_file(path + ".tmp%d" % os.getpid(), ent, 0.05, 1)
+        make_weights.write_file(path + ".tmp%d" % os.getpid(), ent, amp, 1)
         os.replace(path + ".tmp%d" % os.getpid(), path)
     return path
 

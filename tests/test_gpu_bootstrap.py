@@ -23,6 +23,7 @@ CASES = [
     # ResNet-110's scale (q0 = 2^51, Delta = 2^48: resnet110_cifar10_train.onnx.inc Get_context_params)
     (1024, 17, 192, 512, 2, 3, 1, 51, 48),
     (2048, 18, 192, 256, 2, 3, 1, 51, 48),
+    (65536, 33, 192, 32768, 3, 17, 1, 51, 48),  # ResNet-110's parameter set and a call of its
 ]
 
 
