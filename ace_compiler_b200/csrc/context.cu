@@ -115,6 +115,9 @@ Context::Context(const Params& p, int dev) : params(p), device(dev) {
     n_inv_sh[g] = hm::shoup(n_inv[g], m);
   }
   T.N = N; T.logN = logN; T.G = (u32)G;
+  T.small_moduli = 1;
+  for (size_t g = 0; g < G; g++)
+    if (mod[g] >> 60) T.small_moduli = 0;
   T.mod    = to_device(mods);
   {  // the four twiddle tables in one block (one L2 access-policy window can cover them)
     const size_t per = G * (size_t)N;
@@ -148,7 +151,7 @@ Context::Context(const Params& p, int dev) : params(p), device(dev) {
       u64 hat = 1;
       for (size_t k = 0; k < K; k++)
         if (k != i) hat = hm::mulmod(hat, mod[L + k] % qj, qj);
-      phm[j * K + i] = hat;
+      phm[j * K + i] = hat;  // packed below, once small_moduli is known
       prod           = hm::mulmod(prod, mod[L + i] % qj, qj);
     }
     pinv[j]    = hm::invmod_prime(prod, qj);
@@ -158,6 +161,7 @@ Context::Context(const Params& p, int dev) : params(p), device(dev) {
   }
   phat_inv_      = to_device(phi);
   phat_inv_sh_   = to_device(phi_sh);
+  for (u64& h : phm) h = pack_hat(h);
   phat_mod_q_    = to_device(phm);
   pinv_mod_q_    = to_device(pinv);
   pinv_mod_q_sh_ = to_device(pinv_sh);
@@ -335,7 +339,7 @@ const Context::ModUpTab& Context::modup_tab(u32 num_q, u32 part) {
       u64 hat = 1;
       for (u32 k = 0; k < t.n_in; k++)
         if (k != i) hat = hm::mulmod(hat, mod[t.start + k] % tm, tm);
-      hm_[(size_t)o * t.n_in + i] = hat;
+      hm_[(size_t)o * t.n_in + i] = pack_hat(hat);
     }
   }
   t.hatinv    = to_device(hi);

@@ -178,6 +178,11 @@ class Context {
     std::vector<u16> g_in, g_out, out_slot;
   };
   const ModUpTab&  modup_tab(u32 num_q, u32 part);
+  // conversion-matrix entries as base_conv_kernel reads them (split at bit 30 when every modulus
+  // is below 2^60, see kernels.cu)
+  u64 pack_hat(u64 h) const {
+    return T.small_moduli ? ((h >> 30) << 32) | (h & 0x3FFFFFFFull) : h;
+  }
   void             fill_conv_desc(ConvDesc& d, const ModUpTab& t, const u64* x, u64* out);
 
   std::map<std::pair<u32, u32>, ModUpTab>  modup_tabs_;

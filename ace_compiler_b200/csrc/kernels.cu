@@ -503,15 +503,90 @@ struct ConvDescPack {
   ConvDesc d[kMaxConvPack];
 };
 
+// Sum of products without carries.  When every modulus is below 2^60 (DeviceTables::small_moduli)
+// the conversion matrices are stored split at bit 30 -- word = (h >> 30) << 32 | (h & (2^30-1)),
+// Context::pack_hat -- and the scaled inputs y are split the same way in registers.  The four
+// partial products a_i * b_j are < 2^60, so up to 16 of them add up in a 64-bit register: one MAC is
+// four IMAD.WIDE.U32 with a 64-bit addend and nothing else (the generic mac128 takes ~20
+// instructions).  fold() rebuilds the exact 128-bit sum, so the reduced result is unchanged.
+struct DotAcc30 {
+  u64 s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+  __device__ __forceinline__ void mac(u32 a0, u32 a1, u32 b0, u32 b1) {
+    s00 += (u64)a0 * b0;
+    s01 += (u64)a0 * b1;
+    s10 += (u64)a1 * b0;
+    s11 += (u64)a1 * b1;
+  }
+  // value = s00 + (s01 + s10) * 2^30 + s11 * 2^60
+  __device__ __forceinline__ void fold(u64& lo, u64& hi) const {
+    const u64 mid   = s01 + s10;                       // < 2^65: keep the carry
+    const u64 mid_c = mid < s01 ? 1ull : 0ull;
+    u64 l = s00, h = 0;
+    const u64 m_lo = mid << 30, m_hi = (mid >> 34) | (mid_c << 30);
+    l += m_lo; h += m_hi + (l < m_lo ? 1ull : 0ull);
+    const u64 t_lo = s11 << 60, t_hi = s11 >> 4;
+    l += t_lo; h += t_hi + (l < t_lo ? 1ull : 0ull);
+    lo = l; hi = h;
+  }
+};
+
+template <int NIN>
+__device__ __forceinline__ void base_conv_fast(const DeviceTables& T, const ConvDesc& D,
+                                               const u64* sh_hat, u32 n, u32 o_begin, u32 o_end) {
+  u32 y0[NIN], y1[NIN];
+#pragma unroll
+  for (int i = 0; i < NIN; i++) {
+    const u64 q = T.mod[D.g_in[i]].q;
+    const u64 y = mul_shoup(D.x[(size_t)i * T.N + n], D.hatinv[i], D.hatinv_sh[i], q);
+    y0[i] = (u32)y & 0x3FFFFFFFu;
+    y1[i] = (u32)(y >> 30);
+  }
+  for (u32 o = o_begin; o < o_end; o++) {
+    const Modulus m = T.mod[D.g_out[o]];
+    const uint2*  h = reinterpret_cast<const uint2*>(sh_hat + (o - o_begin) * NIN);
+    DotAcc30 acc;
+#pragma unroll
+    for (int i = 0; i < NIN; i++) {
+      const uint2 w = h[i];
+      acc.mac(y0[i], y1[i], w.x, w.y);
+    }
+    u64 lo, hi;
+    acc.fold(lo, hi);
+    D.out[(size_t)D.out_slot[o] * T.N + n] = reduce128(lo, hi, m);
+  }
+}
+
+// One thread per coefficient and group of kConvOutPerThread output limbs; blockIdx.y =
+// descriptor, blockIdx.z = output group (the scaled inputs are recomputed per group: n_in Shoup
+// products against 8 n_in MACs, and the grid gets enough threads to hide latency).  n_in <= 16 with
+// small moduli takes the exact-size carry-free path above; anything else the generic 128-bit
+// accumulation.
+constexpr u32 kConvOutPerThread = 8;
 template <int MAXIN>
-__global__ void __launch_bounds__(128) base_conv_kernel(DeviceTables T, ConvDescPack P) {
-  extern __shared__ u64 sh_hat[];  // [n_out][n_in]
+__global__ void __launch_bounds__(128) base_conv_kernel(DeviceTables T,
+                                                        const __grid_constant__ ConvDescPack P) {
+  extern __shared__ u64 sh_hat[];  // [outputs of this group][n_in]
   const ConvDesc& D = P.d[blockIdx.y];
-  const u32 n_in = D.n_in, n_out = D.n_out;
-  for (u32 i = threadIdx.x; i < n_in * n_out; i += blockDim.x) sh_hat[i] = D.hatmod[i];
+  const u32 n_in = D.n_in;
+  const u32 o_begin = blockIdx.z * kConvOutPerThread;
+  if (o_begin >= D.n_out) return;
+  const u32 o_end = o_begin + kConvOutPerThread < D.n_out ? o_begin + kConvOutPerThread : D.n_out;
+  const u32 n_out = o_end - o_begin;
+  for (u32 i = threadIdx.x; i < n_in * n_out; i += blockDim.x)
+    sh_hat[i] = D.hatmod[(size_t)o_begin * n_in + i];
   __syncthreads();
   const u32 n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= T.N) return;
+  if (MAXIN <= 16 && T.small_moduli) {
+    switch (n_in) {
+#define ACE_BC_CASE(k) case k: if (k <= MAXIN) base_conv_fast<(k <= MAXIN ? k : 1)>(T, D, sh_hat, n, o_begin, o_end); return;
+      ACE_BC_CASE(1) ACE_BC_CASE(2) ACE_BC_CASE(3) ACE_BC_CASE(4) ACE_BC_CASE(5) ACE_BC_CASE(6)
+      ACE_BC_CASE(7) ACE_BC_CASE(8) ACE_BC_CASE(9) ACE_BC_CASE(10) ACE_BC_CASE(11) ACE_BC_CASE(12)
+      ACE_BC_CASE(13) ACE_BC_CASE(14) ACE_BC_CASE(15) ACE_BC_CASE(16)
+#undef ACE_BC_CASE
+      default: return;
+    }
+  }
   u64 y[MAXIN];
 #pragma unroll
   for (int i = 0; i < MAXIN; i++) {
@@ -520,13 +595,17 @@ __global__ void __launch_bounds__(128) base_conv_kernel(DeviceTables T, ConvDesc
       y[i] = mul_shoup(D.x[(size_t)i * T.N + n], D.hatinv[i], D.hatinv_sh[i], q);
     }
   }
-  for (u32 o = 0; o < n_out; o++) {
+  for (u32 o = o_begin; o < o_end; o++) {
     const Modulus m = T.mod[D.g_out[o]];
-    const u64*    h = sh_hat + o * n_in;
+    const u64*    h = sh_hat + (o - o_begin) * n_in;
     u64 lo = 0, hi = 0;
 #pragma unroll
     for (int i = 0; i < MAXIN; i++) {
-      if (i < (int)n_in) mac128(lo, hi, y[i], h[i]);
+      if (i < (int)n_in) {
+        u64 w = h[i];
+        if (T.small_moduli) w = ((w >> 32) << 30) | (w & 0x3FFFFFFFull);  // stored split
+        mac128(lo, hi, y[i], w);
+      }
     }
     D.out[(size_t)D.out_slot[o] * T.N + n] = reduce128(lo, hi, m);
   }
@@ -537,15 +616,14 @@ void launch_base_conv(const DeviceTables& T, const ConvDesc* descs, u32 n_desc,
   prof::Scope prof_scope_("base_conv", s);
   if (n_desc == 0) return;
   ConvDescPack P;
-  u32 max_in = 0, max_sh = 0;
+  u32 max_in = 0, max_out = 0;
   for (u32 i = 0; i < n_desc; i++) {
     P.d[i] = descs[i];
     if (descs[i].n_in > max_in) max_in = descs[i].n_in;
-    u32 sh = descs[i].n_in * descs[i].n_out;
-    if (sh > max_sh) max_sh = sh;
+    if (descs[i].n_out > max_out) max_out = descs[i].n_out;
   }
-  dim3   grid((T.N + 127) / 128, n_desc);
-  size_t shm = max_sh * sizeof(u64);
+  dim3   grid((T.N + 127) / 128, n_desc, (max_out + kConvOutPerThread - 1) / kConvOutPerThread);
+  size_t shm = (size_t)max_in * kConvOutPerThread * sizeof(u64);
   if (max_in <= 4) {
     base_conv_kernel<4><<<grid, 128, shm, s>>>(T, P);
   } else if (max_in <= 12) {

@@ -26,6 +26,7 @@ struct LimbBatch {
 struct DeviceTables {
   u32            N, logN;
   u32            G;        // L + K
+  u32            small_moduli;  // every modulus < 2^60: deferred-carry dot products are exact
   const Modulus* mod;      // [G]
   const u64*     tw;       // [G][N] psi powers, bit-reversed order   (ntt.c:95-101)
   const u64*     tw_sh;    // [G][N] Shoup companions                 (ntt.c:119-126)
