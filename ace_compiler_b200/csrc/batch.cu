@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) copy_batch_kernel(u32 N, const __grid_con
 // ---------------------------------------------------------------------------- ModUp
 void Context::modup_batch(const ModupJob* jobs, size_t n) {
   if (n == 0) return;
-  if (n == 1) { modup_from(jobs[0].out, jobs[0].digit, jobs[0].num_q, jobs[0].part); return; }
+  if (n == 1 && jobs[0].copy_own) { modup_from(jobs[0].out, jobs[0].digit, jobs[0].num_q, jobs[0].part); return; }
   size_t total_in = 0;
   std::vector<const ModUpTab*> tabs(n);
   for (size_t j = 0; j < n; j++) {
@@ -83,6 +83,7 @@ void Context::modup_batch(const ModupJob* jobs, size_t n) {
     };
     for (size_t j = 0; j < n; j++) {
       const ModUpTab& t = *tabs[j];
+      if (!jobs[j].copy_own) continue;  // the consumer reads the digit's own limbs from the source
       for (u32 i = 0; i < t.n_in; i++) {
         u64* dst = jobs[j].out + (size_t)(t.start + i) * N;
         const u64* src = jobs[j].digit + (size_t)i * N;

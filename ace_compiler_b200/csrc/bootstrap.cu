@@ -465,10 +465,89 @@ void Evaluator::rotate_iteration(Ct& result, BtsPrecom& pc,
 
   u64* first = c->alloc_limbs(W, false);
   u64* outer = c->alloc_limbs(2 * (size_t)W, false);   // (outer0, outer1)
-  u64* inner = c->alloc_limbs(2 * (size_t)W, false);
   u64* tmp   = c->alloc_limbs(2 * (size_t)W, false);
-  u64* red   = c->alloc_limbs(nq, false);
   bool outer0_zero = true;
+  if (baby <= kMaxDotBaby && giant <= kMaxDotGiant) {
+    // ---- batched form.  The baby steps only meet in the final accumulations, so: all inner sums
+    // in one pass over the giant-step rotations, ONE ModDown over every inner.c1, ONE ModUp over
+    // all their digits, then per step the key inner product (its own key) fused with the
+    // automorphism and the accumulation.  Exact ring additions commute, the approximate base
+    // conversions see the same inputs as in the step-by-step form: same limbs.
+    u64* inner_all = c->alloc_limbs((size_t)(baby > 1 ? baby - 1 : 1) * 2 * W, false);
+    DotAllArgs da;
+    da.rot = rot; da.rot_stride = 2 * WN; da.c1_offset = WN;
+    da.b = (u32)baby; da.g = (u32)giant; da.pt_pstart = pt_level;
+    for (int32_t i = 0; i < baby; i++) {
+      u32 used = 0;
+      for (int32_t j = 0; j < giant; j++) {
+        const u64* pt = (giant * i + j == num_rot) ? nullptr : tab[step][giant * i + j];
+        if (giant * i + j != num_rot && !pt) throw std::runtime_error("bootstrap: missing diagonal plaintext");
+        da.pt[i * giant + j] = pt;
+        used += pt ? 1 : 0;
+      }
+      // first = inner_0.c0, outer = (0, inner_0.c1)
+      da.out0[i] = i == 0 ? first : inner_all + (size_t)(i - 1) * 2 * WN;
+      da.out1[i] = i == 0 ? outer + WN : inner_all + (size_t)(i - 1) * 2 * WN + WN;
+      c->tr(Context::TR_LIMB_MUL, 0, 2ull * used * W);
+      c->tr(Context::TR_LIMB_ADD, 0, 2ull * (used - 1) * W);
+    }
+    launch_pt_dot_all(c->T, da, ext_b, c->stream);
+    c->launches++;
+    std::vector<int32_t> sw;  // baby steps that need a key switch
+    for (int32_t i = 1; i < baby; i++) {
+      u64* inner = inner_all + (size_t)(i - 1) * 2 * WN;
+      if (rout[step][i] != 0) {
+        sw.push_back(i);
+      } else {
+        launch_ew_basis(c->T, EW_ADD, first, first, inner, ext_b, c->stream);
+        launch_ew_basis(c->T, EW_ADD, outer + WN, outer + WN, inner + WN, ext_b, c->stream);
+        c->tr(Context::TR_LIMB_ADD, 0, 2 * W);
+        c->launches += 2;
+      }
+    }
+    if (!sw.empty()) {
+      const size_t ns = sw.size();
+      u64* red_all = c->alloc_limbs(ns * nq, false);
+      u64* ext_all = c->alloc_limbs(ns * (size_t)beta * W, false);
+      std::vector<ModdownJob> md(ns);
+      std::vector<ModupJob>   mu;
+      for (size_t k = 0; k < ns; k++) {
+        u64* inner = inner_all + (size_t)(sw[k] - 1) * 2 * WN;
+        u64* red   = red_all + k * (size_t)nq * N;
+        md[k] = ModdownJob{red, inner + WN, nq};
+        for (u32 j = 0; j < beta; j++)
+          mu.push_back(ModupJob{ext_all + (k * beta + j) * WN, red + (size_t)c->digit_start(j) * N, nq, j,
+                                false});
+      }
+      c->moddown_batch(md.data(), ns);
+      c->modup_batch(mu.data(), mu.size());
+      for (size_t k = 0; k < ns; k++) {
+        const int32_t val = rout[step][sw[k]];
+        u64* inner = inner_all + (size_t)(sw[k] - 1) * 2 * WN;
+        const int64_t* order = c->auto_order(c->auto_index(val));
+        const int64_t* inv   = c->auto_order_inv(c->auto_index(val));
+        launch_gather_add_basis(c->T, first, inner, order, ext_b, c->stream);  // first += rot(inner.c0)
+        const SwitchKey& key = rot_key(val);
+        if (!key.k0 || !key.k1) throw std::runtime_error("switch key not loaded");
+        launch_ksw_inner_rot(c->T, outer, outer + WN, ext_all + k * beta * WN, red_all + k * (size_t)nq * N,
+                             (u32)c->part_size, key.k0, key.k1, beta, nq, (u32)c->L, K, nullptr, nullptr,
+                             nullptr, inv, !outer0_zero, true, c->stream);
+        outer0_zero = false;
+        const uint64_t n = 2ull * beta * W;  // what ksw_acc counts
+        c->tr(Context::TR_LIMB_MUL, 0, n);
+        c->tr(Context::TR_LIMB_ADD, 0, n);
+        c->tr(Context::TR_LIMB_ROT, 0, 3 * W);
+        c->tr(Context::TR_LIMB_ADD, 0, 3 * W);
+        c->launches += 2;
+      }
+      c->free_limbs(red_all);
+      c->free_limbs(ext_all);
+    }
+    c->free_limbs(inner_all);
+  } else {
+  // ---- step-by-step form (more baby or giant steps than the batched kernel holds)
+  u64* inner = c->alloc_limbs(2 * (size_t)W, false);
+  u64* red   = c->alloc_limbs(nq, false);
   for (int32_t i = 0; i < baby; i++) {
     const int32_t gbase = giant * i;
     DotArgs da;
@@ -520,6 +599,9 @@ void Evaluator::rotate_iteration(Ct& result, BtsPrecom& pc,
       c->launches += 2;
     }
   }
+  c->free_limbs(inner);
+  c->free_limbs(red);
+  }
   // outer.c0 += first; ModDown both
   if (outer0_zero) {
     ACE_CUDA(cudaMemcpyAsync(outer, first, WN * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
@@ -533,7 +615,7 @@ void Evaluator::rotate_iteration(Ct& result, BtsPrecom& pc,
   const double delta = (double)((u64)1 << c->params.scaling_mod_size);
   result.sf  = result.sf * pow(delta, 1);  // Mul_plaintext: sf * plain sf, degree + 1
   result.sfd = result.sfd + 1;
-  for (u64* p : {ext, rot, acc, first, outer, inner, tmp, red}) c->free_limbs(p);
+  for (u64* p : {ext, rot, acc, first, outer, tmp}) c->free_limbs(p);
 }
 
 void Evaluator::coeff_slots_transform(Ct& result, Ct& in, BtsPrecom& pc, bool encoding) {

@@ -91,6 +91,8 @@ Context::Context(const Params& p, int dev) : params(p), device(dev) {
     M.shift   = nbits - 2;
     M.mu64    = (u64)((((u128)1) << (62 + nbits)) / m);
     M.pad     = 0;
+    M.c64     = (u64)((((u128)1) << 64) % m);
+    M.c64_sh  = hm::shoup(M.c64, m);
     // psi = g^((q-1)/2N) with g the smallest generator (number_theory.c:132-157)
     // ... unless the reference's fixed-root table has an entry (fhe_std_parms.c:200-271)
     psi[g] = fixed_root(2 * (u64)N, m);

@@ -44,7 +44,7 @@ struct SwitchKey {
 // (Decomp_modup / Mod_down / Rescale / Encode_plain_from_float) asks for.  The scheduler
 // (sched.h) collects independent calls and hands them over together, so that each step of the
 // primitive is one launch over the limbs of all of them.
-struct ModupJob   { u64* out; const u64* digit; u32 num_q, part; };  // digit: the part's own limbs
+struct ModupJob   { u64* out; const u64* digit; u32 num_q, part; bool copy_own = true; };  // digit: the part's own limbs
 struct ModdownJob { u64* out; const u64* in; u32 num_q; };            // in: [num_q | K]
 struct RescaleJob { u64* out; const u64* in; u32 num_q; };
 struct EncodeJob  { u64* out; const void* src; int kind; u32 len, level, slots, sf_degree, p_cnt; };

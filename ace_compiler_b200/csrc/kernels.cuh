@@ -209,4 +209,17 @@ void launch_ksw_inner_rot(const DeviceTables& T, u64* out0, u64* out1, const u64
 void launch_gather_add_basis(const DeviceTables& T, u64* r, const u64* a, const int64_t* order,
                              Basis bs, cudaStream_t s);
 
+// all baby-step plaintext inner products of one BSGS level (see kernels_ext.cu):
+// rotation j = (rot + j*rot_stride, rot + j*rot_stride + c1_offset); pt[i*g + j] may be null
+constexpr int kMaxDotBaby = 8, kMaxDotGiant = 16;
+struct DotAllArgs {
+  const u64* rot;
+  size_t     rot_stride, c1_offset;
+  const u64* pt[kMaxDotBaby * kMaxDotGiant];
+  u64*       out0[kMaxDotBaby];
+  u64*       out1[kMaxDotBaby];
+  u32        b, g, pt_pstart;
+};
+void launch_pt_dot_all(const DeviceTables& T, const DotAllArgs& args, Basis bs, cudaStream_t s);
+
 }  // namespace ace

@@ -236,4 +236,52 @@ void launch_gather_add_basis(const DeviceTables& T, u64* r, const u64* a, const 
   gather_add_basis_kernel<<<grid_for(T, bs.width()), 256, 0, s>>>(T, r, a, order, bs);
 }
 
+// All baby-step inner sums of one BSGS level in one pass over the giant-step rotations:
+//   out_i = sum_j rot_j (.) pt[i*g + j]        i < b, j < g  (null plaintext = term absent)
+// Each rotation limb is read once instead of b times; the sums are the same exact 128-bit
+// accumulations as pt_dot_kernel's, so the results are identical.
+template <int B>
+__global__ void __launch_bounds__(256) pt_dot_all_kernel(DeviceTables T,
+                                                         const __grid_constant__ DotAllArgs A,
+                                                         Basis bs) {
+  const u32     y    = blockIdx.y;
+  const Modulus m    = T.mod[bs.g(y)];
+  const size_t  off  = (size_t)y * T.N;
+  const size_t  poff = (size_t)(y < bs.nq ? y : A.pt_pstart + (y - bs.nq)) * T.N;
+  const u32     n    = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= T.N) return;
+  u64 lo0[B], hi0[B], lo1[B], hi1[B];
+#pragma unroll
+  for (int i = 0; i < B; i++) lo0[i] = hi0[i] = lo1[i] = hi1[i] = 0;
+  for (u32 j = 0; j < A.g; j++) {
+    const u64 x0 = A.rot[(size_t)j * A.rot_stride + off + n];
+    const u64 x1 = A.rot[(size_t)j * A.rot_stride + A.c1_offset + off + n];
+#pragma unroll
+    for (int i = 0; i < B; i++) {
+      if (i < (int)A.b) {
+        const u64* pt = A.pt[i * A.g + j];
+        if (pt != nullptr) {
+          const u64 p = pt[poff + n];
+          mac128(lo0[i], hi0[i], x0, p);
+          mac128(lo1[i], hi1[i], x1, p);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < B; i++) {
+    if (i < (int)A.b) {
+      A.out0[i][off + n] = reduce128(lo0[i], hi0[i], m);
+      A.out1[i][off + n] = reduce128(lo1[i], hi1[i], m);
+    }
+  }
+}
+
+void launch_pt_dot_all(const DeviceTables& T, const DotAllArgs& args, Basis bs, cudaStream_t s) {
+  prof::Scope prof_scope_("pt_dot_all", s);
+  if (bs.width() == 0 || args.b == 0 || args.g == 0) return;
+  if (args.b <= 4) pt_dot_all_kernel<4><<<grid_for(T, bs.width()), 256, 0, s>>>(T, args, bs);
+  else pt_dot_all_kernel<kMaxDotBaby><<<grid_for(T, bs.width()), 256, 0, s>>>(T, args, bs);
+}
+
 }  // namespace ace

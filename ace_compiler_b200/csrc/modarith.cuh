@@ -30,6 +30,8 @@ struct Modulus {
   u64 mu64;    // floor(2^(62+nbits) / q): single-word Barrett ratio for products a*b, a,b<q
   u32 shift;   // nbits - 2, nbits = bit length of q
   u32 pad;
+  u64 c64;     // 2^64 mod q
+  u64 c64_sh;  // its Shoup companion floor(c64 * 2^64 / q)
 };
 
 ACE_HD u64 add_mod(u64 a, u64 b, u64 q) {
@@ -68,21 +70,17 @@ ACE_HD u64 mul_mod(u64 a, u64 b, const Modulus& m) {
   return r >= m.q ? r - m.q : r;
 }
 
-// 128-bit value (hi:lo) mod q, two-word Barrett with mu = floor(2^128/q).
+// 128-bit value (hi:lo) mod q:  hi * 2^64 + lo = hi * c64 + lo (mod q).  The first term is one
+// Shoup product (exact for any hi < 2^64), the second a one-word Barrett step with
+// mu_hi = floor(2^64 / q) (quotient estimate short by at most 1).  Canonical result, i.e. the same
+// value as the reference's Mod_barrett_128 (fhe_utils.h:241-280), with 2 high + 3 low products
+// instead of 5 + 4.
 ACE_HD u64 reduce128(u64 lo, u64 hi, const Modulus& m) {
-  u64 left_h = mul_hi64(lo, m.mu_lo);
-  u64 mid_lo = lo * m.mu_hi;
-  u64 mid_hi = mul_hi64(lo, m.mu_hi);
-  u64 tmp1   = mid_lo + left_h;
-  u64 tmp2   = mid_hi + (tmp1 < left_h ? 1 : 0);
-  mid_lo     = hi * m.mu_lo;
-  mid_hi     = mul_hi64(hi, m.mu_lo);
-  u64 carry  = (mid_lo + tmp1) < tmp1 ? 1 : 0;
-  u64 qh     = hi * m.mu_hi + tmp2 + mid_hi + carry;
-  u64 r      = lo - qh * m.q;
-  r          = r >= 2 * m.q ? r - 2 * m.q : r;
-  r          = r >= m.q ? r - m.q : r;
-  return r >= m.q ? r - m.q : r;
+  const u64 r1 = mul_shoup(hi, m.c64, m.c64_sh, m.q);
+  const u64 qh = mul_hi64(lo, m.mu_hi);
+  u64 r0 = lo - qh * m.q;
+  r0     = r0 >= m.q ? r0 - m.q : r0;
+  return add_mod(r0, r1, m.q);
 }
 
 // 128-bit multiply-accumulate: (hi:lo) += a * b

@@ -525,7 +525,7 @@ void Scheduler::flush() {
       switch (o.kind) {
         case OP_GATHER:  gather_idx.push_back(sorted[s]); break;
         case OP_ENCODE:  enc.push_back(enc_jobs_[o.p0]); break;
-        case OP_MODUP:   mu.push_back(ModupJob{o.r, o.a, o.p0, o.p1}); break;
+        case OP_MODUP:   mu.push_back(ModupJob{o.r, o.a, o.p0, o.p1, true}); break;
         case OP_MODDOWN: md.push_back(ModdownJob{o.r, o.a, o.p0}); break;
         case OP_RESCALE: rs.push_back(RescaleJob{o.r, o.a, o.p0}); break;
         default:         chain_idx.push_back(sorted[s]); break;
