@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libace_b200.so")
 SOURCES = ["kernels.cu", "kernels_ext.cu", "context.cu", "client.cu", "evaluator.cu",
-           "chebyshev.cu", "bootstrap.cu", "sched.cu", "batch.cu", "prof.cu", "capi.cu", "rt_shim.cu"]
+           "chebyshev.cu", "bootstrap.cu", "sched.cu", "sched_selftest.cu", "batch.cu", "prof.cu", "capi.cu", "rt_shim.cu"]
 
 
 def needs_build():

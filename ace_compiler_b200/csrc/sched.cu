@@ -2,6 +2,8 @@
 #include "sched.h"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "prof.h"
@@ -55,13 +57,46 @@ static inline u32 hash_addr(const u64* p) {
   return (u32)((((uint64_t)(uintptr_t)p) >> 9) * 0x9E3779B97F4A7C15ull >> 32);
 }
 
-Scheduler::Scheduler(Context* c) : c_(c) {
+// ---------------------------------------------------------------------------- product backend
+namespace {
+struct ContextBackend : SchedBackend {
+  Context* c;
+  explicit ContextBackend(Context* ctx) : c(ctx) {}
+  u32    N() const override { return c->N; }
+  u32    K() const override { return (u32)c->K; }
+  u32    digit_start(u32 part) const override { return c->digit_start(part); }
+  u32    digit_len(u32 num_q, u32 part) const override { return c->digit_len(num_q, part); }
+  u64*   alloc(size_t n) override { return c->alloc_limbs(n, false); }
+  void   free(u64* p) override { c->free_limbs(p); }
+  size_t block_limbs(const u64* p) const override { return c->block_limbs(p); }
+  void   count_limb_op(int kind) override {
+    c->tr(kind == 0 ? Context::TR_LIMB_MUL : kind == 1 ? Context::TR_LIMB_ADD : Context::TR_LIMB_ROT, 0);
+  }
+  void run_chains(const ChainPack& pack, u32 n_chains) override {
+    prof::Scope ps("ew_chain", c->stream);
+    ew_chain_kernel<<<dim3((c->N + 255) / 256, n_chains), 256, 0, c->stream>>>(c->T, pack);
+    c->launches++;
+  }
+  void run_gathers(const ChainPack& pack, u32 n) override {
+    prof::Scope ps("gather_batch", c->stream);
+    gather_batch_kernel<<<dim3((c->N + 255) / 256, n), 256, 0, c->stream>>>(c->T, pack);
+    c->launches++;
+  }
+  void run_encode(const EncodeJob* j, size_t n) override { c->encode_batch(j, n); }
+  void run_modup(const ModupJob* j, size_t n) override { c->modup_batch(j, n); }
+  void run_moddown(const ModdownJob* j, size_t n) override { c->moddown_batch(j, n); }
+  void run_rescale(const RescaleJob* j, size_t n) override { c->rescale_batch(j, n); }
+};
+}  // namespace
+SchedBackend* make_context_backend(Context* c) { return new ContextBackend(c); }
+
+Scheduler::Scheduler(SchedBackend* backend) : c_(backend) {
   table_.resize(1u << 16);
   memset(table_.data(), 0, table_.size() * sizeof(Limb));
   mask_ = (u32)table_.size() - 1;
   ops_.reserve(1 << 16);
 }
-Scheduler::~Scheduler() {}
+Scheduler::~Scheduler() { delete c_; }
 
 void Scheduler::grow() {
   std::vector<Limb> old;
@@ -142,7 +177,7 @@ void Scheduler::kill_if_unread(Limb& l) {
     o.r = o.t;
     o.t_live = 0;
     Limb& lt = limb(o.t);  // exists already
-    lt.w_is_t = 0;
+    if (lt.w_op == l.w_op) lt.w_is_t = 0;  // unless a later op has written t since
   } else if (o.kind != OP_NOP) {
     o.kind = OP_NOP;
   }
@@ -156,7 +191,7 @@ void Scheduler::maybe_flush() {
 
 // ---------------------------------------------------------------------------- recording
 u64* Scheduler::alloc(size_t n_limbs, bool zeroed) {
-  u64* p = c_->alloc_limbs(n_limbs, false);
+  u64* p = c_->alloc(n_limbs);
   if (zeroed) zero(p, n_limbs);
   return p;
 }
@@ -165,7 +200,7 @@ void Scheduler::free(u64* block) {
   if (!block) return;
   const size_t n = c_->block_limbs(block);
   for (size_t i = 0; i < n; i++) {
-    const u64* a = block + i * c_->N;
+    const u64* a = block + i * c_->N();
     u32 h = hash_addr(a) & mask_;
     while (table_[h].gen == gen_) {
       if (table_[h].addr == (u64)(uintptr_t)a) { kill_if_unread(table_[h]); break; }
@@ -173,14 +208,14 @@ void Scheduler::free(u64* block) {
     }
   }
   frees_.push_back(block);
-  pending_free_bytes_ += n * c_->N * sizeof(u64);
+  pending_free_bytes_ += n * c_->N() * sizeof(u64);
   maybe_flush();
 }
 
 void Scheduler::zero(u64* r, size_t n_limbs) {
   if (live_ + n_limbs + 8 > table_.size() / 2) grow();
   for (size_t i = 0; i < n_limbs; i++) {
-    u64* p = r + i * c_->N;
+    u64* p = r + i * c_->N();
     Limb& l = limb(p);
     kill_if_unread(l);
     const u32 wave = dep_write(l, false);
@@ -211,8 +246,8 @@ void Scheduler::fill(u64* r, u64 value) {
 
 void Scheduler::copy(u64* r, const u64* a, size_t n_limbs) {
   for (size_t i = 0; i < n_limbs; i++) {
-    u64* rp = r + i * c_->N;
-    const u64* ap = a + i * c_->N;
+    u64* rp = r + i * c_->N();
+    const u64* ap = a + i * c_->N();
     if (rp == ap) continue;
     if (live_ + 8 > table_.size() / 2) grow();
     Limb& la = limb(ap);
@@ -234,7 +269,7 @@ void Scheduler::copy(u64* r, const u64* a, size_t n_limbs) {
 
 void Scheduler::ew(SchedOp op, u64* r, const u64* a, const u64* b, u32 g) {
   if (live_ + 8 > table_.size() / 2) grow();
-  c_->tr(op == OP_MUL ? Context::TR_LIMB_MUL : Context::TR_LIMB_ADD, 0);
+  c_->count_limb_op(op == OP_MUL ? 0 : 1);
   n_ops++;
   const bool za = limb(a).is_zero, zb = limb(b).is_zero;
   // ---- operands known to be zero: the op degenerates (0 + y = y, x * 0 = 0, x - 0 = x)
@@ -246,7 +281,7 @@ void Scheduler::ew(SchedOp op, u64* r, const u64* a, const u64* b, u32 g) {
   // ---- Hw_modmul(tmp, x, y) directly followed by Hw_modadd(r, acc, tmp): one multiply-add
   if (op == OP_ADD && !ops_.empty()) {
     Op& m = ops_.back();
-    if (m.kind == OP_MUL && m.r != r && ((b == m.r) != (a == m.r))) {
+    if (m.kind == OP_MUL && m.g == (uint16_t)g && m.r != r && ((b == m.r) != (a == m.r))) {
       const u64* acc = (b == m.r) ? a : b;
       u64*       tmp = m.r;
       Limb& lt = limb(tmp);
@@ -302,7 +337,7 @@ void Scheduler::ew(SchedOp op, u64* r, const u64* a, const u64* b, u32 g) {
 
 void Scheduler::gather(u64* r, const u64* a, const int64_t* order, u32 g) {
   if (live_ + 8 > table_.size() / 2) grow();
-  c_->tr(Context::TR_LIMB_ROT, 0);
+  c_->count_limb_op(2);
   n_ops++;
   if (r == a) throw std::runtime_error("Hw_rotate in place is not supported");
   Limb& la = limb(a);
@@ -327,11 +362,11 @@ void Scheduler::encode(const EncodeJob& j) {
   if (live_ + nw + 8 > table_.size() / 2) grow();
   u32 wave = 0;
   for (size_t i = 0; i < nw; i++) {
-    Limb& l = limb(j.out + limb_off(c_->N, i));
+    Limb& l = limb(j.out + limb_off(c_->N(), i));
     kill_if_unread(l);
     wave = std::max(wave, dep_write(l, true));
   }
-  for (size_t i = 0; i < nw; i++) note_write(limb(j.out + limb_off(c_->N, i)), wave, true, -1, false);
+  for (size_t i = 0; i < nw; i++) note_write(limb(j.out + limb_off(c_->N(), i)), wave, true, -1, false);
   Op o{};
   o.kind = OP_ENCODE; o.wave = wave; o.p0 = (u32)enc_jobs_.size();
   enc_jobs_.push_back(j);
@@ -341,7 +376,7 @@ void Scheduler::encode(const EncodeJob& j) {
 }
 
 void Scheduler::modup(u64* out, const u64* in, u32 num_q, u32 part) {
-  const u32 N = c_->N, W = num_q + (u32)c_->K;
+  const u32 N = c_->N(), W = num_q + (u32)c_->K();
   const u32 st = c_->digit_start(part), len = c_->digit_len(num_q, part);
   if (live_ + W + len + 8 > table_.size() / 2) grow();
   u32 wave = 0;
@@ -361,7 +396,7 @@ void Scheduler::modup(u64* out, const u64* in, u32 num_q, u32 part) {
 }
 
 void Scheduler::moddown(u64* out, const u64* in, u32 num_q) {
-  const u32 N = c_->N, W = num_q + (u32)c_->K;
+  const u32 N = c_->N(), W = num_q + (u32)c_->K();
   if (live_ + W + num_q + 8 > table_.size() / 2) grow();
   u32 wave = 0;
   for (u32 i = 0; i < W; i++) wave = std::max(wave, dep_read(limb(in + limb_off(N, i)), true));
@@ -380,7 +415,7 @@ void Scheduler::moddown(u64* out, const u64* in, u32 num_q) {
 }
 
 void Scheduler::rescale(u64* out, const u64* in, u32 num_q) {
-  const u32 N = c_->N;
+  const u32 N = c_->N();
   if (num_q < 2) throw std::runtime_error("Rescale: level not enough");
   if (live_ + 2 * num_q + 8 > table_.size() / 2) grow();
   u32 wave = 0;
@@ -466,9 +501,7 @@ void Scheduler::run_chains(std::vector<u32>& idx) {
     if (items == 0) return;
     pack.chain_start[chains] = (uint16_t)items;
     pack.n_chains = chains;
-    prof::Scope ps("ew_chain", c_->stream);
-    ew_chain_kernel<<<dim3((c_->N + 255) / 256, chains), 256, 0, c_->stream>>>(c_->T, pack);
-    c_->launches++;
+    c_->run_chains(pack, chains);
     n_chain_launches++;
     items = chains = 0;
   };
@@ -495,7 +528,7 @@ void Scheduler::run_chains(std::vector<u32>& idx) {
 
 void Scheduler::flush() {
   if (ops_.empty()) {
-    for (u64* p : frees_) c_->free_limbs(p);
+    for (u64* p : frees_) c_->free(p);
     frees_.clear();
     pending_free_bytes_ = 0;
     return;
@@ -510,6 +543,14 @@ void Scheduler::flush() {
   std::vector<u32> sorted(start[max_wave + 1]), pos(start.begin(), start.end() - 1);
   for (u32 i = 0; i < ops_.size(); i++)
     if (ops_[i].kind != OP_NOP) sorted[pos[ops_[i].wave]++] = i;
+  if (getenv("ACE_SCHED_DUMP")) {
+    for (u32 w = 0; w <= max_wave; w++)
+      for (u32 s2 = start[w]; s2 < start[w + 1]; s2++) {
+        const Op& o = ops_[sorted[s2]];
+        fprintf(stderr, "  wave %u op#%u kind %d r=%p a=%p b=%p c=%p t=%p tl=%d\n", w, sorted[s2], (int)o.kind,
+                (void*)o.r, (void*)o.a, (void*)o.b, (void*)o.c, (void*)o.t, (int)o.t_live);
+      }
+  }
   std::vector<u32>        chain_idx, gather_idx;
   std::vector<EncodeJob>  enc;
   std::vector<ModupJob>   mu;
@@ -540,18 +581,16 @@ void Scheduler::flush() {
         it.r = o.r; it.a = o.a; it.b = o.b; it.c = nullptr; it.t = nullptr; it.g = o.g; it.op = OP_GATHER;
       }
       gpack.n_chains = cnt;
-      prof::Scope ps("gather_batch", c_->stream);
-      gather_batch_kernel<<<dim3((c_->N + 255) / 256, cnt), 256, 0, c_->stream>>>(c_->T, gpack);
-      c_->launches++;
+      c_->run_gathers(gpack, cnt);
     }
-    if (!enc.empty()) c_->encode_batch(enc.data(), enc.size());
-    if (!mu.empty()) c_->modup_batch(mu.data(), mu.size());
-    if (!md.empty()) c_->moddown_batch(md.data(), md.size());
-    if (!rs.empty()) c_->rescale_batch(rs.data(), rs.size());
+    if (!enc.empty()) c_->run_encode(enc.data(), enc.size());
+    if (!mu.empty()) c_->run_modup(mu.data(), mu.size());
+    if (!md.empty()) c_->run_moddown(md.data(), md.size());
+    if (!rs.empty()) c_->run_rescale(rs.data(), rs.size());
   }
   ops_.clear();
   enc_jobs_.clear();
-  for (u64* p : frees_) c_->free_limbs(p);
+  for (u64* p : frees_) c_->free(p);
   frees_.clear();
   pending_free_bytes_ = 0;
   gen_++;

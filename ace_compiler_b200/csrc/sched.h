@@ -57,9 +57,33 @@ struct ChainPack {
   u32       n_chains;
 };
 
+// What the scheduler needs from the machine underneath: limb memory and the batched primitives.
+// ContextBackend (sched.cu) is the product -- everything runs on the B200 through Context;
+// HostSimBackend (sched_selftest.cu) interprets the same batches on host arrays with toy
+// arithmetic so that the dependency logic can be tested without a GPU (tests/test_cpu_sched.py).
+struct SchedBackend {
+  virtual ~SchedBackend() {}
+  virtual u32    N() const = 0;
+  virtual u32    K() const = 0;
+  virtual u32    digit_start(u32 part) const = 0;
+  virtual u32    digit_len(u32 num_q, u32 part) const = 0;
+  virtual u64*   alloc(size_t n_limbs) = 0;
+  virtual void   free(u64* block) = 0;
+  virtual size_t block_limbs(const u64* block) const = 0;
+  virtual void   count_limb_op(int kind) = 0;  // 0 mul, 1 add, 2 rotate (op trace)
+  virtual void   run_chains(const ChainPack& pack, u32 n_chains) = 0;
+  virtual void   run_gathers(const ChainPack& pack, u32 n) = 0;
+  virtual void   run_encode(const EncodeJob* jobs, size_t n) = 0;
+  virtual void   run_modup(const ModupJob* jobs, size_t n) = 0;
+  virtual void   run_moddown(const ModdownJob* jobs, size_t n) = 0;
+  virtual void   run_rescale(const RescaleJob* jobs, size_t n) = 0;
+};
+SchedBackend* make_context_backend(Context* c);
+
 class Scheduler {
  public:
-  explicit Scheduler(Context* c);
+  explicit Scheduler(SchedBackend* backend);  // takes ownership
+  explicit Scheduler(Context* c) : Scheduler(make_context_backend(c)) {}
   ~Scheduler();
 
   // ---- recording (what rt_shim.cu calls)
@@ -103,7 +127,7 @@ class Scheduler {
     u32      r_wave_chain, r_wave_heavy;
     uint8_t  has_w, w_heavy, has_r_chain, has_r_heavy, read_since, is_zero, w_is_t;
   };
-  Context*            c_;
+  SchedBackend*       c_;
   std::vector<Op>     ops_;
   std::vector<EncodeJob> enc_jobs_;
   std::vector<u64*>   frees_;
