@@ -50,6 +50,29 @@ def test_resnet20_bit_exact():
     _run("exact", timeout=3000)
 
 
+def test_resnet110_bit_exact():
+    """same protocol for the deepest checked-in model (109 bootstraps, Delta = 2^48) when its
+    golden run exists (tests/golden/resnet110_cifar10_train.json: ~3 h of reference CPU time,
+    tests/golden/make_model_golden.py).  With synthetic weights the activations of this model
+    leave the bootstrap's input range, i.e. the ciphertext contents are
+    chaotic -- which makes limb-for-limb equality with the reference a sharp test of every
+    primitive at this parameter set."""
+    model = "resnet110_cifar10_train"
+    flag = os.environ.get("ACE_MODEL_PARITY")
+    if not os.path.exists(os.path.join(HERE, "golden", model + ".json")):
+        pytest.skip("no golden run for " + model)
+    if flag == "0" or (flag != "1" and not _enough_ram()):
+        pytest.skip("needs ~45 GB of host RAM for the reference's keys (ACE_MODEL_PARITY=1 forces it)")
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", model + "_ref.so")) or \
+            not os.path.exists(os.path.join(ROOT, "ace_compiler_b200", "models", "lib%s.so" % model)):
+        pytest.skip("model units not built (need the reference tree at build time)")
+    r = subprocess.run([sys.executable, os.path.join(HERE, "model_case.py"), model, "exact"],
+                       capture_output=True, text=True, timeout=3000)
+    sys.stdout.write(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + "\n" + r.stderr[-4000:]
+    assert "MODEL PARITY OK" in r.stdout
+
+
 def _driver_logits(env_extra, model=MODEL, n_classes=10):
     exe = os.path.join(ROOT, "tests", "_emitted_bin", model)
     if not os.path.exists(exe):
