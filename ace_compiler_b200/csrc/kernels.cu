@@ -49,13 +49,26 @@ __device__ __forceinline__ bool batch_has_src(const LimbPtrBatch&) { return true
 // the stored result is the same canonical residue the reference produces (ntt.c:206-263).
 __device__ __forceinline__ u64 csub(u64 a, u64 m) { return a >= m ? a - m : a; }
 
-// forward: (u, v) -> (u + w v, u - w v); in/out in [0, 4q)
+// forward: (u, v) -> (u + w v, u - w v); in/out in [0, 4q).
+// LAZY (moduli of at most 55 bits): the conditional subtraction is skipped altogether -- u grows
+// by at most 6q per stage (see mulhi_short), 16 stages keep every value below 98 q < 2^62 for the
+// <= 55-bit moduli this is used for, the Shoup product takes any 64-bit input -- and the final
+// normalisation is one Barrett step (normalize_any).
+// floor(x * w / 2^64) short by at most 2: the product of the two low halves and the low halves of
+// the cross products are left out (3 wide multiplies instead of 4)
+__device__ __forceinline__ u64 mulhi_short(u64 x, u64 w) {
+  const u32 x0 = (u32)x, x1 = (u32)(x >> 32), w0 = (u32)w, w1 = (u32)(w >> 32);
+  const u64 m1 = (u64)x1 * w0, m2 = (u64)x0 * w1;
+  return (u64)x1 * w1 + (m1 >> 32) + (m2 >> 32);
+}
+template <bool LAZY = false>
 __device__ __forceinline__ void ct_butterfly(u64& u, u64& v, u64 w, u64 wsh, u64 q) {
   const u64 q2 = 2 * q;
-  u64 a = csub(u, q2);
-  u64 t = mul_shoup_lazy(v, w, wsh, q);
+  u64 a = LAZY ? u : csub(u, q2);
+  // LAZY: the quotient estimate may be short by 3 in all, t < 5q; the bounds have room for it
+  u64 t = LAZY ? v * w - mulhi_short(v, wsh) * q : mul_shoup_lazy(v, w, wsh, q);
   u     = a + t;
-  v     = a - t + q2;
+  v     = a - t + (LAZY ? 3 * q2 : q2);  // t < 5q in the lazy form
 }
 // inverse: (u, v) -> (u + v, (u - v) w); in/out in [0, 2q)
 __device__ __forceinline__ void gs_butterfly(u64& u, u64& v, u64 w, u64 wsh, u64 q) {
@@ -65,6 +78,11 @@ __device__ __forceinline__ void gs_butterfly(u64& u, u64& v, u64 w, u64 wsh, u64
   v     = mul_shoup_lazy(d, w, wsh, q);
 }
 __device__ __forceinline__ u64 normalize4(u64 a, u64 q) { return csub(csub(a, 2 * q), q); }
+// any a < 2^64: a mod q with mu = floor(2^64 / q) (quotient estimate short by at most 1)
+__device__ __forceinline__ u64 normalize_any(u64 a, u64 q, u64 mu) {
+  return csub(a - __umul64hi(a, mu) * q, q);
+}
+__device__ __forceinline__ bool lazy_modulus(const Modulus& m) { return m.shift <= 53; }  // <= 55 bits
 
 // ---- strided phase, forward: stages 0 .. SA-1, R = 2^SA rows at stride N/R -------------
 template <int SA, class B>
@@ -83,6 +101,7 @@ __global__ void __launch_bounds__(128) ntt_fwd_strided(DeviceTables T, const __g
   u64 x[R];
 #pragma unroll
   for (int r = 0; r < R; r++) x[r] = in[(size_t)r * stride + col];
+  const bool lazy = lazy_modulus(T.mod[g]);  // uniform per block
 #pragma unroll
   for (int s = 0; s < SA; s++) {
     const int m  = 1 << s;
@@ -91,7 +110,8 @@ __global__ void __launch_bounds__(128) ntt_fwd_strided(DeviceTables T, const __g
     for (int p = 0; p < R / 2; p++) {
       const int i  = p / tr;
       const int lo = i * 2 * tr + (p % tr);
-      ct_butterfly(x[lo], x[lo + tr], tw[m + i], twsh[m + i], q);
+      if (lazy) ct_butterfly<true>(x[lo], x[lo + tr], tw[m + i], twsh[m + i], q);
+      else ct_butterfly<false>(x[lo], x[lo + tr], tw[m + i], twsh[m + i], q);
     }
   }
 #pragma unroll
@@ -205,8 +225,11 @@ __global__ void __launch_bounds__(kNttThreads) ntt_inv_tile(DeviceTables T, cons
 
 // ---- tile phase for N >= 4096, register radix-8 version ---------------------------------
 // 512 threads x 8 elements = one 4096-element tile.  The 12 stages run as 4 passes of three
-// radix-2 stages held in registers; between passes the tile is transposed through shared
-// memory (two padded buffers used alternately -> one barrier per exchange).  Pass 0 of the
+// radix-2 stages held in registers; between passes the tile is transposed through one padded
+// shared-memory buffer: a thread writes, at the end of a pass, exactly the positions it read at
+// the start of that pass (no other thread touches them in that pass), so the one barrier between
+// the write of pass p and the read of pass p+1 is all that is needed -- half the shared memory of
+// two alternating buffers, which the L1 gets for the twiddle tables.  Pass 0 of the
 // forward transform reads global memory directly in its register pattern (coalesced) and the
 // last pass leaves 8 consecutive coefficients per thread, written with 16-byte stores; the
 // inverse transform mirrors this.
@@ -219,25 +242,26 @@ __device__ __forceinline__ u32 r8_base(u32 tid, u32 ltq) {
 }
 
 // three forward stages (strides 4tq, 2tq, tq) on x[0..7]; ia = (tile_base + base) >> (ltq+3)
+template <bool LAZY>
 __device__ __forceinline__ void ct_radix8(u64 (&x)[8], const u64* __restrict__ tw,
                                           const u64* __restrict__ twsh, u32 ma, u32 ia, u64 q) {
   {
     const u64 w = __ldg(tw + ma + ia), ws = __ldg(twsh + ma + ia);
 #pragma unroll
-    for (int k = 0; k < 4; k++) ct_butterfly(x[k], x[k + 4], w, ws, q);
+    for (int k = 0; k < 4; k++) ct_butterfly<LAZY>(x[k], x[k + 4], w, ws, q);
   }
 #pragma unroll
   for (int h = 0; h < 2; h++) {
     const u32 idx = 2 * ma + 2 * ia + h;
     const u64 w = __ldg(tw + idx), ws = __ldg(twsh + idx);
-    ct_butterfly(x[4 * h + 0], x[4 * h + 2], w, ws, q);
-    ct_butterfly(x[4 * h + 1], x[4 * h + 3], w, ws, q);
+    ct_butterfly<LAZY>(x[4 * h + 0], x[4 * h + 2], w, ws, q);
+    ct_butterfly<LAZY>(x[4 * h + 1], x[4 * h + 3], w, ws, q);
   }
 #pragma unroll
   for (int h = 0; h < 4; h++) {
     const u32 idx = 4 * ma + 4 * ia + h;
     const u64 w = __ldg(tw + idx), ws = __ldg(twsh + idx);
-    ct_butterfly(x[2 * h], x[2 * h + 1], w, ws, q);
+    ct_butterfly<LAZY>(x[2 * h], x[2 * h + 1], w, ws, q);
   }
 }
 
@@ -265,21 +289,13 @@ __device__ __forceinline__ void gs_radix8(u64 (&x)[8], const u64* __restrict__ t
   }
 }
 
-template <class B>
-__global__ void __launch_bounds__(512, 2) ntt_fwd_tile8(DeviceTables T, const __grid_constant__ B b) {
-  extern __shared__ u64 sm[];
-  u64* buf[2] = {sm, sm + kTileSm};
-  const u32 limb  = blockIdx.y;
-  const u32 g     = b.g[limb];
-  const u64 q     = T.mod[g].q;
-  const u32 tbase = blockIdx.x * kTile;
-  u64*      data  = batch_dst(b, limb, T.N) + tbase;
-  const u64* tw   = T.tw + (size_t)g * T.N;
-  const u64* twsh = T.tw_sh + (size_t)g * T.N;
-  const u32 tid   = threadIdx.x;
-  const u32 m0    = T.N >> kTileLog;  // groups of the first tile stage (stride 2048)
-  // the strided phase (if any) already moved the limb to its destination
-  const u64* in = T.logN == (u32)kTileLog ? batch_src(b, limb, T.N) + tbase : data;
+template <bool LAZY>
+__device__ __forceinline__ void fwd_tile8_body(const DeviceTables& T, u64* sm, const u64* in,
+                                               u64* data, const u64* tw, const u64* twsh, u32 tbase,
+                                               const Modulus& mod) {
+  const u64 q   = mod.q;
+  const u32 tid = threadIdx.x;
+  const u32 m0  = T.N >> kTileLog;  // groups of the first tile stage (stride 2048)
   u64 x[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) x[k] = in[tid + 512 * k];
@@ -289,25 +305,47 @@ __global__ void __launch_bounds__(512, 2) ntt_fwd_tile8(DeviceTables T, const __
     const u32 base = r8_base(tid, ltq);
     if (p > 0) {
 #pragma unroll
-      for (int k = 0; k < 8; k++) x[k] = buf[(p - 1) & 1][kPad(base + (k << ltq))];
+      for (int k = 0; k < 8; k++) x[k] = sm[kPad(base + (k << ltq))];
     }
-    ct_radix8(x, tw, twsh, m0 << (3 * p), (tbase + base) >> (ltq + 3), q);
+    ct_radix8<LAZY>(x, tw, twsh, m0 << (3 * p), (tbase + base) >> (ltq + 3), q);
     if (p < 3) {
+      // (the positions written here are the ones this thread read at the start of the pass)
 #pragma unroll
-      for (int k = 0; k < 8; k++) buf[p & 1][kPad(base + (k << ltq))] = x[k];
+      for (int k = 0; k < 8; k++) sm[kPad(base + (k << ltq))] = x[k];
       __syncthreads();
     }
   }
   ulonglong2* out = reinterpret_cast<ulonglong2*>(data + 8 * tid);
 #pragma unroll
-  for (int k = 0; k < 4; k++)
-    out[k] = make_ulonglong2(normalize4(x[2 * k], q), normalize4(x[2 * k + 1], q));
+  for (int k = 0; k < 4; k++) {
+    if (LAZY)
+      out[k] = make_ulonglong2(normalize_any(x[2 * k], q, mod.mu_hi),
+                               normalize_any(x[2 * k + 1], q, mod.mu_hi));
+    else
+      out[k] = make_ulonglong2(normalize4(x[2 * k], q), normalize4(x[2 * k + 1], q));
+  }
+}
+
+template <class B>
+__global__ void __launch_bounds__(512, 2) ntt_fwd_tile8(DeviceTables T, const __grid_constant__ B b) {
+  extern __shared__ u64 sm[];
+  const u32 limb  = blockIdx.y;
+  const u32 g     = b.g[limb];
+  const Modulus mod = T.mod[g];
+  const u32 tbase = blockIdx.x * kTile;
+  u64*      data  = batch_dst(b, limb, T.N) + tbase;
+  const u64* tw   = T.tw + (size_t)g * T.N;
+  const u64* twsh = T.tw_sh + (size_t)g * T.N;
+  // the strided phase (if any) already moved the limb to its destination
+  const u64* in = T.logN == (u32)kTileLog ? batch_src(b, limb, T.N) + tbase : data;
+  if (lazy_modulus(mod)) fwd_tile8_body<true>(T, sm, in, data, tw, twsh, tbase, mod);
+  else fwd_tile8_body<false>(T, sm, in, data, tw, twsh, tbase, mod);
 }
 
 template <class B>
 __global__ void __launch_bounds__(512, 2) ntt_inv_tile8(DeviceTables T, const __grid_constant__ B b) {
   extern __shared__ u64 sm[];
-  u64* buf[2] = {sm, sm + kTileSm};
+  u64* buf[2] = {sm, sm};
   const u32 limb  = blockIdx.y;
   const u32 g     = b.g[limb];
   const u64 q     = T.mod[g].q;
@@ -383,10 +421,10 @@ static void launch_ntt_impl(const DeviceTables& T, const B& b, cudaStream_t s) {
     static bool attr = false;
     if (!attr) {
       cudaFuncSetAttribute(ntt_fwd_tile8<B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           2 * kTileSm * (int)sizeof(u64));
+                           kTileSm * (int)sizeof(u64));
       attr = true;
     }
-    ntt_fwd_tile8<B><<<grid, 512, 2 * kTileSm * sizeof(u64), s>>>(T, b);
+    ntt_fwd_tile8<B><<<grid, 512, kTileSm * sizeof(u64), s>>>(T, b);
     return;
   }
   u32  threads = tile / 2 < (u32)kNttThreads ? tile / 2 : (u32)kNttThreads;
@@ -403,10 +441,10 @@ static void launch_intt_impl(const DeviceTables& T, const B& b, cudaStream_t s) 
     static bool attr = false;
     if (!attr) {
       cudaFuncSetAttribute(ntt_inv_tile8<B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           2 * kTileSm * (int)sizeof(u64));
+                           kTileSm * (int)sizeof(u64));
       attr = true;
     }
-    ntt_inv_tile8<B><<<grid, 512, 2 * kTileSm * sizeof(u64), s>>>(T, b);
+    ntt_inv_tile8<B><<<grid, 512, kTileSm * sizeof(u64), s>>>(T, b);
   } else {
     u32 threads = tile / 2 < (u32)kNttThreads ? tile / 2 : (u32)kNttThreads;
     ntt_inv_tile<B><<<grid, threads, tile * sizeof(u64), s>>>(T, b);
