@@ -279,7 +279,8 @@ void Evaluator::rotate_precomp(BtsPrecom& pc, vvvcd& coeffs, u32 slots, double s
 void Evaluator::bootstrap_setup(u32 num_slots) {
   const u32 N = c->N, m = 2 * N;
   const u32 slots = num_slots == 0 ? m / 4 : num_slots;
-  if (precom_.count(slots)) return;
+  if (precom().count(slots)) return;
+  if (shared_) throw std::runtime_error("bootstrap tables for a new slot count must be set up on the primary context");
   if (!bootstrap_supported()) throw std::runtime_error("bootstrap: need a larger multiply depth");
   std::unique_ptr<BtsPrecom> pcp(new BtsPrecom);
   BtsPrecom& pc = *pcp;
@@ -352,7 +353,7 @@ void Evaluator::bootstrap_setup(u32 num_slots) {
     rotate_precomp(pc, coeffs, sparse ? 2 * slots : slots, scale_dec, level_dec, false);
   }
   c->sync();
-  precom_[slots] = std::move(pcp);
+  precom()[slots] = std::move(pcp);
 }
 
 // Find_coeffslots_rot_index :214-278
@@ -764,14 +765,14 @@ void Evaluator::eval_bootstrap(Ct& res, Ct& in, u32 raise_level, BtsPrecom& pc) 
 }
 
 void Evaluator::linear_transform(Ct& res, Ct& in, bool encoding) {
-  if (!precom_.count(in.slots)) bootstrap_setup(in.slots);
-  coeff_slots_transform(res, in, *precom_[in.slots], encoding);
+  if (!precom().count(in.slots)) bootstrap_setup(in.slots);
+  coeff_slots_transform(res, in, *precom()[in.slots], encoding);
 }
 
 const u64* Evaluator::diagonal_plain(u32 slots, bool encoding, u32 step, u32 idx, u32* level) {
   if (slots == 0) slots = c->N / 2;
-  if (!precom_.count(slots)) bootstrap_setup(slots);
-  BtsPrecom& pc = *precom_[slots];
+  if (!precom().count(slots)) bootstrap_setup(slots);
+  BtsPrecom& pc = *precom()[slots];
   auto& tab = encoding ? pc.c2s : pc.s2c;
   if (step >= tab.size() || idx >= tab[step].size()) return nullptr;
   *level = (encoding ? pc.c2s_level : pc.s2c_level)[step];
@@ -809,8 +810,8 @@ size_t Evaluator::fft_diagonals(u32 slots, u32 budget, bool flag, bool encoding,
 // Bootstrap (src/ckks/cipher_eval.c:366-404)
 void Evaluator::bootstrap(Ct& res, Ct& in, u32 level_after_bts) {
   const u32 slots = in.slots, q_cnt = (u32)c->L;
-  if (!precom_.count(slots)) bootstrap_setup(slots);
-  BtsPrecom& pc = *precom_[slots];
+  if (!precom().count(slots)) bootstrap_setup(slots);
+  BtsPrecom& pc = *precom()[slots];
   const u32 bts_depth = bootstrap_depth(c->params.hamming_weight);
   if (in.sfd == 1 && in.nq >= level_after_bts) {
     copy(res, in);

@@ -394,7 +394,14 @@ __global__ void fill_limb_kernel(DeviceTables T, LimbBatch b, const ScalarPack v
 }
 
 void Context::init_encoder() {
-  if (enc_tw_) return;
+  if (enc_tw_ && enc_buf_) return;
+  if (enc_tw_) {  // worker context: the tables are shared, the scratch buffers are not
+    const size_t half = N / 2;
+    ACE_CUDA(cudaMalloc(&enc_buf_, half * sizeof(cplx)));
+    ACE_CUDA(cudaMalloc(&enc_pow_, G * sizeof(u64)));
+    ACE_CUDA(cudaMallocHost(&enc_host_, half * sizeof(cplx)));
+    return;
+  }
   // Precompute_fft (ntt.c:585-610) with fft_length = 2N, folded per stage:
   //   tw[logm][i] = rou[(idx_mod - rot_group[i] % idx_mod) * gap]
   const size_t M = 2 * (size_t)N, half = N / 2;

@@ -11,6 +11,7 @@
 #include "context.h"
 #include "prof.h"
 
+#include <algorithm>
 #include <cstring>
 
 #include "host_math.h"
@@ -194,18 +195,43 @@ Context::Context(const Params& p, int dev) : params(p), device(dev) {
 Context::~Context() {
   cudaSetDevice(device);
   cudaStreamSynchronize(stream);
-  for (auto& kv : rot_keys_) { cudaFree(kv.second.k0); cudaFree(kv.second.k1); }
-  cudaFree(relin_key.k0);
-  cudaFree(relin_key.k1);
-  cudaFree(sk_ntt); cudaFree(pk0); cudaFree(pk1);
-  cudaFree(enc_tw_); cudaFree(enc_buf_); cudaFree(enc_pow_);
+  if (!worker_) {
+    for (auto& kv : rot_keys_) { cudaFree(kv.second.k0); cudaFree(kv.second.k1); }
+    cudaFree(relin_key.k0);
+    cudaFree(relin_key.k1);
+    cudaFree(sk_ntt); cudaFree(pk0); cudaFree(pk1);
+    cudaFree(enc_tw_);
+  }
+  cudaFree(enc_buf_); cudaFree(enc_pow_);
   if (enc_host_) cudaFreeHost(enc_host_);
-  for (auto& kv : auto_orders_) cudaFree(kv.second);
-  for (void* p : owned_) cudaFree(p);
+  for (auto& kv : auto_orders_)
+    if (std::find(inherited_orders_.begin(), inherited_orders_.end(), (const void*)kv.second) ==
+        inherited_orders_.end())
+      cudaFree(kv.second);
+  for (size_t i = owned_inherited_; i < owned_.size(); i++) cudaFree(owned_[i]);
   cudaStreamSynchronize(stream);
   for (auto& kv : block_limbs_) cudaFreeAsync(const_cast<u64*>(kv.first), stream);
   cudaStreamSynchronize(stream);
   cudaStreamDestroy(stream);
+}
+
+Context* Context::make_worker() {
+  ACE_CUDA(cudaSetDevice(device));
+  ACE_CUDA(cudaStreamSynchronize(stream));  // everything the worker shares is in place
+  Context* w = new Context(*this);          // memberwise: tables, keys, caches by pointer
+  w->worker_ = true;
+  w->stream = nullptr;
+  ACE_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+  w->free_lists_.clear();
+  w->block_limbs_.clear();
+  w->cached_bytes = w->live_bytes = w->peak_bytes = 0;
+  w->launches = 0;
+  memset(w->trace, 0, sizeof(w->trace));
+  w->owned_inherited_ = w->owned_.size();
+  w->inherited_orders_.clear();
+  for (auto& kv : w->auto_orders_) w->inherited_orders_.push_back(kv.second);
+  w->enc_buf_ = nullptr; w->enc_pow_ = nullptr; w->enc_host_ = nullptr;  // scratch: per context
+  return w;
 }
 
 // ---------------------------------------------------------------------------- memory

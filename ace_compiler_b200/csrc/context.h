@@ -53,6 +53,11 @@ class Context {
  public:
   Context(const Params& p, int device);
   ~Context();
+  // A worker context for another host thread (the reference runs Main_graph from several OpenMP
+  // threads, fhe-cmplr/rtlib/ant/dataset/resnet_cifar.main.inc:81): shares every immutable device
+  // table and all keys with this context, has its own stream, limb allocator, scratch buffers
+  // and counters.  Create after key generation / bootstrap set-up; destroy before this context.
+  Context* make_worker();
 
   // ---- parameter set (host copies)
   Params           params;
@@ -189,6 +194,9 @@ class Context {
   std::unordered_map<u32, int64_t*>        auto_orders_;
   std::unordered_map<u32, SwitchKey>       rot_keys_;
   std::vector<void*>                       owned_;  // device tables freed in the destructor
+  bool   worker_ = false;          // shares tables and keys with a primary context
+  size_t owned_inherited_ = 0;     // owned_[0 .. owned_inherited_) belong to the primary
+  std::vector<const void*> inherited_orders_;
   std::unordered_map<size_t, std::vector<u64*>> free_lists_;  // by size in limbs
   std::unordered_map<const u64*, size_t>        block_limbs_;
   // ModDown tables

@@ -50,6 +50,8 @@ struct BtsPrecom {
 class Evaluator {
  public:
   explicit Evaluator(Context* ctx) : c(ctx) {}
+  // evaluator of a worker context: uses the bootstrap tables of `primary` (read-only)
+  Evaluator(Context* ctx, Evaluator* primary) : c(ctx), shared_(primary) {}
   ~Evaluator();
   Context* c;
 
@@ -94,6 +96,8 @@ class Evaluator {
   typedef std::vector<cd>         vcd;
   typedef std::vector<double>     vd;
   std::map<u32, std::unique_ptr<BtsPrecom>> precom_;
+  Evaluator* shared_ = nullptr;
+  std::map<u32, std::unique_ptr<BtsPrecom>>& precom() { return shared_ ? shared_->precom_ : precom_; }
 
   Basis basis(const Ct& x) const { return Basis{x.nq, x.np, (u32)c->L}; }
   const SwitchKey& rot_key(int32_t rot);

@@ -18,7 +18,9 @@
 #include <cstring>
 #include <ctime>
 #include <map>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/rt_ant/rt_ant.h"
 #include "evaluator.h"
@@ -46,15 +48,27 @@ struct SWITCH_KEY {
 
 namespace {
 
-Context*  g_ctx    = nullptr;
-Evaluator* g_ev    = nullptr;
-Scheduler* g_queue = nullptr;  // deferred execution of the polynomial-level API (sched.h)
+// Execution state is per host thread, like the reference's threadprivate Input_data / Output_data
+// / Tm_stat (rtlib/common/src/io_lib.c:24-25, rt_stat.c:19): the thread that calls Prepare_context
+// owns the primary context; any other thread that enters the API gets a worker context (own
+// stream, limb allocator, scheduler; tables and keys shared, Context::make_worker) on its first
+// call.  The reference's driver runs Run_main_graph from an OpenMP loop over images
+// (ant/dataset/resnet_cifar.main.inc:81); here that puts several images in flight on one GPU.
+Context*   g_primary    = nullptr;
+Evaluator* g_primary_ev = nullptr;
+thread_local Context*   g_ctx    = nullptr;
+thread_local Evaluator* g_ev     = nullptr;
+thread_local Scheduler* g_queue  = nullptr;  // deferred execution of the polynomial-level API
 MODULUS*  g_mod    = nullptr;  // [G] Q then P, contiguous like the reference's arrays
 int       g_device = 0;
-uint64_t  g_enc_seed = 1;
-std::map<std::string, CIPHERTEXT*> g_inputs, g_outputs;
-std::map<u32, SWITCH_KEY*>          g_swk;  // by automorphism index; 0 = relin key
-clock_t g_tm_stamp;
+thread_local uint64_t g_enc_seed = 1;
+thread_local std::map<std::string, CIPHERTEXT*> g_inputs, g_outputs;
+std::map<u32, SWITCH_KEY*> g_swk;  // by automorphism index; 0 = relin key (guarded by g_mu)
+std::mutex g_mu;
+struct Worker { Context* c; Evaluator* ev; Scheduler* q; };
+std::vector<Worker> g_workers;  // every thread's state but the primary's (guarded by g_mu)
+bool g_eager = false;
+thread_local clock_t g_tm_stamp;
 
 // ACE_B200_STATS=1: per-entry-point call counts and host wall time (with a stream sync around
 // the timed calls), printed by Finalize_context -- where Main_graph's time goes
@@ -122,8 +136,27 @@ void stats_sync() {
 
 // ctx_nf(): metadata only.  ctx(): the caller is about to touch device data or the stream, so
 // every recorded limb op is issued first (keeps program order on the stream).
+void attach_worker() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  cudaSetDevice(g_device);
+  Context* w = nullptr;
+  try {
+    w = g_primary->make_worker();
+  } catch (const std::exception& e) {
+    die(e.what());
+  }
+  g_ctx   = w;
+  g_ev    = new Evaluator(w, g_primary_ev);
+  g_queue = new Scheduler(w);
+  g_queue->eager = g_eager;
+  g_enc_seed = 1000003ull * (g_workers.size() + 1) + 1;
+  g_workers.push_back(Worker{g_ctx, g_ev, g_queue});
+}
 Context* ctx_nf() {
-  if (!g_ctx) die("context not prepared (call Prepare_context first)");
+  if (!g_ctx) {
+    if (!g_primary) die("context not prepared (call Prepare_context first)");
+    attach_worker();
+  }
   return g_ctx;
 }
 Context* ctx() {
@@ -247,9 +280,10 @@ u32 mod_index(MODULUS* m) {
 }
 
 SWITCH_KEY* wrap_key(u32 slot, SwitchKey* k) {
+  std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_swk.find(slot);
   if (it != g_swk.end()) return it->second;
-  Context* c = ctx();
+  Context* c = ctx_nf();
   SWITCH_KEY* s = new SWITCH_KEY;
   s->key = k;
   s->pk0 = new POLYNOMIAL[c->dnum];
@@ -298,7 +332,7 @@ API void Ace_set_device(int device) { g_device = device; }
 API void* Ace_context(void) { return g_ctx; }
 
 // ---- B200 extensions used by bench.py / tests: device-side timing and counters
-static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+static thread_local cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 API void Ace_timer_start(void) {
   Context* c = ctx();
   if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
@@ -333,7 +367,7 @@ API int Ace_trace(uint64_t* out, size_t cap) {
 }
 
 API void Prepare_context(void) {
-  if (g_ctx) return;
+  if (g_primary) return;
   g_stats_on   = getenv("ACE_B200_STATS") && getenv("ACE_B200_STATS")[0] >= '1';
   g_stats_sync = g_stats_on && getenv("ACE_B200_STATS")[0] == '2';
   prof::enable(getenv("ACE_B200_PROF") && getenv("ACE_B200_PROF")[0] == '1');
@@ -344,7 +378,7 @@ API void Prepare_context(void) {
   guard([&] {
     Params prm{p->_poly_degree, p->_mul_depth, p->_first_mod_size, p->_scaling_mod_size, parts,
                p->_hamming_weight};
-    g_ctx = new Context(prm, g_device);
+    g_ctx = g_primary = new Context(prm, g_device);
     g_mod = new MODULUS[g_ctx->G];
     for (size_t g = 0; g < g_ctx->G; g++) {
       g_mod[g]._val = (int64_t)g_ctx->mod[g];
@@ -356,10 +390,11 @@ API void Prepare_context(void) {
            "_num_rot_idx = %ld,_hamming_wieght = %ld\n",
            p->_provider, p->_poly_degree, p->_sec_level, p->_mul_depth, p->_first_mod_size,
            p->_scaling_mod_size, parts, g_ctx->K, p->_num_rot_idx, p->_hamming_weight);
-    g_ev = new Evaluator(g_ctx);
+    g_ev = g_primary_ev = new Evaluator(g_ctx);
     g_queue = new Scheduler(g_ctx);
     // ACE_B200_EAGER=1: issue every call at once (no batching across calls)
-    g_queue->eager = getenv("ACE_B200_EAGER") && getenv("ACE_B200_EAGER")[0] == '1';
+    g_eager = getenv("ACE_B200_EAGER") && getenv("ACE_B200_EAGER")[0] == '1';
+    g_queue->eager = g_eager;
     const char* no_keys = getenv("ACE_B200_NO_KEYGEN");  // parity runs import the oracle's keys
     const bool  own_keys = !(no_keys && no_keys[0] == '1');
     const char* seed_env = getenv("ACE_B200_SEED");
@@ -377,29 +412,39 @@ API void Prepare_context(void) {
   }
 }
 
-API void Finalize_context(void) {
-  if (!g_ctx) return;
+API void Finalize_context(void) {  // called by the thread that prepared the context
+  if (!g_primary) return;
   if (g_stats_on) {
     printf("[ace_b200 stats] kernels launched: %zu; scheduler: %zu ops in %zu flushes / %zu waves, "
            "%zu chain launches, %zu mul+add fused, %zu dead stores dropped; peak limb memory "
-           "%.1f GB\n",
+           "%.1f GB; %zu worker thread(s)\n",
            g_ctx->launches, g_queue->n_ops, g_queue->n_flush, g_queue->n_waves,
            g_queue->n_chain_launches, g_queue->n_fused, g_queue->n_dead,
-           g_ctx->peak_bytes / 1073741824.0);
+           g_ctx->peak_bytes / 1073741824.0, g_workers.size());
     for (int i = 0; i < ST_COUNT; i++)
       printf("[ace_b200 stats] %-22s calls %9llu  host time %8.3f s\n", g_stats[i].name,
              (unsigned long long)g_stats[i].calls, g_stats[i].secs);
   }
-  for (auto& kv : g_swk) { delete[] kv.second->pk0; delete[] kv.second->pk1; delete kv.second; }
-  g_swk.clear();
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& kv : g_swk) { delete[] kv.second->pk0; delete[] kv.second->pk1; delete kv.second; }
+    g_swk.clear();
+    for (Worker& w : g_workers) {  // their threads must have finished their images
+      w.q->flush();
+      delete w.q;
+      delete w.ev;
+      delete w.c;
+    }
+    g_workers.clear();
+  }
   Pt_mgr_fini();
   if (g_queue) g_queue->flush();
   delete g_queue;
   g_queue = nullptr;
-  delete g_ev;
-  g_ev = nullptr;
-  delete g_ctx;
-  g_ctx = nullptr;
+  delete g_primary_ev;
+  g_ev = g_primary_ev = nullptr;
+  delete g_primary;
+  g_ctx = g_primary = nullptr;
   delete[] g_mod;
   g_mod = nullptr;
 }

@@ -2,6 +2,7 @@
 #include "sched.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -52,6 +53,10 @@ __global__ void __launch_bounds__(256) gather_batch_kernel(DeviceTables T,
   }
 }
 
+// Deferred frees hold memory: all schedulers of the process (one per host thread that runs
+// images) share a budget of 48 GB of blocks waiting for their flush.
+static std::atomic<int> g_live_schedulers{0};
+
 // ---------------------------------------------------------------------------- limb table
 static inline u32 hash_addr(const u64* p) {
   return (u32)((((uint64_t)(uintptr_t)p) >> 9) * 0x9E3779B97F4A7C15ull >> 32);
@@ -91,12 +96,16 @@ struct ContextBackend : SchedBackend {
 SchedBackend* make_context_backend(Context* c) { return new ContextBackend(c); }
 
 Scheduler::Scheduler(SchedBackend* backend) : c_(backend) {
+  g_live_schedulers++;
   table_.resize(1u << 16);
   memset(table_.data(), 0, table_.size() * sizeof(Limb));
   mask_ = (u32)table_.size() - 1;
   ops_.reserve(1 << 16);
 }
-Scheduler::~Scheduler() { delete c_; }
+Scheduler::~Scheduler() {
+  g_live_schedulers--;
+  delete c_;
+}
 
 void Scheduler::grow() {
   std::vector<Limb> old;
@@ -186,7 +195,8 @@ void Scheduler::kill_if_unread(Limb& l) {
 }
 
 void Scheduler::maybe_flush() {
-  if (eager || ops_.size() > (1u << 18) || pending_free_bytes_ > ((size_t)40 << 30)) flush();
+  const size_t limit = ((size_t)48 << 30) / (size_t)std::max(1, g_live_schedulers.load());
+  if (eager || ops_.size() > (1u << 18) || pending_free_bytes_ > limit) flush();
 }
 
 // ---------------------------------------------------------------------------- recording

@@ -34,6 +34,18 @@ def test_resnet20_logits():
     _run()
 
 
+def test_resnet20_three_images_in_flight():
+    """three host threads on one prepared context (worker contexts: own stream, allocator and
+    scheduler, shared tables and keys): every image decrypts to the reference's logits"""
+    if not os.path.exists(os.path.join(ROOT, "ace_compiler_b200", "models", "lib%s.so" % MODEL)):
+        pytest.skip("model unit not built (needs the reference tree at build time)")
+    r = subprocess.run([sys.executable, os.path.join(HERE, "model_threads_case.py"), MODEL, "3", "2"],
+                       capture_output=True, text=True, timeout=900)
+    sys.stdout.write(r.stdout[-2000:])
+    assert r.returncode == 0, r.stdout[-3000:] + "\n" + r.stderr[-4000:]
+    assert "THREADS PARITY OK" in r.stdout
+
+
 def _enough_ram():
     try:
         return os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES") >= 64 * 2**30
