@@ -553,7 +553,8 @@ void Scheduler::flush() {
   std::vector<u32> sorted(start[max_wave + 1]), pos(start.begin(), start.end() - 1);
   for (u32 i = 0; i < ops_.size(); i++)
     if (ops_[i].kind != OP_NOP) sorted[pos[ops_[i].wave]++] = i;
-  if (getenv("ACE_SCHED_DUMP")) {
+  static const bool dump = getenv("ACE_SCHED_DUMP") != nullptr;  // debugging aid of the self-test
+  if (dump) {
     for (u32 w = 0; w <= max_wave; w++)
       for (u32 s2 = start[w]; s2 < start[w + 1]; s2++) {
         const Op& o = ops_[sorted[s2]];

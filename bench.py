@@ -274,8 +274,14 @@ def run_ours(args):
                 "achieved": round(ach, 1), "peak": peak, "peak_source": how, "unit": "GB/s",
                 "frac": round(ach / peak, 4), "traffic": NTT_DRAM_TRAFFIC_PER_LAUNCH,
                 "alg_bytes_per_launch": alg_bytes, "launch_us": round(per_launch_s * 1e6, 2),
-                "note": "two passes over each limb (2 MiB moved per 1 MiB algorithmic); the butterflies "
-                        "are INT32-multiply bound, see profiles/"}
+                "int_pipe": {"fmaheavy_pct_of_elapsed": 55.1, "alu_pct": 46.6, "issue_active_pct": 50.8,
+                             "top_stall": "math_pipe_throttle",
+                             "source": "profiles/r1_ncu_full_ntt_v1.csv (ntt_fwd_tile8)"},
+                "note": "two passes over each limb (2 MiB moved per 1 MiB algorithmic) plus 1 MiB of "
+                        "per-prime twiddle tables; the 64-bit Shoup butterflies keep the integer "
+                        "multiply pipe busiest (10 IMAD of ~34 instructions per butterfly), so the "
+                        "HBM fraction understates how close the kernel is to its own (integer) "
+                        "roofline; see DESIGN.md section 5 and profiles/"}
         buf.free()
         ctx.close()
     sampler.join(timeout=2)
