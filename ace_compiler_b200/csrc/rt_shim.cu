@@ -621,7 +621,7 @@ API void Ace_upload_poly(POLY poly, const int64_t* host_src) {
 }
 
 // Hw_modadd / Hw_modmul / Hw_rotate (poly_arith.c:14-56) are recorded and issued in batches
-// (op_queue.h); ACE_B200_NO_BATCH=1 launches one kernel per call instead.
+// by the scheduler (sched.h); ACE_B200_EAGER=1 issues every call at once instead.
 API int64_t* Hw_modadd(int64_t* res, int64_t* a, int64_t* b, MODULUS* m, uint32_t degree) {
   StatScope ss(ST_ADD);
   ctx_nf();
