@@ -24,7 +24,7 @@ static const size_t kAuxBits = 60;  // AUXBITS, include/util/fhe_types.h:27-29
 template <typename Tp>
 Tp* Context::to_device(const std::vector<Tp>& v) {
   Tp* d = nullptr;
-  ACE_CUDA(cudaMalloc(&d, v.size() * sizeof(Tp) + 16));
+  dev_malloc(&d, v.size() * sizeof(Tp) + 16);
   h2d_sync(d, v.data(), v.size() * sizeof(Tp));
   owned_.push_back(d);
   return d;
@@ -125,7 +125,7 @@ Context::Context(const Params& p, int dev) : params(p), device(dev) {
   {  // the four twiddle tables in one block (one L2 access-policy window can cover them)
     const size_t per = G * (size_t)N;
     u64* blk = nullptr;
-    ACE_CUDA(cudaMalloc(&blk, 4 * per * sizeof(u64)));
+    dev_malloc(&blk, 4 * per * sizeof(u64));
     owned_.push_back(blk);
     h2d_sync(blk, tw.data(), per * sizeof(u64));
     h2d_sync(blk + per, tw_sh.data(), per * sizeof(u64));
@@ -268,9 +268,25 @@ void Context::free_limbs(u64* p) {
   auto it = block_limbs_.find(p);
   if (it == block_limbs_.end()) throw std::runtime_error("free_limbs: unknown block");
   const size_t bytes = it->second * N * sizeof(u64);
+  live_bytes -= bytes;
+  if (cached_bytes + bytes > kCacheCapBytes) {  // enough idle blocks already: back to the pool
+    block_limbs_.erase(it);
+    ACE_CUDA(cudaFreeAsync(p, stream));
+    return;
+  }
   free_lists_[it->second].push_back(p);
   cached_bytes += bytes;
-  live_bytes -= bytes;
+}
+void Context::dev_malloc(void** p, size_t bytes) {
+  if (cudaMalloc(p, bytes) == cudaSuccess) return;
+  cudaGetLastError();
+  ACE_CUDA(cudaDeviceSynchronize());
+  trim_cache();
+  ACE_CUDA(cudaStreamSynchronize(stream));
+  cudaMemPool_t pool;
+  ACE_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  ACE_CUDA(cudaMemPoolTrimTo(pool, 0));
+  ACE_CUDA(cudaMalloc(p, bytes));
 }
 void Context::trim_cache() {
   for (auto& kv : free_lists_) {
@@ -467,7 +483,7 @@ const int64_t* Context::auto_order(u32 k) {  // number_theory.c:201-214 (is_ntt 
     ord[hm::bit_reverse((u32)j, logN)] = (int64_t)hm::bit_reverse((u32)idx, logN);
   }
   int64_t* d = nullptr;
-  ACE_CUDA(cudaMalloc(&d, N * sizeof(int64_t)));
+  dev_malloc(&d, N * sizeof(int64_t));
   h2d_sync(d, ord.data(), N * sizeof(int64_t));
   auto_orders_[k] = d;
   return d;
@@ -486,7 +502,7 @@ void Context::import_key_limbs(SwitchKey& key, u32 part, int which, const u64* h
   if (part >= dnum) throw std::runtime_error("key part out of range");
   size_t per = G * (size_t)N;
   u64**  dst = which ? &key.k1 : &key.k0;
-  if (*dst == nullptr) ACE_CUDA(cudaMalloc(dst, dnum * per * sizeof(u64)));
+  if (*dst == nullptr) dev_malloc(dst, dnum * per * sizeof(u64));
   h2d_sync(*dst + part * per, host, per * sizeof(u64));
 }
 

@@ -75,6 +75,12 @@ class Context {
   u64* alloc_limbs(size_t n_limbs, bool zero);
   void free_limbs(u64* p);
   void trim_cache();  // return every cached block to the driver
+  // device memory for tables and keys (plain cudaMalloc).  The stream-ordered pool behind the limb
+  // allocator keeps what it once had; when a plain allocation fails, the cached limb blocks and
+  // the pool's idle memory are given back and the allocation is tried again.
+  void dev_malloc(void** p, size_t bytes);
+  template <typename Tp> void dev_malloc(Tp** p, size_t bytes) { dev_malloc(reinterpret_cast<void**>(p), bytes); }
+  static constexpr size_t kCacheCapBytes = (size_t)6 << 30;  // cached (idle) limb blocks per context
   size_t block_limbs(const u64* p) const {
     auto it = block_limbs_.find(p);
     if (it == block_limbs_.end()) throw std::runtime_error("unknown limb block");
