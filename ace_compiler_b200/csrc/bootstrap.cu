@@ -475,6 +475,7 @@ void Evaluator::rotate_iteration(Ct& result, BtsPrecom& pc,
     // automorphism and the accumulation.  Exact ring additions commute, the approximate base
     // conversions see the same inputs as in the step-by-step form: same limbs.
     u64* inner_all = c->alloc_limbs((size_t)(baby > 1 ? baby - 1 : 1) * 2 * W, false);
+    u64* zero_pt   = c->alloc_limbs((size_t)pt_level + K, true);  // stands in for the absent diagonal
     DotAllArgs da;
     da.rot = rot; da.rot_stride = 2 * WN; da.c1_offset = WN;
     da.b = (u32)baby; da.g = (u32)giant; da.pt_pstart = pt_level;
@@ -483,7 +484,7 @@ void Evaluator::rotate_iteration(Ct& result, BtsPrecom& pc,
       for (int32_t j = 0; j < giant; j++) {
         const u64* pt = (giant * i + j == num_rot) ? nullptr : tab[step][giant * i + j];
         if (giant * i + j != num_rot && !pt) throw std::runtime_error("bootstrap: missing diagonal plaintext");
-        da.pt[i * giant + j] = pt;
+        da.pt[i * giant + j] = pt ? pt : zero_pt;  // absent term: multiply by zero
         used += pt ? 1 : 0;
       }
       // first = inner_0.c0, outer = (0, inner_0.c1)
@@ -545,6 +546,7 @@ void Evaluator::rotate_iteration(Ct& result, BtsPrecom& pc,
       c->free_limbs(ext_all);
     }
     c->free_limbs(inner_all);
+    c->free_limbs(zero_pt);
   } else {
   // ---- step-by-step form (more baby or giant steps than the batched kernel holds)
   u64* inner = c->alloc_limbs(2 * (size_t)W, false);

@@ -12,6 +12,9 @@
 #include "prof.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <cstring>
 
 #include "host_math.h"
@@ -235,8 +238,27 @@ Context* Context::make_worker() {
 }
 
 // ---------------------------------------------------------------------------- memory
+static std::atomic<unsigned> g_pressure_epoch{0};
+void Context::relieve_pressure() {
+  const unsigned e = g_pressure_epoch.load(std::memory_order_relaxed);
+  if (e == pressure_seen_) return;
+  pressure_seen_ = e;
+  trim_cache();
+}
+
+// Blocks come in size classes (four per octave: 8, 10, 12, 14, 16, 20, ...), not exact sizes: a
+// polynomial of 33 limbs reuses the block a polynomial of 34 limbs left behind.  With exact sizes
+// every level of the modulus chain kept its own idle blocks (~30 GB per context at the ResNet set).
+static size_t size_class(size_t n) {
+  if (n <= 8) return n;
+  size_t step = 2;
+  while (8 * step <= n) step *= 2;  // n in (4*step, 8*step]
+  return (n + step - 1) / step * step;
+}
+
 u64* Context::alloc_limbs(size_t n_limbs, bool zero) {
-  n_limbs = std::max<size_t>(n_limbs, 1);
+  relieve_pressure();
+  n_limbs = size_class(std::max<size_t>(n_limbs, 1));
   const size_t bytes = n_limbs * N * sizeof(u64);
   u64* p = nullptr;
   auto it = free_lists_.find(n_limbs);
@@ -247,12 +269,18 @@ u64* Context::alloc_limbs(size_t n_limbs, bool zero) {
   } else {
     // new blocks come from the driver's stream-ordered pool (no device synchronisation)
     cudaError_t e = cudaMallocAsync(&p, bytes, stream);
-    if (e != cudaSuccess) {  // out of memory: give the cached blocks back and retry once
+    for (int attempt = 0; e != cudaSuccess && attempt < 40; attempt++) {
+      // out of memory: give the idle blocks back -- ours now, the other contexts' at their next
+      // allocator call -- and try again
       cudaGetLastError();
       ACE_CUDA(cudaStreamSynchronize(stream));
       trim_cache();
-      ACE_CUDA(cudaMallocAsync(&p, bytes, stream));
+      g_pressure_epoch++;
+      pressure_seen_ = g_pressure_epoch.load();
+      if (attempt) std::this_thread::sleep_for(std::chrono::milliseconds(50));
+      e = cudaMallocAsync(&p, bytes, stream);
     }
+    ACE_CUDA(e);
     block_limbs_[p] = n_limbs;
   }
   live_bytes += bytes;
@@ -265,6 +293,7 @@ u64* Context::alloc_limbs(size_t n_limbs, bool zero) {
 }
 void Context::free_limbs(u64* p) {
   if (!p) return;
+  relieve_pressure();
   auto it = block_limbs_.find(p);
   if (it == block_limbs_.end()) throw std::runtime_error("free_limbs: unknown block");
   const size_t bytes = it->second * N * sizeof(u64);
@@ -278,15 +307,21 @@ void Context::free_limbs(u64* p) {
   cached_bytes += bytes;
 }
 void Context::dev_malloc(void** p, size_t bytes) {
-  if (cudaMalloc(p, bytes) == cudaSuccess) return;
-  cudaGetLastError();
-  ACE_CUDA(cudaDeviceSynchronize());
-  trim_cache();
-  ACE_CUDA(cudaStreamSynchronize(stream));
-  cudaMemPool_t pool;
-  ACE_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-  ACE_CUDA(cudaMemPoolTrimTo(pool, 0));
-  ACE_CUDA(cudaMalloc(p, bytes));
+  cudaError_t e = cudaMalloc(p, bytes);
+  for (int attempt = 0; e != cudaSuccess && attempt < 40; attempt++) {
+    cudaGetLastError();
+    ACE_CUDA(cudaDeviceSynchronize());
+    trim_cache();
+    g_pressure_epoch++;
+    pressure_seen_ = g_pressure_epoch.load();
+    ACE_CUDA(cudaStreamSynchronize(stream));
+    cudaMemPool_t pool;
+    ACE_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    ACE_CUDA(cudaMemPoolTrimTo(pool, 0));
+    if (attempt) std::this_thread::sleep_for(std::chrono::milliseconds(50));
+    e = cudaMalloc(p, bytes);
+  }
+  ACE_CUDA(e);
 }
 void Context::trim_cache() {
   for (auto& kv : free_lists_) {

@@ -80,7 +80,11 @@ class Context {
   // the pool's idle memory are given back and the allocation is tried again.
   void dev_malloc(void** p, size_t bytes);
   template <typename Tp> void dev_malloc(Tp** p, size_t bytes) { dev_malloc(reinterpret_cast<void**>(p), bytes); }
-  static constexpr size_t kCacheCapBytes = (size_t)6 << 30;  // cached (idle) limb blocks per context
+  static constexpr size_t kCacheCapBytes = (size_t)1 << 40;  // idle blocks per context: no static cap
+  // memory pressure: an allocation failed somewhere in the process; every context gives its idle
+  // blocks back at its next allocator call (free lists are touched by their own thread only)
+  void relieve_pressure();
+  unsigned pressure_seen_ = 0;
   size_t block_limbs(const u64* p) const {
     auto it = block_limbs_.find(p);
     if (it == block_limbs_.end()) throw std::runtime_error("unknown limb block");

@@ -210,7 +210,8 @@ void launch_gather_add_basis(const DeviceTables& T, u64* r, const u64* a, const 
                              Basis bs, cudaStream_t s);
 
 // all baby-step plaintext inner products of one BSGS level (see kernels_ext.cu):
-// rotation j = (rot + j*rot_stride, rot + j*rot_stride + c1_offset); pt[i*g + j] may be null
+// rotation j = (rot + j*rot_stride, rot + j*rot_stride + c1_offset); every pt[i*g + j] must be a
+// valid plaintext (an all-zero one where the term is absent)
 constexpr int kMaxDotBaby = 8, kMaxDotGiant = 16;
 struct DotAllArgs {
   const u64* rot;

@@ -237,7 +237,7 @@ void launch_gather_add_basis(const DeviceTables& T, u64* r, const u64* a, const 
 }
 
 // All baby-step inner sums of one BSGS level in one pass over the giant-step rotations:
-//   out_i = sum_j rot_j (.) pt[i*g + j]        i < b, j < g  (null plaintext = term absent)
+//   out_i = sum_j rot_j (.) pt[i*g + j]        i < b, j < g  (absent terms: a zero plaintext)
 // Each rotation limb is read once instead of b times; the sums are the same exact 128-bit
 // accumulations as pt_dot_kernel's, so the results are identical.
 template <int B>
@@ -256,15 +256,16 @@ __global__ void __launch_bounds__(256) pt_dot_all_kernel(DeviceTables T,
   for (u32 j = 0; j < A.g; j++) {
     const u64 x0 = A.rot[(size_t)j * A.rot_stride + off + n];
     const u64 x1 = A.rot[(size_t)j * A.rot_stride + A.c1_offset + off + n];
+    // every table entry is a valid pointer (absent terms point at a zero plaintext), so the B
+    // loads of this step are independent and go out together
+    u64 p[B];
+#pragma unroll
+    for (int i = 0; i < B; i++) p[i] = A.pt[(i < (int)A.b ? i : 0) * A.g + j][poff + n];
 #pragma unroll
     for (int i = 0; i < B; i++) {
       if (i < (int)A.b) {
-        const u64* pt = A.pt[i * A.g + j];
-        if (pt != nullptr) {
-          const u64 p = pt[poff + n];
-          mac128(lo0[i], hi0[i], x0, p);
-          mac128(lo1[i], hi1[i], x1, p);
-        }
+        mac128(lo0[i], hi0[i], x0, p[i]);
+        mac128(lo1[i], hi1[i], x1, p[i]);
       }
     }
   }

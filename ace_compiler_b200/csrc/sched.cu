@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) gather_batch_kernel(DeviceTables T,
 }
 
 // Deferred frees hold memory: all schedulers of the process (one per host thread that runs
-// images) share a budget of 30 GB of blocks waiting for their flush.
+// images) share a budget of 48 GB of blocks waiting for their flush.
 static std::atomic<int> g_live_schedulers{0};
 
 // ---------------------------------------------------------------------------- limb table
@@ -195,7 +195,7 @@ void Scheduler::kill_if_unread(Limb& l) {
 }
 
 void Scheduler::maybe_flush() {
-  const size_t limit = ((size_t)30 << 30) / (size_t)std::max(1, g_live_schedulers.load());
+  const size_t limit = ((size_t)48 << 30) / (size_t)std::max(1, g_live_schedulers.load());
   if (eager || ops_.size() > (1u << 18) || pending_free_bytes_ > limit) flush();
 }
 
