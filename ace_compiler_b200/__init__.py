@@ -74,7 +74,6 @@ SIGNATURES = {
                                 vp, vp, u32, u32, C.c_double, u32, u32]),
     "ace_timer_start": (C.c_int, [vp]),
     "ace_timer_stop_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
-    "ace_sched_selftest": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_size_t)]),
 }
 
 _lib = None

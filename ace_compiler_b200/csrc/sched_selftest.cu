@@ -8,7 +8,7 @@
 // limb, 16-bit primes): once call by call (eager) and once deferred.  At every synchronisation
 // point the contents of all live blocks must agree.  The toy backend processes the chains, gathers
 // and jobs of a batch in REVERSE order, so two ops that the scheduler wrongly put into one wave
-// show up as a mismatch.  Exposed as ace_sched_selftest() (include/ace_b200.h); used by
+// show up as a mismatch.  Built into libace_b200_selftest.so only (build.py), never into the product library; used by
 // tests/test_cpu_sched.py.  TEST INFRASTRUCTURE: nothing on the product path calls this.
 #include <cstdio>
 #include <cstdlib>

@@ -145,16 +145,6 @@ int ace_bootstrap(ace_ctx* ctx, int64_t* r0, int64_t* r1, uint32_t* out_level, d
 int ace_timer_start(ace_ctx* ctx);
 int ace_timer_stop_ms(ace_ctx* ctx, float* ms);
 
-/* ---- host-only self-test of the deferred-execution scheduler (csrc/sched.h): a pseudo-random
- *      program over the recorded polynomial-level API (what the emitted code does through
- *      Hw_modadd/Hw_modmul/Hw_rotate, Decomp_modup, Mod_down, Rescale, Pt_from_msg, Alloc_poly,
- *      Free_poly_data; reference semantics = call-by-call execution) is run call by call and
- *      deferred on a host-simulated backend; 0 = identical at every synchronisation point,
- *      k > 0 = first mismatch at point k-1, < 0 = error.  stats: 6 counters of the deferred run
- *      (ops, flushes, waves, fused mul+add, dropped stores, chain launches), may be NULL.
- *      sync_permille: synchronisation points per 1000 ops (0 = one deferred window).  Needs no GPU. */
-int ace_sched_selftest(uint64_t seed, uint32_t n_ops, uint32_t sync_permille, size_t* stats);
-
 #ifdef __cplusplus
 }
 #endif
