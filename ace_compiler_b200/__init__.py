@@ -72,6 +72,8 @@ SIGNATURES = {
     "ace_keygen_rotations": (C.c_int, [vp, C.c_uint64, vp, sz]),
     "ace_bootstrap": (C.c_int, [vp, vp, vp, C.POINTER(u32), C.POINTER(C.c_double), C.POINTER(u32),
                                 vp, vp, u32, u32, C.c_double, u32, u32]),
+    "ace_measure_pipe_peaks": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.c_int]),
+    "ace_ntt_bfly_peak": (C.c_double, [vp, C.c_int, C.c_int]),
     "ace_timer_start": (C.c_int, [vp]),
     "ace_timer_stop_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
 }

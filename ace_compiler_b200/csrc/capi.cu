@@ -294,6 +294,11 @@ int ace_bootstrap(ace_ctx* ctx, int64_t* r0, int64_t* r1, uint32_t* out_level, d
                  sf_degree, [&](Ct& o, Ct& i) { ctx->ev->bootstrap(o, i, level_after_bts); }))
 }
 
+double ace_ntt_bfly_peak(ace_ctx* ctx, int form, int ctas_per_sm) {
+  if (!ctx || !ntt16_usable(ctx->c->T)) return -1.0;
+  cudaSetDevice(ctx->c->device);
+  return ntt16_bfly_peak(ctx->c->T, form, ctas_per_sm, ctx->c->stream);
+}
 int ace_timer_start(ace_ctx* ctx) { ACE_TRY(ACE_CUDA(cudaEventRecord(ctx->ev0, ctx->c->stream))) }
 int ace_timer_stop_ms(ace_ctx* ctx, float* ms) {
   ACE_TRY(ACE_CUDA(cudaEventRecord(ctx->ev1, ctx->c->stream));

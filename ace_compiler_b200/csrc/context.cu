@@ -141,6 +141,81 @@ Context::Context(const Params& p, int dev) : params(p), device(dev) {
   }
   T.n_inv    = to_device(n_inv);
   T.n_inv_sh = to_device(n_inv_sh);
+  T.ftw2 = T.itw2 = T.ips2 = nullptr;
+  T.ftwd = T.itwd = T.ipsd = nullptr;
+  T.fp64_max_q = 0;
+  {  // N = 2^16 (ntt16.cu): interleaved {w, w'} tables; moduli must be below 2^61
+    bool ok = logN == 16 && getenv("ACE_B200_OLD_NTT") == nullptr;
+    for (size_t g = 0; g < G; g++) ok = ok && (mod[g] >> 61) == 0;
+    if (ok) {
+      const size_t per = G * (size_t)N;  // entries of 2 words
+      std::vector<u64> f2(2 * per), i2(2 * per), p2(2 * per);
+      for (size_t g = 0; g < G; g++) {
+        const u64 m = mod[g];
+        u64* f = f2.data() + 2 * g * (size_t)N;
+        u64* iv = i2.data() + 2 * g * (size_t)N;
+        u64* ps = p2.data() + 2 * g * (size_t)N;
+        for (u32 i = 0; i < N; i++) {
+          f[2 * i]     = tw[g * (size_t)N + i];
+          f[2 * i + 1] = tw_sh[g * (size_t)N + i];
+        }
+        // decimation-in-time inverse: [mm + j] = omega_(2mm)^-j, omega = psi^2
+        const u64 psi_inv = hm::invmod_prime(psi[g], m);
+        const u64 om_inv  = hm::mulmod(psi_inv, psi_inv, m);
+        iv[0] = iv[1] = 0;
+        for (u32 mm = 1; mm < N; mm <<= 1) {
+          const u64 base = hm::powmod(om_inv, N / (2 * mm), m);
+          u64 pw = 1;
+          for (u32 j = 0; j < mm; j++) {
+            iv[2 * (mm + j)]     = pw;
+            iv[2 * (mm + j) + 1] = hm::shoup(pw, m);
+            pw = hm::mulmod(pw, base, m);
+          }
+        }
+        u64 pw = n_inv[g];  // psi^-n N^-1
+        for (u32 i = 0; i < N; i++) {
+          ps[2 * i]     = pw;
+          ps[2 * i + 1] = hm::shoup(pw, m);
+          pw = hm::mulmod(pw, psi_inv, m);
+        }
+      }
+      u64* blk = nullptr;
+      dev_malloc(&blk, 6 * per * sizeof(u64));
+      owned_.push_back(blk);
+      h2d_sync(blk, f2.data(), 2 * per * sizeof(u64));
+      h2d_sync(blk + 2 * per, i2.data(), 2 * per * sizeof(u64));
+      h2d_sync(blk + 4 * per, p2.data(), 2 * per * sizeof(u64));
+      T.ftw2 = reinterpret_cast<const ulonglong2*>(blk);
+      T.itw2 = reinterpret_cast<const ulonglong2*>(blk + 2 * per);
+      T.ips2 = reinterpret_cast<const ulonglong2*>(blk + 4 * per);
+      // FP64 butterfly (ntt16.cu): the same values as doubles for the moduli below 1.5e15
+      // (1.5 q < 2^51); other rows stay zero and are never read
+      if (getenv("ACE_B200_NO_FP64_NTT") == nullptr) {
+        const u64 max_q = 1500000000000000ull;
+        bool any = false;
+        std::vector<double> fd(per, 0.0), id(per, 0.0), pd(per, 0.0);
+        for (size_t g = 0; g < G; g++) {
+          if (mod[g] >= max_q) continue;
+          any = true;
+          for (size_t i = 0; i < N; i++) {
+            fd[g * (size_t)N + i] = (double)f2[2 * (g * (size_t)N + i)];
+            id[g * (size_t)N + i] = (double)i2[2 * (g * (size_t)N + i)];
+            pd[g * (size_t)N + i] = (double)p2[2 * (g * (size_t)N + i)];
+          }
+        }
+        if (any) {
+          double* dblk = nullptr;
+          dev_malloc(&dblk, 3 * per * sizeof(double));
+          owned_.push_back(reinterpret_cast<u64*>(dblk));
+          h2d_sync(dblk, fd.data(), per * sizeof(double));
+          h2d_sync(dblk + per, id.data(), per * sizeof(double));
+          h2d_sync(dblk + 2 * per, pd.data(), per * sizeof(double));
+          T.ftwd = dblk; T.itwd = dblk + per; T.ipsd = dblk + 2 * per;
+          T.fp64_max_q = max_q;
+        }
+      }
+    }
+  }
 
   // ---- ModDown constants (crt.c Precompute_primes(p) + Precompute_new_base(p, q))
   std::vector<u64> phi(K), phi_sh(K), phm(L * K), pinv(L), pinv_sh(L), pm(L), pm_sh(L);

@@ -11,6 +11,9 @@
 //
 // All of these are integer kernels: NTT and base conversion are bound by the INT32 multiply
 // pipe (IMAD), the rest by HBM bandwidth.  No tensor-core path is used.
+#include <cstdio>
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "prof.h"
 
@@ -410,10 +413,34 @@ static void launch_strided_any(bool fwd, const DeviceTables& T, const B& b, cuda
   }
 }
 
+// ACE_B200_NTTHIST=1: histogram of batch sizes (limbs per launch), printed at exit
+static struct NttHist {
+  bool on = getenv("ACE_B200_NTTHIST") != nullptr;
+  size_t fwd[kMaxBatch + 1] = {0}, inv[kMaxBatch + 1] = {0};
+  ~NttHist() {
+    if (!on) return;
+    for (int d = 0; d < 2; d++) {
+      const size_t* h = d ? inv : fwd;
+      size_t launches = 0, limbs = 0;
+      for (int i = 0; i <= kMaxBatch; i++) { launches += h[i]; limbs += h[i] * i; }
+      printf("[ace_b200 ntthist] %s: %zu launches, %zu limbs; limbs by batch size:", d ? "intt" : "ntt", launches, limbs);
+      const int edges[] = {1, 2, 3, 5, 9, 17, 25, 37, 49, 73, 97, 145, 193};
+      for (int e = 0; e + 1 < 13; e++) {
+        size_t l = 0, n = 0;
+        for (int i = edges[e]; i < edges[e + 1] && i <= kMaxBatch; i++) { l += h[i] * i; n += h[i]; }
+        printf(" [%d-%d]: %zu limbs/%zu", edges[e], edges[e + 1] - 1, l, n);
+      }
+      printf("\n");
+    }
+  }
+} g_ntt_hist;
+
 template <class B>
 static void launch_ntt_impl(const DeviceTables& T, const B& b, cudaStream_t s) {
   if (b.n == 0) return;
+  if (g_ntt_hist.on) g_ntt_hist.fwd[b.n <= (u32)kMaxBatch ? b.n : kMaxBatch]++;
   prof::Scope prof_scope_("ntt", s);
+  if (ntt16_usable(T)) { launch_ntt16(T, b, s); return; }
   const u32 tile = T.N < (u32)kTile ? T.N : (u32)kTile;
   if (T.logN > (u32)kTileLog) launch_strided_any<B>(true, T, b, s);
   dim3 grid(T.N / tile, b.n);
@@ -434,7 +461,9 @@ static void launch_ntt_impl(const DeviceTables& T, const B& b, cudaStream_t s) {
 template <class B>
 static void launch_intt_impl(const DeviceTables& T, const B& b, cudaStream_t s) {
   if (b.n == 0) return;
+  if (g_ntt_hist.on) g_ntt_hist.inv[b.n <= (u32)kMaxBatch ? b.n : kMaxBatch]++;
   prof::Scope prof_scope_("intt", s);
+  if (ntt16_usable(T)) { launch_intt16(T, b, s); return; }
   const u32 tile = T.N < (u32)kTile ? T.N : (u32)kTile;
   dim3 grid(T.N / tile, b.n);
   if (T.logN >= (u32)kTileLog) {

@@ -34,7 +34,26 @@ struct DeviceTables {
   const u64*     itw_sh;
   const u64*     n_inv;    // [G]
   const u64*     n_inv_sh;
+  // N = 2^16 transforms (ntt16.cu): twiddles interleaved with their Shoup companions {w, w'}
+  const ulonglong2* ftw2;  // [G][N] forward, same order as tw
+  const ulonglong2* itw2;  // [G][N] inverse, decimation in time: [m + j] = omega_(2m)^-j, j < m
+  const ulonglong2* ips2;  // [G][N] psi^-n N^-1
+  // the same three tables as exact integers in doubles, for the FP64 butterfly (moduli < fp64_max_q)
+  const double* ftwd;
+  const double* itwd;
+  const double* ipsd;
+  u64           fp64_max_q;
 };
+
+// N = 2^16 only (ntt16.cu); launch_ntt / launch_intt route here when ntt16_usable()
+bool ntt16_usable(const DeviceTables& T);
+double ntt16_bfly_peak(const DeviceTables& T, int form, int ctas_per_sm, cudaStream_t st);
+struct LimbBatch;
+struct LimbPtrBatch;
+void launch_ntt16(const DeviceTables& T, const LimbBatch& b, cudaStream_t s);
+void launch_ntt16(const DeviceTables& T, const LimbPtrBatch& b, cudaStream_t s);
+void launch_intt16(const DeviceTables& T, const LimbBatch& b, cudaStream_t s);
+void launch_intt16(const DeviceTables& T, const LimbPtrBatch& b, cudaStream_t s);
 
 void launch_ntt(const DeviceTables& T, const LimbBatch& b, cudaStream_t s);
 void launch_intt(const DeviceTables& T, const LimbBatch& b, cudaStream_t s);

@@ -416,10 +416,11 @@ API void Finalize_context(void) {  // called by the thread that prepared the con
   if (!g_primary) return;
   if (g_stats_on) {
     printf("[ace_b200 stats] kernels launched: %zu; scheduler: %zu ops in %zu flushes / %zu waves, "
-           "%zu chain launches, %zu mul+add fused, %zu dead stores dropped; peak limb memory "
-           "%.1f GB; %zu worker thread(s)\n",
+           "%zu chain launches, %zu mul+add fused, %zu dead stores dropped, %zu of %zu Decomp_modup "
+           "served from an earlier result; peak limb memory %.1f GB; %zu worker thread(s)\n",
            g_ctx->launches, g_queue->n_ops, g_queue->n_flush, g_queue->n_waves,
-           g_queue->n_chain_launches, g_queue->n_fused, g_queue->n_dead,
+           g_queue->n_chain_launches, g_queue->n_fused, g_queue->n_dead, g_queue->n_modup_shared,
+           g_queue->n_modup,
            g_ctx->peak_bytes / 1073741824.0, g_workers.size());
     for (int i = 0; i < ST_COUNT; i++)
       printf("[ace_b200 stats] %-22s calls %9llu  host time %8.3f s\n", g_stats[i].name,

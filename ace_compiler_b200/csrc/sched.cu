@@ -101,6 +101,8 @@ Scheduler::Scheduler(SchedBackend* backend) : c_(backend) {
   memset(table_.data(), 0, table_.size() * sizeof(Limb));
   mask_ = (u32)table_.size() - 1;
   ops_.reserve(1 << 16);
+  if (getenv("ACE_B200_NO_MODUP_SHARE")) share_modup = false;
+  if (getenv("ACE_B200_MODUP_NOHIT")) modup_nohit_ = true;
 }
 Scheduler::~Scheduler() {
   g_live_schedulers--;
@@ -171,6 +173,26 @@ void Scheduler::note_write(Limb& l, u32 wave, bool heavy, int32_t op, bool as_t)
   l.read_since = 0;
   l.has_r_chain = l.has_r_heavy = 0;
   l.is_zero = 0;
+  l.w_seq = ++wseq_;
+  l.alias = nullptr;
+}
+
+const u64* Scheduler::resolve(const u64* a) {
+  const u64* t = limb(a).alias;
+  return t ? t : a;
+}
+
+// consumers that take a block of consecutive limbs cannot follow per-limb renames: copy the kept
+// data into place first (recorded like any other copy)
+void Scheduler::materialize(const u64* p, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    u64* q = const_cast<u64*>(p) + i * c_->N();
+    if (live_ + 8 > table_.size() / 2) grow();
+    const u64* src = limb(q).alias;
+    if (!src) continue;
+    limb(q).alias = nullptr;
+    copy(q, src, 1);
+  }
 }
 
 // the limb is about to be overwritten (or its block freed): if nothing read what the last
@@ -195,6 +217,7 @@ void Scheduler::kill_if_unread(Limb& l) {
 }
 
 void Scheduler::maybe_flush() {
+  if (in_flush_) return;
   const size_t limit = ((size_t)48 << 30) / (size_t)std::max(1, g_live_schedulers.load());
   if (eager || ops_.size() > (1u << 18) || pending_free_bytes_ > limit) flush();
 }
@@ -213,7 +236,7 @@ void Scheduler::free(u64* block) {
     const u64* a = block + i * c_->N();
     u32 h = hash_addr(a) & mask_;
     while (table_[h].gen == gen_) {
-      if (table_[h].addr == (u64)(uintptr_t)a) { kill_if_unread(table_[h]); break; }
+      if (table_[h].addr == (u64)(uintptr_t)a) { kill_if_unread(table_[h]); table_[h].alias = nullptr; break; }
       h = (h + 1) & mask_;
     }
   }
@@ -260,6 +283,7 @@ void Scheduler::copy(u64* r, const u64* a, size_t n_limbs) {
     const u64* ap = a + i * c_->N();
     if (rp == ap) continue;
     if (live_ + 8 > table_.size() / 2) grow();
+    ap = resolve(ap);
     Limb& la = limb(ap);
     if (la.is_zero) { zero(rp, 1); continue; }
     const u32 wa = dep_read(la, false);
@@ -281,6 +305,8 @@ void Scheduler::ew(SchedOp op, u64* r, const u64* a, const u64* b, u32 g) {
   if (live_ + 8 > table_.size() / 2) grow();
   c_->count_limb_op(op == OP_MUL ? 0 : 1);
   n_ops++;
+  a = resolve(a);
+  b = resolve(b);
   const bool za = limb(a).is_zero, zb = limb(b).is_zero;
   // ---- operands known to be zero: the op degenerates (0 + y = y, x * 0 = 0, x - 0 = x)
   if (za || zb) {
@@ -350,6 +376,7 @@ void Scheduler::gather(u64* r, const u64* a, const int64_t* order, u32 g) {
   c_->count_limb_op(2);
   n_ops++;
   if (r == a) throw std::runtime_error("Hw_rotate in place is not supported");
+  a = resolve(a);
   Limb& la = limb(a);
   u32 wave = dep_read(la, true);
   Limb& lr = limb(r);
@@ -388,31 +415,69 @@ void Scheduler::encode(const EncodeJob& j) {
 void Scheduler::modup(u64* out, const u64* in, u32 num_q, u32 part) {
   const u32 N = c_->N(), W = num_q + (u32)c_->K();
   const u32 st = c_->digit_start(part), len = c_->digit_len(num_q, part);
-  if (live_ + W + len + 8 > table_.size() / 2) grow();
+  if (live_ + 2 * W + len + 8 > table_.size() / 2) grow();
+  n_modup++;
+  materialize(in + limb_off(N, st), len);
+  u64* dst = out;
+  if (share_modup && !eager) {
+    // a kept result of the same digit of the same, unmodified polynomial?
+    const ModupKey key{in + limb_off(N, st), num_q, part};
+    auto it = modup_cache_.find(key);
+    bool hit = it != modup_cache_.end() && !modup_nohit_;
+    if (hit)
+      for (u32 i = 0; i < len && hit; i++) hit = limb(in + limb_off(N, st + i)).w_seq <= it->second.stamp;
+    if (!hit) {
+      dst = c_->alloc(W);
+      pending_free_bytes_ += (size_t)W * N * sizeof(u64);
+      if (it != modup_cache_.end()) {
+        frees_.push_back(it->second.buf);  // stale: released once the recorded ops are issued
+        it->second = ModupEntry{dst, wseq_};
+      } else {
+        modup_cache_[key] = ModupEntry{dst, wseq_};
+      }
+    } else {
+      dst = it->second.buf;
+      n_modup_shared++;
+    }
+    // the caller's limbs now stand for the kept ones; what they held is unobservable
+    for (u32 i = 0; i < W; i++) {
+      u64* o = out + limb_off(N, i);
+      Limb& l = limb(o);
+      kill_if_unread(l);
+      if (!l.alias) aliased_.push_back(o);
+      l.alias = dst + limb_off(N, i);
+      l.is_zero = 0;
+    }
+    n_ops++;
+    if (hit) { maybe_flush(); return; }
+  }
   u32 wave = 0;
   for (u32 i = 0; i < len; i++) wave = std::max(wave, dep_read(limb(in + limb_off(N, st + i)), true));
+  const bool overlap = dst + limb_off(N, W) > in + limb_off(N, st) && dst < in + limb_off(N, st + len);
   for (u32 i = 0; i < W; i++) {
-    Limb& l = limb(out + limb_off(N, i));
-    kill_if_unread(l);
+    Limb& l = limb(dst + limb_off(N, i));
+    if (!overlap) kill_if_unread(l);
     wave = std::max(wave, dep_write(l, true));
   }
   for (u32 i = 0; i < len; i++) note_read(limb(in + limb_off(N, st + i)), wave, true);
-  for (u32 i = 0; i < W; i++) note_write(limb(out + limb_off(N, i)), wave, true, -1, false);
+  for (u32 i = 0; i < W; i++) note_write(limb(dst + limb_off(N, i)), wave, true, -1, false);
   Op o{};
-  o.kind = OP_MODUP; o.r = out; o.a = in + limb_off(N, st); o.p0 = num_q; o.p1 = part; o.wave = wave;
+  o.kind = OP_MODUP; o.r = dst; o.a = in + limb_off(N, st); o.p0 = num_q; o.p1 = part; o.wave = wave;
   ops_.push_back(o);
-  n_ops++;
+  if (dst == out) n_ops++;
   maybe_flush();
 }
 
 void Scheduler::moddown(u64* out, const u64* in, u32 num_q) {
   const u32 N = c_->N(), W = num_q + (u32)c_->K();
+  materialize(in, W);
   if (live_ + W + num_q + 8 > table_.size() / 2) grow();
   u32 wave = 0;
   for (u32 i = 0; i < W; i++) wave = std::max(wave, dep_read(limb(in + limb_off(N, i)), true));
+  const bool overlap = out + limb_off(N, num_q) > in && out < in + limb_off(N, W);
   for (u32 i = 0; i < num_q; i++) {
     Limb& l = limb(out + limb_off(N, i));
-    kill_if_unread(l);
+    if (!overlap) kill_if_unread(l);  // (in place: what the last op stored there is the input)
     wave = std::max(wave, dep_write(l, true));
   }
   for (u32 i = 0; i < W; i++) note_read(limb(in + limb_off(N, i)), wave, true);
@@ -427,6 +492,7 @@ void Scheduler::moddown(u64* out, const u64* in, u32 num_q) {
 void Scheduler::rescale(u64* out, const u64* in, u32 num_q) {
   const u32 N = c_->N();
   if (num_q < 2) throw std::runtime_error("Rescale: level not enough");
+  materialize(in, num_q);
   if (live_ + 2 * num_q + 8 > table_.size() / 2) grow();
   u32 wave = 0;
   for (u32 i = 0; i < num_q; i++) wave = std::max(wave, dep_read(limb(in + limb_off(N, i)), true));
@@ -537,6 +603,17 @@ void Scheduler::run_chains(std::vector<u32>& idx) {
 }
 
 void Scheduler::flush() {
+  // renamed limbs that are still alive get their data in place: after the window the caller may
+  // read them by other means (the table of renames does not survive the window)
+  if (!aliased_.empty()) {
+    std::vector<u64*> al;
+    al.swap(aliased_);
+    in_flush_ = true;  // the copies recorded below must not re-enter flush()
+    for (u64* q : al) materialize(q, 1);
+    in_flush_ = false;
+  }
+  for (auto& kv : modup_cache_) frees_.push_back(kv.second.buf);
+  modup_cache_.clear();
   if (ops_.empty()) {
     for (u64* p : frees_) c_->free(p);
     frees_.clear();
@@ -606,6 +683,7 @@ void Scheduler::flush() {
   pending_free_bytes_ = 0;
   gen_++;
   live_ = 0;
+  wseq_ = 0;
   if (gen_ == 0) {  // generation counter wrapped: really clear the table
     memset(table_.data(), 0, table_.size() * sizeof(Limb));
     gen_ = 1;

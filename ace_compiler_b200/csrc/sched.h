@@ -21,12 +21,22 @@
 //     when the first use overwrites the limb, the product of `Hw_modmul(tmp, a, b)` that the
 //     next `Hw_modadd(acc, acc, tmp)` consumes (fused to one multiply-add) once tmp is
 //     overwritten or freed, and additions of a limb known to be zero;
-//   * Free_poly_data is deferred until the ops that use the block have been issued.
+//   * Free_poly_data is deferred until the ops that use the block have been issued;
+//   * Decomp_modup results are kept in scheduler-owned buffers and the caller's output limbs are
+//     *renamed* to them (every later read of such a limb is redirected, nothing is copied unless a
+//     multi-limb consumer or the end of the window needs the data in place).  A repeated
+//     Decomp_modup(x, part) of a polynomial that has not been written since -- the nine Rotate()
+//     calls of one convolution input, resnet20_cifar10_pre.onnx.inc:6972-7063, each run their own
+//     ModUp of the same c1 -- is served from the first result: SURVEY 8(f4), the hoisting the
+//     reference's own bootstrap does by hand (ckks_bootstrap_context.c:1284-1299).  Because the
+//     emitted `ext` buffer is never physically written, the digits of one key switch no longer
+//     wait for each other (write-after-read on `ext`) and run as one batch.
 // Every op still computes the same canonical residues from the same operands in an order
 // consistent with program order, so results are bit-identical to call-by-call execution
 // (ACE_B200_EAGER=1 flushes after every call; tests compare the two modes).
 #pragma once
 #include <cstdint>
+#include <map>
 #include <vector>
 
 #include "context.h"
@@ -103,7 +113,9 @@ class Scheduler {
   bool empty() const { return ops_.empty() && frees_.empty(); }
 
   bool   eager = false;  // flush after every call
+  bool   share_modup = true;  // keep and re-use Decomp_modup results (off: write them in place)
   size_t n_flush = 0, n_ops = 0, n_dead = 0, n_fused = 0, n_waves = 0, n_chain_launches = 0;
+  size_t n_modup = 0, n_modup_shared = 0;  // Decomp_modup calls recorded / served from an earlier one
 
  private:
   struct Op {
@@ -126,16 +138,36 @@ class Scheduler {
     u32      w_wave;
     u32      r_wave_chain, r_wave_heavy;
     uint8_t  has_w, w_heavy, has_r_chain, has_r_heavy, read_since, is_zero, w_is_t;
+    u32        w_seq;   // stamp of the last recorded write (0: not written in this window)
+    const u64* alias;   // reads of this limb are served from there (a kept Decomp_modup result)
+  };
+  struct ModupKey {
+    const u64* digit;
+    u32        num_q, part;
+    bool operator<(const ModupKey& o) const {
+      if (digit != o.digit) return digit < o.digit;
+      if (num_q != o.num_q) return num_q < o.num_q;
+      return part < o.part;
+    }
+  };
+  struct ModupEntry {
+    u64* buf;    // [num_q + K] limbs, owned by the scheduler until the end of the window
+    u32  stamp;  // wseq_ when it was recorded: valid while no source limb has a later w_seq
   };
   SchedBackend*       c_;
   std::vector<Op>     ops_;
   std::vector<EncodeJob> enc_jobs_;
   std::vector<u64*>   frees_;
   std::vector<Limb>   table_;
-  u32                 gen_ = 1, mask_ = 0, live_ = 0;
+  u32                 gen_ = 1, mask_ = 0, live_ = 0, wseq_ = 0;
   size_t              pending_free_bytes_ = 0;
+  bool                in_flush_ = false, modup_nohit_ = false;
+  std::map<ModupKey, ModupEntry> modup_cache_;
+  std::vector<u64*>   aliased_;  // limbs that were given an alias in this window
 
   Limb& limb(const u64* addr);
+  const u64* resolve(const u64* a);           // where a read of limb a is served from
+  void  materialize(const u64* p, size_t n);  // bring renamed limbs back in place (block consumers)
   u32   dep_read(Limb& l, bool heavy) const;
   u32   dep_write(Limb& l, bool heavy) const;
   void  note_read(Limb& l, u32 wave, bool heavy);

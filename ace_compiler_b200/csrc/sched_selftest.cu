@@ -38,10 +38,16 @@ struct HostSimBackend : SchedBackend {
     u32 beta = (num_q + kPart - 1) / kPart, st = kPart * part;
     return part == beta - 1 ? num_q - st : kPart;
   }
+  // set by the program before each of ITS allocations; the scheduler's own buffers (kept ModUp
+  // results, only in the deferred run) must not shift the pattern of the program's blocks
+  int64_t next_tag = -1;
   u64* alloc(size_t n) override {
     u64* p = new u64[n * kN];
-    // "uninitialised" memory with reproducible contents: both runs allocate in the same order
-    for (size_t i = 0; i < n * kN; i++) p[i] = (alloc_counter * 977 + i * 31 + 5) % 1000;
+    // "uninitialised" memory with reproducible contents: the program's blocks get the same
+    // pattern in both runs
+    const uint64_t tag = next_tag >= 0 ? (uint64_t)next_tag : 0xABCDEFull;
+    next_tag = -1;
+    for (size_t i = 0; i < n * kN; i++) p[i] = (tag * 977 + i * 31 + 5) % 1000;
     alloc_counter++;
     blocks[p] = n;
     return p;
@@ -153,8 +159,9 @@ struct Rng {
 };
 
 struct Block {
-  u64*   p;
-  size_t n;
+  u64*    p;
+  size_t  n;
+  int64_t id;  // allocation number: addresses are recycled differently in the two runs
 };
 
 // runs the program; returns one hash per synchronisation point
@@ -169,7 +176,13 @@ std::vector<uint64_t> run_program(uint64_t seed, u32 n_ops, u32 sync_permille, b
   int64_t orders[3][kN];
   for (int t = 0; t < 3; t++)
     for (u32 i = 0; i < kN; i++) orders[t][i] = (int64_t)((i * (2 * t + 3) + t) % kN);  // permutations
-  auto new_block = [&](size_t n, bool zeroed) { blk.push_back(Block{S.alloc(n, zeroed), n}); };
+  int64_t n_prog_allocs = 0;
+  auto new_block = [&](size_t n, bool zeroed) {
+    be->next_tag = n_prog_allocs++;
+    blk.push_back(Block{S.alloc(n, zeroed), n, n_prog_allocs - 1});
+  };
+  int64_t last_mu_in = -1;  // the source block of the previous Decomp_modup: repeated now and then
+  u32 last_mu_nq = 0, last_mu_part = 0;
   for (int i = 0; i < 6; i++) new_block(2 + rng.below(9), rng.below(2));
   auto pick = [&](size_t min_limbs) -> int {  // a live block with at least min_limbs, or -1
     for (int tries = 0; tries < 16; tries++) {
@@ -272,7 +285,17 @@ std::vector<uint64_t> run_program(uint64_t seed, u32 n_ops, u32 sync_permille, b
       u32 nq = 1 + rng.below(6);
       int bi = pick(nq), bo = pick(nq + kK);
       u32 part = rng.below((nq + kPart - 1) / kPart);
-      if (bi >= 0 && bo >= 0 && bi != bo) { TR("%u modup %s <- %s nq=%u part=%u\n", op, where(blk[bo].p), where(blk[bi].p), nq, part); S.modup(blk[bo].p, blk[bi].p, nq, part); }
+      if (last_mu_in >= 0 && rng.below(2)) {  // the same digit of the same polynomial again (9 rotations
+                                         // of one convolution input): must see intervening writes
+        for (int b = 0; b < (int)blk.size(); b++)
+          if (blk[b].id == last_mu_in && blk[b].n >= last_mu_nq) { bi = b; nq = last_mu_nq; part = last_mu_part; }
+        bo = pick(nq + kK);
+      }
+      if (bi >= 0 && bo >= 0 && bi != bo) {
+        TR("%u modup %s <- %s nq=%u part=%u\n", op, where(blk[bo].p), where(blk[bi].p), nq, part);
+        S.modup(blk[bo].p, blk[bi].p, nq, part);
+        last_mu_in = blk[bi].id; last_mu_nq = nq; last_mu_part = part;
+      }
     } else if (kind < 90) {  // Mod_down
       u32 nq = 1 + rng.below(6);
       int bi = pick(nq + kK), bo = pick(nq);
@@ -299,6 +322,7 @@ std::vector<uint64_t> run_program(uint64_t seed, u32 n_ops, u32 sync_permille, b
   if (stats) {
     stats[0] = S.n_ops; stats[1] = S.n_flush; stats[2] = S.n_waves; stats[3] = S.n_fused;
     stats[4] = S.n_dead; stats[5] = S.n_chain_launches;
+    stats[6] = S.n_modup; stats[7] = S.n_modup_shared;
   }
   for (const Block& b : blk) S.free(b.p);
   S.flush();
@@ -311,8 +335,9 @@ std::vector<uint64_t> run_program(uint64_t seed, u32 n_ops, u32 sync_permille, b
 // sync_permille: how often the program synchronises (30 = every ~33 ops, 1 = every ~1000, 0 = only
 // at the end: one long deferred window).
 // 0 = deferred execution reproduced call-by-call execution at every synchronisation point;
-// k > 0 = first mismatch at synchronisation point k-1; stats (6 values, may be null) describe the
-// deferred run: ops, flushes, waves, fused mul+add, dropped stores, chain launches
+// k > 0 = first mismatch at synchronisation point k-1; stats (8 values, may be null) describe the
+// deferred run: ops, flushes, waves, fused mul+add, dropped stores, chain launches, Decomp_modup
+// calls, Decomp_modup calls served from an earlier result
 extern "C" __attribute__((visibility("default"))) int ace_sched_selftest(uint64_t seed,
                                                                          uint32_t n_ops,
                                                                          uint32_t sync_permille,

@@ -145,6 +145,18 @@ int ace_bootstrap(ace_ctx* ctx, int64_t* r0, int64_t* r1, uint32_t* out_level, d
 int ace_timer_start(ace_ctx* ctx);
 int ace_timer_stop_ms(ace_ctx* ctx, float* ms);
 
+/* ---- measurement: instruction-rate peaks of the device (csrc/peaks.cu), the roofline denominators
+ *      of the integer-bound kernels (NTT, base conversion).  gops[0..6] = G thread-instructions/s of
+ *      IMAD.WIDE.U32, IMAD (32-bit), IADD3, DFMA, IMAD.WIDE issued 1:1 with IADD3, IMAD.HI.U32,
+ *      IMAD.WIDE issued 1:1 with DFMA.  No reference
+ *      counterpart (the reference reports wall time only, rtlib/include/common/rt_stat.h). */
+int ace_measure_pipe_peaks(int device, double* gops, int n);
+/* G butterflies/s of the NTT's radix-16 register pass with no memory traffic (csrc/ntt16.cu): the
+ * arithmetic ceiling of the transform kernels on this device.  form 0: FP64 butterfly (moduli below
+ * 2^50.4), 1: 64-bit integer lazy butterfly, 2: integer with conditional subtraction (58-61 bit
+ * moduli); < 0 if N != 2^16 or the form is not in use. */
+double ace_ntt_bfly_peak(ace_ctx* ctx, int form, int ctas_per_sm);
+
 #ifdef __cplusplus
 }
 #endif

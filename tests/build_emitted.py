@@ -16,7 +16,7 @@ REF_DS = "/root/reference/fhe-cmplr/rtlib/ant/dataset"
 MODELS = ["resnet20_cifar10_pre", "resnet32_cifar100_pre", "resnet56_cifar10_pre",
           "resnet110_cifar10_train"]
 EXAMPLES = ["add", "add_const", "mul_const", "rotate", "rotate_02", "relin", "relin_02",
-            "gemm", "gemm_02", "conv2d", "avg_pool", "relu"]
+            "gemm", "gemm_02", "conv2d", "avg_pool", "relu", "bootstrap", "bootstrap_02"]
 
 
 def build_all(verbose=False):

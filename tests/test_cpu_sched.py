@@ -30,10 +30,10 @@ def _selftest_lib():
 @pytest.mark.parametrize("seed", range(1, 41))
 def test_deferred_equals_eager_random_program(seed):
     lib = _selftest_lib()
-    stats = (C.c_size_t * 6)()
+    stats = (C.c_size_t * 8)()
     rc = lib.ace_sched_selftest(seed, 6000, 30, stats)
     assert rc == 0, "mismatch at synchronisation point %d (seed %d)" % (rc - 1, seed)
-    ops, flushes, waves, fused, dead, chains = list(stats)
+    ops, flushes, waves, fused, dead, chains, modups, shared = list(stats)
     assert ops >= 6000 and waves >= flushes > 0
 
 
@@ -41,10 +41,12 @@ def test_scheduler_actually_defers():
     """the deferred run must batch (few waves per op), fuse and drop stores -- otherwise the test
     above compares eager with eager"""
     lib = _selftest_lib()
-    stats = (C.c_size_t * 6)()
+    stats = (C.c_size_t * 8)()
     assert lib.ace_sched_selftest(12345, 20000, 30, stats) == 0
-    ops, flushes, waves, fused, dead, chains = list(stats)
+    ops, flushes, waves, fused, dead, chains, modups, shared = list(stats)
     assert waves < ops / 3 and fused > 100 and dead > 100, list(stats)
+    # repeated Decomp_modup calls of an unmodified polynomial are served from the first result
+    assert modups > 500 and shared > 50, list(stats)
 
 
 @pytest.mark.parametrize("seed,sync_permille", [(s, p) for s in range(200, 212) for p in (1, 3)])
@@ -60,6 +62,6 @@ def test_one_window_hits_the_flush_threshold():
     """no synchronisation at all: the scheduler flushes by itself at 2^18 recorded ops, chains are
     longer than one launch, the limb table is rehashed"""
     lib = _selftest_lib()
-    stats = (C.c_size_t * 6)()
+    stats = (C.c_size_t * 8)()
     assert lib.ace_sched_selftest(99, 400000, 0, stats) == 0
     assert stats[1] >= 2  # flushed on its own at least once before the final synchronisation

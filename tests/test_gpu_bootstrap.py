@@ -38,3 +38,26 @@ def test_bootstrap_bit_exact(case):
     sys.stdout.write(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-2000:] + "\n" + r.stderr[-4000:]
     assert "BOOTSTRAP PARITY OK" in r.stdout
+
+
+# RT_BTS_CLEAR_IMAG=1 (rt_env.h:41, used by the reference's accuracy.sh): the final conjugate-and-add
+# branch of Eval_bootstrap (ckks_bootstrap_context.c:1812-1822) instead of the plain integer scaling
+CLEAR_IMAG_CASES = [
+    (1024, 17, 192, 512, 2, 3, 1),   # fully packed
+    (2048, 18, 192, 256, 2, 3, 1),   # sparsely packed
+    (4096, 20, 192, 2048, 3, 5, 0),  # odd+even table
+]
+
+
+@pytest.mark.parametrize("case", CLEAR_IMAG_CASES, ids=lambda c: "N%d_s%d_even%d" % (c[0], c[3], c[6]))
+def test_bootstrap_clear_imag_bit_exact(case):
+    N, depth, hw, slots, lin, lafter, even = case
+    env = dict(os.environ)
+    env["RTLIB_BTS_EVEN_POLY"] = str(even)
+    env["RT_BTS_CLEAR_IMAG"] = "1"
+    r = subprocess.run([sys.executable, os.path.join(HERE, "bootstrap_case.py"), str(N), str(depth),
+                        str(hw), str(slots), str(lin), str(lafter)],
+                       env=env, capture_output=True, text=True, timeout=1500)
+    sys.stdout.write(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-2000:] + "\n" + r.stderr[-4000:]
+    assert "BOOTSTRAP PARITY OK" in r.stdout

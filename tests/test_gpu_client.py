@@ -126,7 +126,7 @@ def test_own_keys_roundtrip():
 
 
 EXAMPLES = ["add", "add_const", "mul_const", "rotate", "rotate_02", "relin", "relin_02",
-            "gemm", "gemm_02", "conv2d", "avg_pool"]
+            "gemm", "gemm_02", "conv2d", "avg_pool", "relu", "bootstrap", "bootstrap_02"]
 
 
 @pytest.mark.parametrize("name", EXAMPLES)
@@ -134,6 +134,6 @@ def test_emitted_example_program(name):
     exe = os.path.join(ROOT, "tests", "_emitted_bin", "eg_" + name)
     if not os.path.exists(exe):
         pytest.skip("emitted example binaries not built (tests/build_emitted.py needs /root/reference)")
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SUCESS!" in r.stdout, r.stdout[-2000:]
