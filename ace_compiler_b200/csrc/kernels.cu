@@ -13,6 +13,8 @@
 // pipe (IMAD), the rest by HBM bandwidth.  No tensor-core path is used.
 #include <cstdio>
 #include <cstdlib>
+#include <stdexcept>
+#include <string>
 
 #include "kernels.cuh"
 #include "prof.h"
@@ -623,30 +625,25 @@ __device__ __forceinline__ void base_conv_fast(const DeviceTables& T, const Conv
   }
 }
 
-// One thread per coefficient and group of kConvOutPerThread output limbs; blockIdx.y =
-// descriptor, blockIdx.z = output group (the scaled inputs are recomputed per group: n_in Shoup
-// products against 8 n_in MACs, and the grid gets enough threads to hide latency).  n_in <= 16 with
-// small moduli takes the exact-size carry-free path above; anything else the generic 128-bit
-// accumulation.
-constexpr u32 kConvOutPerThread = 8;
+// One thread per coefficient; blockIdx.y = descriptor.  The n_in inputs are scaled ONCE (n_in
+// Shoup products) and stay in registers while the thread walks over every output limb; the whole
+// conversion matrix of the descriptor sits in shared memory.  (Round 1 split the outputs over
+// blockIdx.z in groups of 8 and rescaled the inputs in every group: at l = 34 a digit's 12 inputs
+// were scaled 5 times.)  n_in <= 16 with small moduli takes the exact-size carry-free path above;
+// anything else the generic 128-bit accumulation.
 template <int MAXIN>
 __global__ void __launch_bounds__(128) base_conv_kernel(DeviceTables T,
                                                         const __grid_constant__ ConvDescPack P) {
-  extern __shared__ u64 sh_hat[];  // [outputs of this group][n_in]
+  extern __shared__ u64 sh_hat[];  // [n_out][n_in]
   const ConvDesc& D = P.d[blockIdx.y];
-  const u32 n_in = D.n_in;
-  const u32 o_begin = blockIdx.z * kConvOutPerThread;
-  if (o_begin >= D.n_out) return;
-  const u32 o_end = o_begin + kConvOutPerThread < D.n_out ? o_begin + kConvOutPerThread : D.n_out;
-  const u32 n_out = o_end - o_begin;
-  for (u32 i = threadIdx.x; i < n_in * n_out; i += blockDim.x)
-    sh_hat[i] = D.hatmod[(size_t)o_begin * n_in + i];
+  const u32 n_in = D.n_in, n_out = D.n_out;
+  for (u32 i = threadIdx.x; i < n_in * n_out; i += blockDim.x) sh_hat[i] = D.hatmod[i];
   __syncthreads();
   const u32 n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= T.N) return;
   if (MAXIN <= 16 && T.small_moduli) {
     switch (n_in) {
-#define ACE_BC_CASE(k) case k: if (k <= MAXIN) base_conv_fast<(k <= MAXIN ? k : 1)>(T, D, sh_hat, n, o_begin, o_end); return;
+#define ACE_BC_CASE(k) case k: if (k <= MAXIN) base_conv_fast<(k <= MAXIN ? k : 1)>(T, D, sh_hat, n, 0, n_out); return;
       ACE_BC_CASE(1) ACE_BC_CASE(2) ACE_BC_CASE(3) ACE_BC_CASE(4) ACE_BC_CASE(5) ACE_BC_CASE(6)
       ACE_BC_CASE(7) ACE_BC_CASE(8) ACE_BC_CASE(9) ACE_BC_CASE(10) ACE_BC_CASE(11) ACE_BC_CASE(12)
       ACE_BC_CASE(13) ACE_BC_CASE(14) ACE_BC_CASE(15) ACE_BC_CASE(16)
@@ -662,9 +659,9 @@ __global__ void __launch_bounds__(128) base_conv_kernel(DeviceTables T,
       y[i] = mul_shoup(D.x[(size_t)i * T.N + n], D.hatinv[i], D.hatinv_sh[i], q);
     }
   }
-  for (u32 o = o_begin; o < o_end; o++) {
+  for (u32 o = 0; o < n_out; o++) {
     const Modulus m = T.mod[D.g_out[o]];
-    const u64*    h = sh_hat + (o - o_begin) * n_in;
+    const u64*    h = sh_hat + o * n_in;
     u64 lo = 0, hi = 0;
 #pragma unroll
     for (int i = 0; i < MAXIN; i++) {
@@ -689,8 +686,12 @@ void launch_base_conv(const DeviceTables& T, const ConvDesc* descs, u32 n_desc,
     if (descs[i].n_in > max_in) max_in = descs[i].n_in;
     if (descs[i].n_out > max_out) max_out = descs[i].n_out;
   }
-  dim3   grid((T.N + 127) / 128, n_desc, (max_out + kConvOutPerThread - 1) / kConvOutPerThread);
-  size_t shm = (size_t)max_in * kConvOutPerThread * sizeof(u64);
+  // ADVICE (round 1): more than 48 inputs were silently ignored, and the generic 128-bit
+  // accumulation overflows beyond 16 terms of 2^62-sized factors: refuse instead
+  if (max_in > 48 || max_out > 64 || (!T.small_moduli && max_in > 16))
+    throw std::runtime_error("base conversion: unsupported digit size (n_in " + std::to_string(max_in) + ")");
+  dim3   grid((T.N + 127) / 128, n_desc);
+  size_t shm = (size_t)max_in * max_out * sizeof(u64);
   if (max_in <= 4) {
     base_conv_kernel<4><<<grid, 128, shm, s>>>(T, P);
   } else if (max_in <= 12) {

@@ -248,22 +248,24 @@ constexpr int kRowPad  = 17 * 16;  // a 256-coefficient row in shared memory, 1 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 
-// PRE (small batches, one CTA per SM, no register limit): all 30 twiddles of the two passes are
-// loaded up front, in parallel with the coefficients, instead of stage by stage -- a small batch
-// is bound by the latency of its dependent loads, not by throughput.
-#define ACE_TW_DECL typename A::TW twa_[PRE ? 15 : 1], twb_[PRE ? 15 : 1]
+// PRE, bit 0 / bit 1: the 15 twiddles of the first / second pass are loaded up front, in parallel
+// with the coefficients, instead of stage by stage.  The kernels wait on memory, not on the
+// pipes (top stall: long scoreboard), so loads are issued as early as the registers allow: both
+// passes for small batches (one CTA per SM, no register limit), the second pass for the FP64
+// form of large batches (a twiddle is one double there), nothing for the integer form of large
+// batches (60 more registers would cost a resident CTA).
+#define ACE_TW_DECL typename A::TW twa_[(PRE & 1) ? 15 : 1], twb_[(PRE & 2) ? 15 : 1]
 #define ACE_TW_PRELOAD(PTRA, PTRB, NA)                                               \
-  if (PRE) {                                                                         \
-    _Pragma("unroll") for (int i_ = 0; i_ < 4; i_++)                                 \
-      _Pragma("unroll") for (int h_ = 0; h_ < (1 << i_); h_++) {                     \
-        if ((1 << i_) - 1 + h_ >= 15 - (NA)) twa_[(1 << i_) - 1 + h_] = A::ld(PTRA(i_, h_)); \
-        twb_[(1 << i_) - 1 + h_] = A::ld(PTRB(i_, h_));                              \
-      }                                                                              \
-  }
-#define ACE_TW_GET(ARR, PTR, i, h) (PRE ? ARR[(1 << (i)) - 1 + (h)] : A::ld(PTR(i, h)))
+  _Pragma("unroll") for (int i_ = 0; i_ < 4; i_++)                                   \
+    _Pragma("unroll") for (int h_ = 0; h_ < (1 << i_); h_++) {                       \
+      if ((PRE & 1) && (1 << i_) - 1 + h_ >= 15 - (NA)) twa_[(1 << i_) - 1 + h_] = A::ld(PTRA(i_, h_)); \
+      if (PRE & 2) twb_[(1 << i_) - 1 + h_] = A::ld(PTRB(i_, h_));                   \
+    }
+#define ACE_TW_GET_A(PTR, i, h) ((PRE & 1) ? twa_[(1 << (i)) - 1 + (h)] : A::ld(PTR(i, h)))
+#define ACE_TW_GET_B(PTR, i, h) ((PRE & 2) ? twb_[(1 << (i)) - 1 + (h)] : A::ld(PTR(i, h)))
 
 // ---------------- forward K1: stages 0-7 along r, 16 columns per CTA -------------------------
-template <class A, bool PRE>
+template <class A, int PRE>
 __device__ __forceinline__ void fwd_cols_body(const DeviceTables& T, u32 g, u64* sm, const u64* in, u64* out) {
   typedef typename A::E E;
   const typename A::Mod M = A::make(T.mod[g]);
@@ -278,7 +280,7 @@ __device__ __forceinline__ void fwd_cols_body(const DeviceTables& T, u32 g, u64*
   E x[16];
 #pragma unroll
   for (int k = 0; k < 16; k++) x[k] = A::from_canonical(in[(j + 16 * k) * 256 + col], M);
-#define TW_A(i, h) ACE_TW_GET(twa_, PA, i, h)
+#define TW_A(i, h) ACE_TW_GET_A(PA, i, h)
   ACE_R16_FWD(x, TW_A)
 #undef TW_A
 #pragma unroll
@@ -286,7 +288,7 @@ __device__ __forceinline__ void fwd_cols_body(const DeviceTables& T, u32 g, u64*
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 16; k++) x[k] = A::from_mid(sm[(16 * j + k) * 16 + c]);
-#define TW_B(i, h) ACE_TW_GET(twb_, PB, i, h)
+#define TW_B(i, h) ACE_TW_GET_B(PB, i, h)
   ACE_R16_FWD(x, TW_B)
 #undef TW_B
 #undef PA
@@ -296,7 +298,7 @@ __device__ __forceinline__ void fwd_cols_body(const DeviceTables& T, u32 g, u64*
 }
 
 // ---------------- forward K2: stages 8-15 inside a row, 16 rows per CTA ----------------------
-template <class A, bool PRE>
+template <class A, int PRE>
 __device__ __forceinline__ void fwd_rows_body(const DeviceTables& T, u32 g, u64* sm, u64* data) {
   typedef typename A::E E;
   const typename A::Mod M = A::make(T.mod[g]);
@@ -313,7 +315,7 @@ __device__ __forceinline__ void fwd_rows_body(const DeviceTables& T, u32 g, u64*
   E x[16];
 #pragma unroll
   for (int k = 0; k < 16; k++) x[k] = A::from_mid(row[j + 16 * k]);
-#define TW_A(i, h) ACE_TW_GET(twa_, PA, i, h)
+#define TW_A(i, h) ACE_TW_GET_A(PA, i, h)
   ACE_R16_FWD(x, TW_A)
 #undef TW_A
 #pragma unroll
@@ -321,7 +323,7 @@ __device__ __forceinline__ void fwd_rows_body(const DeviceTables& T, u32 g, u64*
   __syncwarp();
 #pragma unroll
   for (int k = 0; k < 16; k++) x[k] = A::from_mid(srow[17 * j + k]);
-#define TW_B(i, h) ACE_TW_GET(twb_, PB, i, h)
+#define TW_B(i, h) ACE_TW_GET_B(PB, i, h)
   ACE_R16_FWD(x, TW_B)
 #undef TW_B
 #undef PA
@@ -333,7 +335,7 @@ __device__ __forceinline__ void fwd_rows_body(const DeviceTables& T, u32 g, u64*
 }
 
 // ---------------- inverse K1: DIT stages m = 1 .. 128 inside a row ---------------------------
-template <class A, bool PRE>
+template <class A, int PRE>
 __device__ __forceinline__ void inv_rows_body(const DeviceTables& T, u32 g, u64* sm, const u64* in, u64* out) {
   typedef typename A::E E;
   const typename A::Mod M = A::make(T.mod[g]);
@@ -353,7 +355,7 @@ __device__ __forceinline__ void inv_rows_body(const DeviceTables& T, u32 g, u64*
     const ulonglong2 v = i2[k];
     x[2 * k] = A::from_canonical(v.x, M); x[2 * k + 1] = A::from_canonical(v.y, M);
   }
-#define TW_A(i, e) ACE_TW_GET(twa_, PA, i, e)
+#define TW_A(i, e) ACE_TW_GET_A(PA, i, e)
   ACE_R16_DIT_HEAD(x, TW_A)
 #undef TW_A
 #pragma unroll
@@ -361,7 +363,7 @@ __device__ __forceinline__ void inv_rows_body(const DeviceTables& T, u32 g, u64*
   __syncwarp();
 #pragma unroll
   for (int k = 0; k < 16; k++) x[k] = A::from_mid(srow[17 * k + j]);
-#define TW_B(i, e) ACE_TW_GET(twb_, PB, i, e)
+#define TW_B(i, e) ACE_TW_GET_B(PB, i, e)
   ACE_R16_DIT(x, TW_B)
 #undef TW_B
 #undef PA
@@ -372,7 +374,7 @@ __device__ __forceinline__ void inv_rows_body(const DeviceTables& T, u32 g, u64*
 }
 
 // ---------------- inverse K2: DIT stages m = 256 .. 32768 along r, then * psi^-n N^-1 ---------
-template <class A, bool PRE>
+template <class A, int PRE>
 __device__ __forceinline__ void inv_cols_body(const DeviceTables& T, u32 g, u64* sm, u64* data) {
   typedef typename A::E E;
   const typename A::Mod M = A::make(T.mod[g]);
@@ -388,7 +390,7 @@ __device__ __forceinline__ void inv_cols_body(const DeviceTables& T, u32 g, u64*
   E x[16];
 #pragma unroll
   for (int k = 0; k < 16; k++) x[k] = A::from_mid(data[(16 * j + k) * 256 + col]);
-#define TW_A(i, e) ACE_TW_GET(twa_, PA, i, e)
+#define TW_A(i, e) ACE_TW_GET_A(PA, i, e)
   ACE_R16_DIT(x, TW_A)
 #undef TW_A
 #pragma unroll
@@ -396,7 +398,7 @@ __device__ __forceinline__ void inv_cols_body(const DeviceTables& T, u32 g, u64*
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 16; k++) x[k] = A::from_mid(sm[(j + 16 * k) * 16 + c]);
-#define TW_B(i, e) ACE_TW_GET(twb_, PB, i, e)
+#define TW_B(i, e) ACE_TW_GET_B(PB, i, e)
   ACE_R16_DIT(x, TW_B)
 #undef TW_B
 #undef PA
@@ -425,14 +427,15 @@ __global__ void __launch_bounds__(kThreads, PRE ? 1 : 3) ntt16_kernel(DeviceTabl
   const int ar = arith_of(T, T.mod[g]);
   const u64* src = b_src(b, limb, 65536);
   u64* dst = b_dst(b, limb, 65536);
-#define ACE_DISPATCH(CALL)                                 \
-  if (ar == 0) { typedef ArithDP A; CALL; }                \
-  else if (ar == 1) { typedef ArithInt<false> A; CALL; }   \
-  else { typedef ArithInt<true> A; CALL; }
-  if (KIND == FWD_COLS) { ACE_DISPATCH((fwd_cols_body<A, PRE>(T, g, sm, src, dst))) }
-  if (KIND == FWD_ROWS) { ACE_DISPATCH((fwd_rows_body<A, PRE>(T, g, sm, dst))) }
-  if (KIND == INV_ROWS) { ACE_DISPATCH((inv_rows_body<A, PRE>(T, g, sm, src, dst))) }
-  if (KIND == INV_COLS) { ACE_DISPATCH((inv_cols_body<A, PRE>(T, g, sm, dst))) }
+  constexpr int PD = PRE ? 3 : 2, PI = PRE ? 3 : 0;  // what is preloaded: FP64 / integer form
+#define ACE_DISPATCH(BODY, ...)                                                  \
+  if (ar == 0) BODY<ArithDP, PD>(__VA_ARGS__);                                   \
+  else if (ar == 1) BODY<ArithInt<false>, PI>(__VA_ARGS__);                      \
+  else BODY<ArithInt<true>, PI>(__VA_ARGS__);
+  if (KIND == FWD_COLS) { ACE_DISPATCH(fwd_cols_body, T, g, sm, src, dst) }
+  if (KIND == FWD_ROWS) { ACE_DISPATCH(fwd_rows_body, T, g, sm, dst) }
+  if (KIND == INV_ROWS) { ACE_DISPATCH(inv_rows_body, T, g, sm, src, dst) }
+  if (KIND == INV_COLS) { ACE_DISPATCH(inv_cols_body, T, g, sm, dst) }
 #undef ACE_DISPATCH
 }
 

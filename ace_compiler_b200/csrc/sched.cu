@@ -14,8 +14,12 @@ namespace ace {
 // ---------------------------------------------------------------------------- kernels
 // one thread per coefficient, blockIdx.y = chain; the items of a chain run in program order.
 // Plain (non-restrict, non-ldg) accesses: a later item may read what an earlier one wrote.
+// (Keeping the last stored value in a register -- the accumulator of consecutive multiply-adds --
+// and dropping stores that a later item of the chain overwrites was measured: 8 % SLOWER, 281 vs
+// 260 ms per two ResNet-20 images; the extra dependences cost more memory-level parallelism than
+// the saved loads give back.  Not kept.)
 __global__ void __launch_bounds__(256) ew_chain_kernel(DeviceTables T,
-                                                       const __grid_constant__ ChainPack P) {
+                                                             const __grid_constant__ ChainPack P) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= T.N) return;
   const u32 k0 = P.chain_start[blockIdx.y], k1 = P.chain_start[blockIdx.y + 1];
@@ -41,16 +45,31 @@ __global__ void __launch_bounds__(256) ew_chain_kernel(DeviceTables T,
   }
 }
 
-// independent gathers (Hw_rotate): blockIdx.y = item, b = the int64 order table
+// independent gathers (Hw_rotate): blockIdx.y = item, b = the int64 order table.  A CTA owns 256
+// consecutive outputs.  For the evaluation-domain tables of Auto_order() their sources form one
+// aligned block of 256 as well (see ksw_inner_rot_kernel, kernels_ext.cu): the block is read
+// coalesced into shared memory and permuted there.  Anything else (coefficient-domain tables,
+// negative entries: number_theory.c:215-224) takes the direct path; the CTA decides by itself.
 __global__ void __launch_bounds__(256) gather_batch_kernel(DeviceTables T,
                                                            const __grid_constant__ ChainPack P) {
+  __shared__ u64     stage[256];
+  __shared__ int64_t first;
   const ChainItem& it    = P.it[blockIdx.y];
   const int64_t*   order = reinterpret_cast<const int64_t*>(it.b);
   const u64        q     = T.mod[it.g].q;
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
-    const int64_t k = order[i];
-    it.r[i] = k >= 0 ? it.a[k] : q - it.a[-k];
+  const u32        i     = blockIdx.x * 256 + threadIdx.x;
+  const bool       in    = i < T.N;
+  const int64_t    k     = in ? order[i] : 0;
+  if (threadIdx.x == 0) first = k;
+  __syncthreads();
+  const bool blocked = T.N % 256 == 0 && __syncthreads_and(k >= 0 && (k >> 8) == (first >> 8));
+  if (blocked) {
+    stage[threadIdx.x] = it.a[(first & ~(int64_t)255) + threadIdx.x];
+    __syncthreads();
+    it.r[i] = stage[k & 255];
+    return;
   }
+  if (in) it.r[i] = k >= 0 ? it.a[k] : q - it.a[-k];
 }
 
 // Deferred frees hold memory: all schedulers of the process (one per host thread that runs

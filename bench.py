@@ -37,25 +37,43 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# BASELINE.json configs 1 and 3-5: the reference's checked-in emitted ResNets (all N = 2^16, 34 Q
+# limbs, 11 P limbs, dnum = 3).  The default (headline) is ResNet-20; --model selects the others.
+MODELS = {
+    "resnet20_cifar10_pre": dict(sf=50, classes=10, bootstraps=19, title="ResNet-20 CIFAR-10"),
+    "resnet32_cifar100_pre": dict(sf=50, classes=100, bootstraps=31, title="ResNet-32 CIFAR-100"),
+    "resnet56_cifar10_pre": dict(sf=50, classes=10, bootstraps=55, title="ResNet-56 CIFAR-10"),
+    "resnet110_cifar10_train": dict(sf=48, classes=10, bootstraps=109, title="ResNet-110 CIFAR-10"),
+}
 MODEL = "resnet20_cifar10_pre"
 N, DEPTH, Q0, SF, PARTS, HW = 65536, 33, 51, 50, 3, 192
 METRIC = "resnet20_cifar10_encrypted_inference_throughput"
 UNIT = "images/s"
-WORKLOAD = ("ResNet-20 CIFAR-10 single-image encrypted inference: ACE-emitted "
-            "resnet20_cifar10_pre.onnx.inc (N=2^16, L=34, K=11, dnum=3, 19 bootstraps), "
-            "synthetic weights/image")
+WORKLOAD = ""
+CLASSES = 10
+
+
+def select_model(name):
+    global MODEL, SF, METRIC, WORKLOAD, CLASSES
+    cfg = MODELS[name]
+    MODEL, SF, CLASSES = name, cfg["sf"], cfg["classes"]
+    METRIC = name.replace("_pre", "").replace("_train", "") + "_encrypted_inference_throughput"
+    WORKLOAD = ("%s single-image encrypted inference: ACE-emitted %s.onnx.inc (N=2^16, L=34, K=11, "
+                "dnum=3, Delta=2^%d, %d bootstraps), synthetic weights/image"
+                % (cfg["title"], name, cfg["sf"], cfg["bootstraps"]))
+
+
+select_model(MODEL)
 TRACE_CLASSES = ["modup_digit", "moddown_poly", "rescale_poly", "encode", "limb_mul", "limb_add",
                  "limb_rot", "limb_ntt"]
 TRACE_LEVELS = 72
 # images in flight per GPU: 3 measured best that fits comfortably (1: 0.93, 2: 1.15, 3: 1.21
 # images/s on one B200); every image in flight has its own stream, allocator cache and deferred frees
 DEFAULT_STREAMS = 3
-# dram__bytes_read.sum + dram__bytes_write.sum of one 45-limb forward NTT (ntt_fwd_strided<4> +
-# ntt_fwd_tile8) from the ncu --set full capture profiles/r1_ncu_full_ntt_v1.csv: 23.6 MB (data)
-# + 70.8 MB (data + 47.2 MB of twiddle tables) read, ~1 MB written back inside the launches (the
-# rest of the 47 MB of results leaves L2 later).  Algorithmic bytes are 47.2 MB: the excess is
-# the per-prime twiddle tables (w and its Shoup companion, 1 MiB per limb).
-NTT_DRAM_TRAFFIC_PER_LAUNCH = 95.4e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one 45-limb forward NTT: taken from the ncu
+# --set full capture summarised in this file (written by tools/ncu_traffic.py from the .ncu-rep);
+# null when no capture of the current kernels has been committed
+NTT_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r2_ncu_ntt_traffic.json")
 
 
 def read_peaks():
@@ -157,6 +175,149 @@ def load_trace(model):
         return json.load(f)["per_image"]
 
 
+# ----------------------------------------------------------------------- kernel rooflines
+def kernel_rooflines(device):
+    """Device timings (CUDA events on the context stream, inputs resident) of the primitives of
+    BASELINE.json config 2 at the model's parameter set, each against the roofline that bounds it:
+    algorithmic bytes / time against the measured HBM peak, and for the
+    integer-bound ones butterflies/s against the measured arithmetic ceiling of the radix-16
+    register pass (ace_ntt_bfly_peak) resp. 64x64-bit MACs/s against the measured IMAD.WIDE rate
+    (ace_measure_pipe_peaks).  Returns (roofline of the dominant kernel, table)."""
+    import ace_compiler_b200 as ace
+    ctx = ace.Context(N, DEPTH, Q0, SF, PARTS, device=device)
+    lib, h = ctx.lib, ctx.h
+    L, K, G = ctx.L, ctx.K, ctx.L + ctx.K
+    NB, LIMB = N * 8, N * 8.0
+    peak, how = read_peaks()
+    rng = np.random.default_rng(7)
+    mods = np.concatenate([ctx.q, ctx.p])
+
+    def rand(gs):
+        return np.stack([rng.integers(0, mods[g], N, dtype=np.int64) for g in gs])
+
+    for is_rot, rot in [(False, 0), (True, 1)]:
+        k0 = np.stack([rand(range(G)) for _ in range(PARTS)])
+        k1 = np.stack([rand(range(G)) for _ in range(PARTS)])
+        ctx.import_switch_key(is_rot, rot, k0, k1)
+
+    def timeit(fn, reps=20, warm=3):
+        for _ in range(warm):
+            fn()
+        ctx.sync()
+        lib.ace_timer_start(h)
+        for _ in range(reps):
+            fn()
+        ms = C.c_float()
+        lib.ace_timer_stop_ms(h, C.byref(ms))
+        return ms.value / reps * 1e3  # us
+
+    pipes = (C.c_double * 7)()
+    lib.ace_measure_pipe_peaks(device, pipes, 7)
+    imad_wide, imad, dfma = pipes[0], pipes[1], pipes[3]
+    ceil = {f: lib.ace_ntt_bfly_peak(h, f, 3) for f in (0, 1, 2)}  # G butterflies/s: fp64, int, int+csub
+    n_fp64 = sum(1 for g in range(L) if ceil[0] > 0 and mods[g] < 1500000000000000)
+    bfly_per_limb = N // 2 * 16
+
+    def bfly_ceiling_s(n_q, n_p):  # seconds the butterflies alone would take at the ceilings
+        fq = min(n_fp64, max(0, n_q - 1)) if n_q else 0  # q_0 is a 51-bit prime: integer form
+        return bfly_per_limb * (fq / (ceil[0] * 1e9) if fq else 0.0) + bfly_per_limb * (
+            (n_q - fq) / (ceil[1] * 1e9) + n_p / (ceil[2] * 1e9))
+
+    # three copies of every operand, used round robin: 3 x 47 MB of limbs + tables do not stay in L2
+    full = ctx.put(rand(list(range(G)) * 3))
+    rows = []
+
+    def add(name, us, alg_limbs, bound, extra=None):
+        gbs = alg_limbs * LIMB / (us * 1e-6) / 1e9
+        row = {"name": name, "us": round(us, 2), "alg_MiB": round(alg_limbs * LIMB / 2**20, 1),
+               "GBps": round(gbs, 1), "hbm_frac": round(gbs / peak, 4), "bound": bound}
+        if extra:
+            row.update(extra)
+        rows.append(row)
+        return row
+
+    cnt = [0]
+
+    def rr():
+        cnt[0] += 1
+        return full.ptr + (cnt[0] % 3) * G * NB
+
+    def int_ntt(us, nq, np_):
+        return {"butterflies_per_s_G": round((nq + np_) * bfly_per_limb / us / 1e3, 1),
+                "arith_ceiling_frac": round(bfly_ceiling_s(nq, np_) / (us * 1e-6), 4)}
+
+    us = timeit(lambda: lib.ace_ntt(h, rr(), 0, G), reps=30, warm=6)
+    ntt_row = add("ntt x%d" % G, us, 2 * G, "int/fp64 pipes", int_ntt(us, L, K))
+    us = timeit(lambda: lib.ace_intt(h, rr(), 0, G), reps=30, warm=6)
+    add("intt x%d" % G, us, 2 * G, "int/fp64 pipes", int_ntt(us, L, K))
+    us = timeit(lambda: lib.ace_ntt(h, rr(), 0, L))
+    add("ntt x%d (Q)" % L, us, 2 * L, "int/fp64 pipes", int_ntt(us, L, 0))
+    us = timeit(lambda: lib.ace_ntt(h, rr() + L * NB, L, K))
+    add("ntt x%d (P)" % K, us, 2 * K, "int pipe", int_ntt(us, 0, K))
+    us = timeit(lambda: lib.ace_ntt(h, rr(), 0, 1))
+    add("ntt x1", us, 2, "latency", int_ntt(us, 1, 0))
+    for lv in (L, (L + 1) // 2):
+        beta = -(-lv // ctx.part_size)
+        a = ctx.put(rand(list(range(lv)) * 2))
+        b = ctx.put(rand(list(range(lv)) * 2))
+        o = ctx.empty(2 * lv)
+        ext = ctx.empty(lv + K, zero=True)
+        e2 = ctx.put(rand(list(range(lv)) + [L + i for i in range(K)]))
+        a0, a1, b0, b1 = a.ptr, a.ptr + lv * NB, b.ptr, b.ptr + lv * NB
+        o0, o1 = o.ptr, o.ptr + lv * NB
+        tag = " L=%d" % lv
+        add("limb_mul x%d%s" % (lv, tag), timeit(lambda: lib.ace_hw_modmul(h, o0, a0, b0, 0, lv)), 3 * lv, "hbm")
+        add("limb_add x%d%s" % (lv, tag), timeit(lambda: lib.ace_hw_modadd(h, o0, a0, b0, 0, lv)), 3 * lv, "hbm")
+        alpha = min(ctx.part_size, lv)
+        us = timeit(lambda: lib.ace_decomp_modup(h, ext.ptr, a0, lv, 0))
+        macs = N * alpha * (lv - alpha + K)
+        add("modup_digit" + tag, us, alpha + lv + K, "int pipe",
+            {"macs_per_s_G": round(macs / us / 1e3, 1), "transforms": alpha + lv - alpha + K})
+        us = timeit(lambda: lib.ace_mod_down(h, o0, e2.ptr, lv))
+        add("moddown_poly" + tag, us, lv + K + lv, "int pipe",
+            {"macs_per_s_G": round(N * K * lv / us / 1e3, 1), "transforms": K + lv})
+        add("rescale_poly" + tag, timeit(lambda: lib.ace_rescale(h, o0, a0, lv)), 2 * lv - 1, "int pipe",
+            {"transforms": lv})
+        ks_limbs = 4 * lv + 2 * beta * (lv + K)
+        add("key_switch" + tag, timeit(lambda: lib.ace_key_switch(h, o0, o1, a1, lv, 0, 0)), ks_limbs,
+            "composite", {"transforms": beta * (lv + K) + 2 * K + 2 * lv})
+        add("ct_rotate" + tag, timeit(lambda: lib.ace_ct_rotate(h, o0, o1, a0, a1, lv, 1)), ks_limbs, "composite")
+        add("ct_mul_relin" + tag, timeit(lambda: lib.ace_ct_mul_relin(h, o0, o1, a0, a1, b0, b1, lv)),
+            ks_limbs + 7 * lv, "composite")
+        add("ct_rescale" + tag, timeit(lambda: lib.ace_ct_rescale(h, o0, o1, a0, a1, lv)), 4 * lv - 2, "int pipe")
+        vals = rng.uniform(-0.05, 0.05, N // 2)
+        pt = ctx.empty(lv)
+        add("encode" + tag, timeit(lambda: lib.ace_encode(h, pt.ptr, vals.ctypes.data_as(C.c_void_p), N // 2, lv,
+                                                            N // 2, 1, 0), reps=5),
+            lv + 0.25, "fp64 + h2d (host message)")
+        for x in (a, b, o, ext, e2, pt):
+            x.free()
+    traffic = None
+    try:
+        traffic = json.load(open(NTT_TRAFFIC_FILE))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    alg_bytes = G * N * 8 * 2
+    roof = {"bound": "hbm", "kernel": "ntt16 forward, K1 cols + K2 rows (%d limbs/launch pair)" % G,
+            "achieved": ntt_row["GBps"], "peak": peak, "peak_source": how, "unit": "GB/s",
+            "frac": ntt_row["hbm_frac"], "traffic": traffic, "alg_bytes_per_launch": alg_bytes,
+            "launch_us": ntt_row["us"],
+            "arith": {"butterflies_per_s_G": ntt_row["butterflies_per_s_G"],
+                      "ceiling_frac": ntt_row["arith_ceiling_frac"],
+                      "ceiling_G_bfly_per_s": {"fp64": round(ceil[0], 1), "int64_lazy": round(ceil[1], 1),
+                                               "int64_csub": round(ceil[2], 1)},
+                      "limbs": {"fp64": n_fp64, "int64_lazy": L - n_fp64, "int64_csub": K},
+                      "pipe_peaks_G_instr_per_s": {"imad_wide_u32": round(imad_wide, 1), "imad": round(imad, 1),
+                                                   "dfma": round(dfma, 1)}},
+            "note": "the transform is bound by the multiply pipes, not by HBM: frac (algorithmic "
+                    "bytes against the measured HBM peak) is reported as the contract asks, "
+                    "arith.ceiling_frac is the fraction of the measured butterfly rate of the "
+                    "radix-16 register pass with no memory traffic (all measured in this run)"}
+    full.free()
+    ctx.close()
+    return roof, rows
+
+
 # --------------------------------------------------------------------------------- ours
 def run_ours(args):
     from ace_compiler_b200.model_runner import EmittedModel, synthetic_image
@@ -173,7 +334,7 @@ def run_ours(args):
     def step_e2e(i):
         m.prepare_input(images[i % len(images)].numpy())
         m.run()
-        return m.handle_output(10)
+        return m.handle_output(CLASSES)
 
     t0 = time.time()
     logits = step_e2e(0)
@@ -183,7 +344,7 @@ def run_ours(args):
     m.timer_start()
     m.run()
     ms_single = m.timer_stop_ms()
-    m.handle_output(10)
+    m.handle_output(CLASSES)
 
     # ---- S images in flight per GPU: S host threads, each with its own stream / allocator /
     # scheduler inside the runtime (the reference's OpenMP-over-images driver); thread 0 is this one
@@ -245,45 +406,11 @@ def run_ours(args):
         print("trace written to", path, file=sys.stderr)
     m.close()
 
-    # ---- roofline of the dominant kernel family: batched forward NTT over all L+K limbs
-    roof = None
+    # ---- rooflines, all measured live: the dominant kernel family (batched forward NTT over all
+    # L+K limbs) and a table over the primitives of BASELINE.json config 2
+    roof, by_kernel = None, None
     if rank == 0:
-        import ace_compiler_b200 as ace
-        ctx = ace.Context(N, DEPTH, Q0, SF, PARTS, device=local)
-        lib, h = ctx.lib, ctx.h
-        G = ctx.L + ctx.K
-        NB = N * 8
-        rng = np.random.default_rng(7)
-        mods = np.concatenate([ctx.q, ctx.p])
-        buf = ctx.put(np.stack([rng.integers(0, mods[g % G], N, dtype=np.int64)
-                                for g in range(3 * G)]))
-        reps = 30
-        for k in range(6):
-            lib.ace_ntt(h, buf.ptr + (k % 3) * G * NB, 0, G)
-        ctx.sync()
-        lib.ace_timer_start(h)
-        for r in range(reps):
-            lib.ace_ntt(h, buf.ptr + (r % 3) * G * NB, 0, G)
-        t = C.c_float()
-        lib.ace_timer_stop_ms(h, C.byref(t))
-        per_launch_s = t.value / reps / 1e3
-        alg_bytes = G * N * 8 * 2  # read + write each limb once (1 MiB per limb)
-        peak, how = read_peaks()
-        ach = alg_bytes / per_launch_s / 1e9
-        roof = {"bound": "hbm", "kernel": "ntt_fwd_strided<4> + ntt_fwd_tile8 (%d limbs/launch)" % G,
-                "achieved": round(ach, 1), "peak": peak, "peak_source": how, "unit": "GB/s",
-                "frac": round(ach / peak, 4), "traffic": NTT_DRAM_TRAFFIC_PER_LAUNCH,
-                "alg_bytes_per_launch": alg_bytes, "launch_us": round(per_launch_s * 1e6, 2),
-                "int_pipe": {"fmaheavy_pct_of_elapsed": 55.1, "alu_pct": 46.6, "issue_active_pct": 50.8,
-                             "top_stall": "math_pipe_throttle",
-                             "source": "profiles/r1_ncu_full_ntt_v1.csv (ntt_fwd_tile8)"},
-                "note": "two passes over each limb (2 MiB moved per 1 MiB algorithmic) plus 1 MiB of "
-                        "per-prime twiddle tables; the 64-bit Shoup butterflies keep the integer "
-                        "multiply pipe busiest (10 IMAD of ~34 instructions per butterfly), so the "
-                        "HBM fraction understates how close the kernel is to its own (integer) "
-                        "roofline; see DESIGN.md section 5 and profiles/"}
-        buf.free()
-        ctx.close()
+        roof, by_kernel = kernel_rooflines(local)
     sampler.join(timeout=2)
 
     total = world * args.steps * S
@@ -311,14 +438,31 @@ def run_ours(args):
     }
     if rank == 0:
         line["roofline"] = roof
+        line["roofline_by_kernel"] = by_kernel
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(trace_to_json(trace), threads=1)
+            base = cpu_baseline(trace_to_json(trace), threads=1)
+            unit_us = base.pop("unit_us")
+            for row in by_kernel:  # the reference's cost of the same primitive on one host core
+                if row["name"] in unit_us:
+                    row["cpu_us"] = round(unit_us[row["name"]], 1)
+                    row["speedup_vs_1_core"] = round(unit_us[row["name"]] / row["us"], 1)
+            line["cpu_baseline"] = base
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------- reference
+def reference_calibration():
+    """composed / real: the composed CPU figure against REAL end-to-end runs of the same emitted unit
+    on the unmodified reference (profiles/r2_reference_real_run.json, written by
+    tools/reference_real_run.py; one entry per host it was run on)"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_reference_real_run.json")))
+    except Exception:
+        return None
+
+
 def _interp(levels, costs, l):
     return float(np.interp(l, levels, costs))
 
@@ -377,11 +521,20 @@ def cpu_baseline(trace, threads):
     if threads > 1:
         f = ref.lib.ref_bench_chain
         f.restype, f.argtypes = _C.c_double, [_C.c_int, _C.c_int, u32, i32]
-        t1 = f(1, 1, 17, 1)
-        tn = f(threads, 1, 17, 1)
+        t1 = f(1, 5, 17, 1)        # 5 iterations per thread: a single one moved the figure by
+        tn = f(threads, 5, 17, 1)  # +-12 % from run to run
         eff = min(1.0, t1 / tn)
+    top = len(levels) - 1
+    unit_us = {"modup_digit L=%d" % levels[top]: 1e6 * unit["modup_digit"][top],
+               "moddown_poly L=%d" % levels[top]: 1e6 * unit["moddown_poly"][top],
+               "rescale_poly L=%d" % levels[top]: 1e6 * unit["rescale_poly"][top],
+               "encode L=%d" % levels[top]: 1e6 * unit["encode"][top],
+               "limb_mul x%d L=%d" % (levels[top], levels[top]): 1e6 * limb["limb_mul"] * levels[top],
+               "limb_add x%d L=%d" % (levels[top], levels[top]): 1e6 * limb["limb_add"] * levels[top],
+               "ntt x%d" % (L + K): 1e6 * limb["limb_ntt"] * (L + K), "ntt x1": 1e6 * limb["limb_ntt"]}
+    calib = reference_calibration()
     return {"value": round(threads * eff / secs, 6), "unit": UNIT, "cores": threads,
-            "kind": "reference",
+            "kind": "reference", "unit_us": unit_us, "composed_over_real": calib,
             "s_per_image_1thread": round(secs, 1), "parallel_efficiency": round(eff, 3),
             "sample": "unit costs of Decomp_modup/Mod_down/Rescale/encode at levels %s and of a limb "
                       "mul/add/rotate/NTT on oracle/_ref (-O3), x the op trace of one image "
@@ -402,6 +555,7 @@ def run_reference(args):
         pass
     t0 = time.time()
     base = cpu_baseline(load_trace(MODEL), threads)
+    base.pop("unit_us", None)
     s_img = base["s_per_image_1thread"]
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -425,9 +579,12 @@ def main():
     ap.add_argument("--streams", type=int, default=DEFAULT_STREAMS,
                     help="images in flight per GPU (host threads, one stream each)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--model", default=MODEL, choices=sorted(MODELS),
+                    help="emitted model (BASELINE.json configs 1, 3-5); default: the headline ResNet-20")
     ap.add_argument("--record-trace", action="store_true",
                     help="write tests/emitted/<model>.trace.json from this run")
     args = ap.parse_args()
+    select_model(args.model)
     if args.impl == "reference":
         run_reference(args)
     else:

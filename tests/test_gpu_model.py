@@ -62,14 +62,7 @@ def test_resnet20_bit_exact():
     _run("exact", timeout=3000)
 
 
-def test_resnet110_bit_exact():
-    """same protocol for the deepest checked-in model (109 bootstraps, Delta = 2^48) when its
-    golden run exists (tests/golden/resnet110_cifar10_train.json: ~3 h of reference CPU time,
-    tests/golden/make_model_golden.py).  With synthetic weights the activations of this model
-    leave the bootstrap's input range (DESIGN.md section 8), i.e. the ciphertext contents are
-    chaotic -- which makes limb-for-limb equality with the reference a sharp test of every
-    primitive at this parameter set."""
-    model = "resnet110_cifar10_train"
+def _bit_exact(model):
     flag = os.environ.get("ACE_MODEL_PARITY")
     if not os.path.exists(os.path.join(HERE, "golden", model + ".json")):
         pytest.skip("no golden run for " + model)
@@ -83,6 +76,25 @@ def test_resnet110_bit_exact():
     sys.stdout.write(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + "\n" + r.stderr[-4000:]
     assert "MODEL PARITY OK" in r.stdout
+
+
+def test_resnet110_bit_exact():
+    """same protocol for the deepest checked-in model (109 bootstraps, Delta = 2^48) when its
+    golden run exists (tests/golden/resnet110_cifar10_train.json: ~3 h of reference CPU time,
+    tests/golden/make_model_golden.py).  With synthetic weights the activations of this model
+    leave the bootstrap's input range (DESIGN.md section 8), i.e. the ciphertext contents are
+    chaotic -- which makes limb-for-limb equality with the reference a sharp test of every
+    primitive at this parameter set."""
+    _bit_exact("resnet110_cifar10_train")
+
+
+@pytest.mark.parametrize("model", ["resnet32_cifar100_pre", "resnet56_cifar10_pre"])
+def test_resnet32_56_bit_exact(model):
+    """BASELINE.json configs 3 and 4: output ciphertext SHA-256 against the golden run of the
+    compiled, unmodified reference (tests/golden/<model>.json; 2 582 s and ~5 000 s of reference
+    CPU time on this container, tests/golden/make_model_golden.py): 298 rotation keys and 100
+    classes for ResNet-32 / CIFAR-100, 55 bootstraps for ResNet-56."""
+    _bit_exact(model)
 
 
 def _driver_logits(env_extra, model=MODEL, n_classes=10):

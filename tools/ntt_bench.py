@@ -38,7 +38,7 @@ def main():
     t_q = timeit(lambda: lib.ace_ntt(h, d.ptr, 0, ctx.L))
     t_p = timeit(lambda: lib.ace_ntt(h, d.ptr + ctx.L * N * 8, ctx.L, ctx.K))
     small = []
-    for n in (1, 2, 4, 8, 16, 24):
+    for n in (1, 2, 4, 8, 9, 10, 16, 18, 19, 24, 27, 28, 30, 33):
         small.append("x%d %.1f/%.1f" % (n, timeit(lambda: lib.ace_ntt(h, d.ptr, 0, n)), timeit(lambda: lib.ace_intt(h, d.ptr, 0, n))))
     print("small batches (ntt/intt us): " + "  ".join(small))
     d2 = ctx.put(x)
