@@ -73,6 +73,19 @@ SIGNATURES = {
     "ace_bootstrap": (C.c_int, [vp, vp, vp, C.POINTER(u32), C.POINTER(C.c_double), C.POINTER(u32),
                                 vp, vp, u32, u32, C.c_double, u32, u32]),
     "ace_measure_pipe_peaks": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.c_int]),
+    "ace_keygen_reference": (C.c_int, [vp, vp, C.c_uint64, u32, vp, sz]),
+    "ace_keygen_autos": (C.c_int, [vp, vp, sz]),
+    "ace_sk_export": (C.c_int, [vp, vp]),
+    "ace_pk_export": (C.c_int, [vp, vp, vp]),
+    "ace_swk_export": (C.c_int, [vp, C.c_int, u32, u32, C.c_int, vp]),
+    "ace_keys_save": (C.c_int, [vp, C.c_char_p, C.c_int]),
+    "ace_keys_load": (C.c_int, [vp, C.c_char_p]),
+    "ace_ct_save": (C.c_int, [vp, C.c_char_p, vp, vp, u32, u32, u32, C.c_double]),
+    "ace_ct_load": (C.c_int, [vp, C.c_char_p, vp, vp, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_double)]),
+    "ace_refrng_words": (None, [vp, C.c_uint64, vp, sz]),
+    "ace_refrng_uniform": (None, [vp, C.c_uint64, vp, sz, C.c_uint64]),
+    "ace_refrng_ternary": (None, [vp, C.c_uint64, vp, sz, C.c_int64]),
+    "ace_refrng_triangle": (None, [u32, vp, sz]),
     "ace_ntt_bfly_peak": (C.c_double, [vp, C.c_int, C.c_int]),
     "ace_timer_start": (C.c_int, [vp]),
     "ace_timer_stop_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
@@ -321,6 +334,54 @@ class Context:
     def keygen(self, seed, rots):
         r = (i32 * max(1, len(rots)))(*rots)
         self._ck(self.lib.ace_keygen(self.h, seed, r, len(rots)))
+
+    def keygen_reference(self, seed16, counter, tri_base, rots):
+        """the reference's own generators, consumed in its order: bit-identical keys
+        (ckks_key_generator.c:13-37; csrc/refrng.h)"""
+        sd = (C.c_uint32 * 16)(*[int(x) & 0xFFFFFFFF for x in seed16])
+        r = (C.c_int32 * max(1, len(rots)))(*rots)
+        self._ck(self.lib.ace_keygen_reference(self.h, sd, counter, tri_base, r, len(rots)))
+
+    def keygen_autos(self, autos):
+        """more switch keys by automorphism index on the current stream (Bootstrap_keygen)"""
+        a = (C.c_uint32 * max(1, len(autos)))(*autos)
+        self._ck(self.lib.ace_keygen_autos(self.h, a, len(autos)))
+
+    def export_secret_key(self):
+        s = np.empty((self.L + self.K, self.N), np.int64)
+        self._ck(self.lib.ace_sk_export(self.h, _hp(s)))
+        return s
+
+    def export_public_key(self):
+        p0, p1 = np.empty((self.L, self.N), np.int64), np.empty((self.L, self.N), np.int64)
+        self._ck(self.lib.ace_pk_export(self.h, _hp(p0), _hp(p1)))
+        return p0, p1
+
+    def export_switch_key(self, is_rot, auto_idx=0):
+        """(parts, L+K, N) key0, key1 -- the layout of import_switch_key"""
+        k0 = np.empty((self.parts, self.L + self.K, self.N), np.int64)
+        k1 = np.empty_like(k0)
+        for part in range(self.parts):
+            self._ck(self.lib.ace_swk_export(self.h, int(is_rot), auto_idx, part, 0, _hp(k0[part])))
+            self._ck(self.lib.ace_swk_export(self.h, int(is_rot), auto_idx, part, 1, _hp(k1[part])))
+        return k0, k1
+
+    def save_keys(self, path, with_secret=False):
+        self._ck(self.lib.ace_keys_save(self.h, path.encode(), int(with_secret)))
+
+    def load_keys(self, path):
+        self._ck(self.lib.ace_keys_load(self.h, path.encode()))
+
+    def save_ct(self, path, c0, c1, level, slots, sf_degree, scale):
+        self._ck(self.lib.ace_ct_save(self.h, path.encode(), c0, c1, level, slots, sf_degree, scale))
+
+    def load_ct(self, path, max_level):
+        """returns (DevPoly holding c0 | c1 at max_level stride, level, slots, sf_degree, scale)"""
+        d = self.empty(2 * max_level)
+        lv, sl, sfd, sc = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_double()
+        self._ck(self.lib.ace_ct_load(self.h, path.encode(), d.ptr, d.ptr + max_level * self.N * 8, max_level,
+                                      C.byref(lv), C.byref(sl), C.byref(sfd), C.byref(sc)))
+        return d, lv.value, sl.value, sfd.value, sc.value
 
     def import_secret_key(self, sk):
         sk = np.ascontiguousarray(sk, dtype=np.int64)

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libace_b200.so")
 SELFTEST_LIB = os.path.join(HERE, "libace_b200_selftest.so")
-SOURCES = ["kernels.cu", "ntt16.cu", "kernels_ext.cu", "context.cu", "client.cu",
+SOURCES = ["kernels.cu", "ntt16.cu", "kernels_ext.cu", "context.cu", "client.cu", "keyfile.cu",
            "evaluator.cu", "chebyshev.cu", "bootstrap.cu", "sched.cu", "batch.cu", "prof.cu", "peaks.cu",
            "capi.cu", "rt_shim.cu"]
 SELFTEST_SOURCES = ["sched_selftest.cu"]

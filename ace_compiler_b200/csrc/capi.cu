@@ -7,6 +7,7 @@
 
 #include "../../include/ace_b200.h"
 #include "evaluator.h"
+#include "refrng.h"
 
 using namespace ace;
 
@@ -281,10 +282,42 @@ size_t ace_bootstrap_fft_diagonals(uint32_t slots, uint32_t level_budget, int fl
   return Evaluator::fft_diagonals(slots, level_budget, flag != 0, encoding != 0, out);
 }
 int ace_keygen_rotations(ace_ctx* ctx, uint64_t seed, const int32_t* rots, size_t n) {
-  ACE_TRY(for (size_t i = 0; i < n; i++) {
-    u32 k = ctx->c->auto_index(rots[i]);
-    if (!ctx->c->has_rot_key(k)) ctx->c->gen_auto_key(k, seed + i);
-  })
+  ACE_TRY((void)seed;  // the stream is the context's (ace_keygen / ace_keygen_reference)
+          ctx->c->keygen_rotations(rots, n))
+}
+int ace_keygen_reference(ace_ctx* ctx, const uint32_t* seed16, uint64_t counter, uint32_t tri_base,
+                         const int32_t* rots, size_t n) {
+  ACE_TRY(ctx->c->keygen_reference(seed16, counter, tri_base, rots, n))
+}
+int ace_keygen_autos(ace_ctx* ctx, const uint32_t* auto_idx, size_t n) {
+  ACE_TRY(for (size_t i = 0; i < n; i++)
+            if (!ctx->c->has_rot_key(auto_idx[i])) ctx->c->gen_auto_key(auto_idx[i]);)
+}
+int ace_sk_export(ace_ctx* ctx, int64_t* host_sk_ntt_qp) {
+  ACE_TRY(if (!ctx->c->sk_ntt) throw std::runtime_error("secret key missing");
+          ctx->c->download(U(host_sk_ntt_qp), ctx->c->sk_ntt, ctx->c->G))
+}
+int ace_pk_export(ace_ctx* ctx, int64_t* host_pk0, int64_t* host_pk1) {
+  ACE_TRY(if (!ctx->c->pk0) throw std::runtime_error("public key missing");
+          ctx->c->download(U(host_pk0), ctx->c->pk0, ctx->c->L);
+          ctx->c->download(U(host_pk1), ctx->c->pk1, ctx->c->L))
+}
+int ace_swk_export(ace_ctx* ctx, int is_rot, uint32_t auto_idx, uint32_t part, int which, int64_t* host_poly) {
+  ACE_TRY(if (is_rot && !ctx->c->has_rot_key(auto_idx)) throw std::runtime_error("no such rotation key");
+          SwitchKey& k = is_rot ? ctx->c->rot_key(auto_idx) : ctx->c->relin_key;
+          if (!k.k0 || part >= ctx->c->dnum) throw std::runtime_error("switch key missing");
+          const size_t per = ctx->c->G * (size_t)ctx->c->N;
+          ctx->c->download(U(host_poly), (which ? k.k1 : k.k0) + part * per, ctx->c->G))
+}
+int ace_keys_save(ace_ctx* ctx, const char* path, int with_secret) { ACE_TRY(ctx->c->save_keys(path, with_secret != 0)) }
+int ace_keys_load(ace_ctx* ctx, const char* path) { ACE_TRY(ctx->c->load_keys(path)) }
+int ace_ct_save(ace_ctx* ctx, const char* path, const int64_t* c0, const int64_t* c1, uint32_t level,
+                uint32_t slots, uint32_t sf_degree, double scale) {
+  ACE_TRY(check_level(ctx->c, level); ctx->c->save_ct(path, U(c0), U(c1), level, slots, sf_degree, scale))
+}
+int ace_ct_load(ace_ctx* ctx, const char* path, int64_t* c0, int64_t* c1, uint32_t max_level, uint32_t* level,
+                uint32_t* slots, uint32_t* sf_degree, double* scale) {
+  ACE_TRY(ctx->c->load_ct(path, U(c0), U(c1), max_level, level, slots, sf_degree, scale))
 }
 int ace_bootstrap(ace_ctx* ctx, int64_t* r0, int64_t* r1, uint32_t* out_level, double* out_scale,
                   uint32_t* out_sf_degree, const int64_t* c0, const int64_t* c1, uint32_t level,
@@ -294,6 +327,26 @@ int ace_bootstrap(ace_ctx* ctx, int64_t* r0, int64_t* r1, uint32_t* out_level, d
                  sf_degree, [&](Ct& o, Ct& i) { ctx->ev->bootstrap(o, i, level_after_bts); }))
 }
 
+void ace_refrng_words(const uint32_t* seed16, uint64_t counter, uint32_t* out, size_t n) {
+  refrng::Blake2Prng g;
+  g.pin(seed16, counter);
+  for (size_t i = 0; i < n; i++) out[i] = g.next();
+}
+void ace_refrng_uniform(const uint32_t* seed16, uint64_t counter, int64_t* out, size_t n, uint64_t bound) {
+  refrng::Blake2Prng g;
+  g.pin(seed16, counter);
+  g.sample_uniform(out, n, bound);
+}
+void ace_refrng_ternary(const uint32_t* seed16, uint64_t counter, int64_t* out, size_t n, int64_t hw) {
+  refrng::Blake2Prng g;
+  g.pin(seed16, counter);
+  g.sample_ternary(out, n, hw);
+}
+void ace_refrng_triangle(uint32_t seed, int64_t* out, size_t n) {
+  refrng::GlibcRandom g;
+  g.srandom(seed);
+  g.sample_triangle(out, n);
+}
 double ace_ntt_bfly_peak(ace_ctx* ctx, int form, int ctas_per_sm) {
   if (!ctx || !ntt16_usable(ctx->c->T)) return -1.0;
   cudaSetDevice(ctx->c->device);

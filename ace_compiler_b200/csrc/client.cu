@@ -1,7 +1,8 @@
 // client.cu -- key generation, encryption/decryption and CKKS encode/decode for the B200
-// runtime.  Arithmetic runs on the GPU with the kernels of kernels.cu; sampling uses a
-// counter-based generator (NOT the reference's BLAKE2/rand() streams: keys produced here are
-// valid but not bit-identical to the reference's -- parity runs import the oracle's keys).
+// runtime.  Arithmetic runs on the GPU with the kernels of kernels.cu.  Sampling: by default
+// ChaCha20 keyed from the operating system's entropy (keys are valid, not the reference's);
+// keygen_reference() consumes the reference's own BLAKE2Xb / rand() streams (refrng.h) in the
+// reference's order and reproduces its keys and encryptions bit for bit from the same seeds.
 //
 // Reference routines followed (paths under fhe-cmplr/rtlib/ant/):
 //   keys       src/util/ckks_key_generator.c:69-336, src/util/polynomial.c:1349-1412
@@ -12,41 +13,78 @@
 #include <cmath>
 #include <complex>
 #include <cstring>
-#include <random>
+#include <sys/random.h>
+
+#include <thread>
 
 #include "context.h"
+#include "refrng.h"
 #include "prof.h"
 #include "host_math.h"
 
 namespace ace {
 
 // ------------------------------------------------------------------------------ sampling
-__device__ __forceinline__ u64 mix64(u64 x) {  // splitmix64 finaliser
-  x += 0x9e3779b97f4a7c15ull;
-  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
-  x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
-  return x ^ (x >> 31);
+// Default sampler: ChaCha20 (RFC 8439 block function) as a counter-based generator.  The 256-bit
+// key comes from the operating system (getrandom) unless the caller pins a seed (tests); every
+// sample is addressed by (purpose, key id, digit, limb, coefficient) in the nonce / counter words,
+// so streams of different keys, digits and encryptions never overlap (domain separation instead
+// of seed arithmetic).  One 64-byte block per coefficient: 8 64-bit candidates for rejection
+// sampling below the largest multiple of q (bias-free; all 8 rejected: probability < 2^-100).
+// The reference's own generators (BLAKE2Xb + rand(), refrng.h) are used by keygen_reference().
+enum : u32 { kPurposeUniform = 1, kPurposeError = 2, kPurposeEncU = 3, kPurposeEncE1 = 4, kPurposeEncE2 = 5 };
+
+struct ChaChaKey { u32 k[8]; };
+
+__host__ __device__ __forceinline__ u32 rotl32(u32 x, int n) { return (x << n) | (x >> (32 - n)); }
+__host__ __device__ inline void chacha20_block(const u32 (&key)[8], u32 counter, u32 n0, u32 n1, u32 n2,
+                                               u32 (&out)[16]) {
+  u32 st[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3],
+                key[4], key[5], key[6], key[7], counter, n0, n1, n2};
+  u32 x[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) x[i] = st[i];
+#define ACE_QR(a, b, c, d)                                   \
+  x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 16); x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 12); \
+  x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 8);  x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 7);
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    ACE_QR(0, 4, 8, 12) ACE_QR(1, 5, 9, 13) ACE_QR(2, 6, 10, 14) ACE_QR(3, 7, 11, 15)
+    ACE_QR(0, 5, 10, 15) ACE_QR(1, 6, 11, 12) ACE_QR(2, 7, 8, 13) ACE_QR(3, 4, 9, 14)
+  }
+#undef ACE_QR
+#pragma unroll
+  for (int i = 0; i < 16; i++) out[i] = x[i] + st[i];
 }
 
-// uniform residues: limb l (modulus g[l]) gets floor(r * q / 2^64), r a 64-bit hash
-__global__ void uniform_kernel(DeviceTables T, LimbBatch b, u64 seed) {
-  const u32 limb = blockIdx.y;
-  const u64 q    = T.mod[b.g[limb]].q;
-  u64*      out  = b.base + (size_t)b.slot[limb] * T.N;
+// uniform residues of limb l (modulus g[l]): nonce = (purpose | digit << 8 | limb << 16, id_lo, id_hi)
+__global__ void uniform_kernel(DeviceTables T, LimbBatch b, ChaChaKey key, u32 digit, u64 id) {
+  const u32     limb = blockIdx.y;
+  const Modulus m    = T.mod[b.g[limb]];
+  u64*          out  = b.base + (size_t)b.slot[limb] * T.N;
+  const u64     lim  = 0 - m.c64;  // 2^64 - (2^64 mod q): the largest multiple of q below 2^64
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
-    u64 r  = mix64(mix64(seed + limb) ^ (u64)i);
-    out[i] = __umul64hi(r, q);
+    u32 w[16];
+    chacha20_block(key.k, i, kPurposeUniform | (digit << 8) | (limb << 16), (u32)id, (u32)(id >> 32), w);
+    u64 x = ((u64)w[1] << 32) | w[0];
+#pragma unroll
+    for (int c = 1; c < 8; c++)
+      if (x >= lim) x = ((u64)w[2 * c + 1] << 32) | w[2 * c];
+    u64 r = x - __umul64hi(x, m.mu_hi) * m.q;
+    out[i] = r >= m.q ? r - m.q : r;
   }
 }
 
 // "triangle" samples (random_sample.c:78-97): -1, +1 with probability 1/4 each, else 0;
 // the same small coefficient is written to every limb of the batch (Transform_values_to_rns)
-__global__ void triangle_kernel(DeviceTables T, LimbBatch b, u64 seed) {
+__global__ void triangle_kernel(DeviceTables T, LimbBatch b, ChaChaKey key, u32 purpose, u32 digit, u64 id) {
   const u32 limb = blockIdx.y;
   const u64 q    = T.mod[b.g[limb]].q;
   u64*      out  = b.base + (size_t)b.slot[limb] * T.N;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
-    u64 r  = mix64(seed ^ ((u64)i << 20)) & 3;
+    u32 w[16];
+    chacha20_block(key.k, i, purpose | (digit << 8), (u32)id, (u32)(id >> 32), w);
+    const u32 r = w[0] & 3;
     out[i] = r == 0 ? q - 1 : (r == 1 ? 1 : 0);
   }
 }
@@ -87,29 +125,141 @@ static LimbBatch all_limbs(u64* base, u32 g0, u32 n) {
 
 static dim3 grid_for(u32 N, u32 n) { return dim3((N + 255) / 256, n); }
 
-void Context::gen_secret_key(u64 seed) {
-  std::mt19937_64 rng(seed);
+// ---------------------------------------------------------------------------- generator state
+// secure mode: key = 256 bits from the OS (or expanded from a pinned test seed);
+// reference mode: the reference's own streams (refrng.h), consumed in the reference's order
+struct Context::RngState {
+  ChaChaKey          key;
+  bool               reference = false;
+  refrng::BulkPrng   prng;           // reference mode: BLAKE2Xb stream (uniform, ternary)
+  u32                tri_base = 0;   // reference mode: Sample_triangle call k draws from
+  u32                tri_calls = 0;  //   glibc random() after srandom(tri_base + k)
+  std::vector<int64_t> host;         // staging for host-sampled values
+};
+
+void refrng::BulkPrng::refill() {
+  words.resize(kBatch * 1024);
+  const unsigned nt = std::max(1u, std::min(threads, std::thread::hardware_concurrency()));
+  std::vector<std::thread> pool;
+  const uint64_t c0 = counter;
+  for (unsigned t = 0; t < nt; t++)
+    pool.emplace_back([this, t, nt, c0] {
+      for (size_t k = t; k < kBatch; k += nt) {
+        const uint64_t c = c0 + k;
+        uint8_t in[8];
+        for (int i = 0; i < 8; i++) in[i] = (uint8_t)(c >> (8 * i));
+        blake2xb(reinterpret_cast<uint8_t*>(words.data() + k * 1024), 4096, in, 8,
+                 reinterpret_cast<const uint8_t*>(seed), 64);
+      }
+    });
+  for (auto& th : pool) th.join();
+  counter += kBatch;
+  pos = 0;
+}
+
+Context::RngState* Context::rng() {
+  if (!rng_) {
+    rng_ = std::make_shared<RngState>();
+    if (getrandom(rng_->key.k, sizeof(rng_->key.k), 0) != (ssize_t)sizeof(rng_->key.k))
+      throw std::runtime_error("getrandom failed: no entropy for key generation");
+  }
+  return rng_.get();
+}
+
+// TEST ONLY: a reproducible key stream.  Anyone who knows the seed can regenerate every key.
+void Context::rng_seed_for_tests(u64 seed) {
+  if (!rng_) rng_ = std::make_shared<RngState>();
+  const u32 k0[8] = {(u32)seed, (u32)(seed >> 32), 0x6b657973u, 0x65656421u, 0, 0, 0, 0};
+  u32 w[16];
+  chacha20_block(k0, 0, 0, 0, 0, w);
+  for (int i = 0; i < 8; i++) rng_->key.k[i] = w[i];
+  rng_->reference = false;
+}
+
+// the reference's generators from pinned seeds (what the test harness pins on the reference side)
+void Context::rng_pin_reference(const u32* seed16, u64 counter, u32 tri_base) {
+  if (!rng_) rng_ = std::make_shared<RngState>();
+  rng_->reference = true;
+  rng_->prng.pin(seed16, counter);
+  rng_->tri_base = tri_base;
+  rng_->tri_calls = 0;
+}
+
+// ---- the two samplers behind every key / encryption ------------------------------------------
+// n_limbs uniform limbs (moduli g0 ..) at dst: Sample_uniform_poly (polynomial.c:1349-1372)
+void Context::sample_uniform(u64* dst, u32 g0, u32 n_limbs, u32 digit, u64 id) {
+  RngState* R = rng();
+  LimbBatch b = all_limbs(dst, g0, n_limbs);
+  if (!R->reference) {
+    uniform_kernel<<<grid_for(N, n_limbs), 256, 0, stream>>>(T, b, R->key, digit, id);
+    return;
+  }
+  R->host.resize((size_t)n_limbs * N);
+  for (u32 l = 0; l < n_limbs; l++) R->prng.sample_uniform(R->host.data() + (size_t)l * N, N, mod[g0 + l]);
+  h2d_sync(dst, R->host.data(), (size_t)n_limbs * N * sizeof(u64));
+}
+
+// one triangle polynomial, its residues written to n_limbs limbs at dst (coefficient form):
+// Sample_triangle + Transform_values_to_qbase / _qpbase (ckks_key_generator.c:93-96, 173-174)
+void Context::sample_triangle(u64* dst, u32 g0, u32 n_limbs, u32 purpose, u32 digit, u64 id) {
+  RngState* R = rng();
+  LimbBatch b = all_limbs(dst, g0, n_limbs);
+  if (!R->reference) {
+    triangle_kernel<<<grid_for(N, n_limbs), 256, 0, stream>>>(T, b, R->key, purpose, digit, id);
+    return;
+  }
+  R->host.resize(N);
+  refrng::GlibcRandom g;
+  g.srandom(R->tri_base + R->tri_calls++);
+  g.sample_triangle(R->host.data(), N);
+  small_to_rns(dst, g0, n_limbs, R->host.data());
+}
+
+void Context::small_to_rns(u64* dst, u32 g0, u32 n_limbs, const int64_t* host_small) {
+  int64_t* dv = nullptr;
+  ACE_CUDA(cudaMallocAsync(&dv, N * sizeof(int64_t), stream));
+  h2d_sync(dv, host_small, N * sizeof(int64_t));
+  LimbBatch b = all_limbs(dst, g0, n_limbs);
+  small_to_rns_kernel<<<grid_for(N, n_limbs), 256, 0, stream>>>(T, b, dv);
+  ACE_CUDA(cudaFreeAsync(dv, stream));
+}
+
+// Generate_secret_key (ckks_key_generator.c:69-82): ternary s (Sample_ternary_poly), NTT
+void Context::gen_secret_key() {
+  RngState* R = rng();
   std::vector<int64_t> s(N, 0);
   size_t hw = params.hamming_weight;
-  if (hw == 0) {  // uniform ternary (random_sample.c:127-131)
-    for (auto& x : s) x = (int64_t)(rng() % 3) - 1;
+  if (R->reference) {
+    R->prng.sample_ternary(s.data(), N, (int64_t)hw);
   } else {
-    if (hw > N) hw = N;
-    size_t placed = 0;
-    while (placed < hw) {
-      size_t idx = rng() % N;
-      if (s[idx] == 0) { s[idx] = (rng() & 1) ? 1 : -1; placed++; }
+    // host-side draw from the ChaCha20 stream (purpose 0): same distribution as Sample_ternary
+    u32 w[16];
+    u32 blk = 0, at = 16;
+    auto next = [&]() -> u32 {
+      if (at == 16) { chacha20_block(R->key.k, blk++, 0, 0x736b, 0, w); at = 0; }
+      return w[at++];
+    };
+    auto below = [&](u32 n) -> u32 {  // unbiased
+      const u32 lim = 0xFFFFFFFFu - 0xFFFFFFFFu % n;
+      u32 x;
+      do x = next(); while (x >= lim);
+      return x % n;
+    };
+    if (hw == 0) {  // uniform ternary (random_sample.c:127-131)
+      for (auto& x : s) x = (int64_t)below(3) - 1;
+    } else {
+      if (hw > N) hw = N;
+      size_t placed = 0;
+      while (placed < hw) {
+        const size_t idx = below(N);
+        if (s[idx] == 0) { s[idx] = (next() & 1) ? 1 : -1; placed++; }
+      }
     }
   }
-  int64_t* dv = nullptr;
-  ACE_CUDA(cudaMalloc(&dv, N * sizeof(int64_t)));
-  h2d_sync(dv, s.data(), N * sizeof(int64_t));
   if (!sk_ntt) ACE_CUDA(cudaMalloc(&sk_ntt, G * (size_t)N * sizeof(u64)));
-  LimbBatch b = all_limbs(sk_ntt, 0, (u32)G);
-  small_to_rns_kernel<<<grid_for(N, (u32)G), 256, 0, stream>>>(T, b, dv);
+  small_to_rns(sk_ntt, 0, (u32)G, s.data());
   ntt(sk_ntt, 0, (u32)G);
   sync();
-  cudaFree(dv);
 }
 
 void Context::import_secret_key(const u64* host_ntt_qp) {
@@ -124,15 +274,14 @@ void Context::import_public_key(const u64* h0, const u64* h1) {
   h2d_sync(pk1, h1, L * (size_t)N * sizeof(u64));
 }
 
-// pk = (-a s + e, a) over Q  (ckks_key_generator.c:84-125)
-void Context::gen_public_key(u64 seed) {
+// pk = (-a s + e, a) over Q  (ckks_key_generator.c:84-125; e is drawn before a)
+void Context::gen_public_key() {
   if (!sk_ntt) throw std::runtime_error("secret key missing");
   if (!pk0) ACE_CUDA(cudaMalloc(&pk0, L * (size_t)N * sizeof(u64)));
   if (!pk1) ACE_CUDA(cudaMalloc(&pk1, L * (size_t)N * sizeof(u64)));
   u64* e = alloc_limbs(L, false);
-  LimbBatch ba = all_limbs(pk1, 0, (u32)L), be = all_limbs(e, 0, (u32)L);
-  uniform_kernel<<<grid_for(N, (u32)L), 256, 0, stream>>>(T, ba, seed * 3 + 1);
-  triangle_kernel<<<grid_for(N, (u32)L), 256, 0, stream>>>(T, be, seed * 3 + 2);
+  sample_triangle(e, 0, (u32)L, kPurposeError, 0, /*id*/ 1);
+  sample_uniform(pk1, 0, (u32)L, 0, /*id*/ 1);
   ntt(e, 0, (u32)L);
   launch_ew(T, EW_MUL, pk0, pk1, sk_ntt, 0, (u32)L, stream);
   launch_ew(T, EW_SUB, pk0, e, pk0, 0, (u32)L, stream);
@@ -142,7 +291,8 @@ void Context::gen_public_key(u64 seed) {
 
 // Generate_switching_key (ckks_key_generator.c:127-200): for every digit j
 //   a_j uniform over Q u P,  b_j = e_j + [P]_q * new_key (digit limbs only) - a_j * old_key
-void Context::gen_switch_key(SwitchKey& key, const u64* new_key, const u64* old_key, u64 seed) {
+// id: what the key is for (2 = relinearisation, 2^32 + automorphism index = rotation)
+void Context::gen_switch_key(SwitchKey& key, const u64* new_key, const u64* old_key, u64 id) {
   const size_t per = G * (size_t)N;
   if (!key.k0) ACE_CUDA(cudaMalloc(&key.k0, dnum * per * sizeof(u64)));
   if (!key.k1) ACE_CUDA(cudaMalloc(&key.k1, dnum * per * sizeof(u64)));
@@ -153,10 +303,9 @@ void Context::gen_switch_key(SwitchKey& key, const u64* new_key, const u64* old_
   for (size_t j = 0; j < dnum; j++) {
     u64* a = key.k1 + j * per;
     u64* b = key.k0 + j * per;
-    LimbBatch ba = all_limbs(a, 0, (u32)G), be = all_limbs(e, 0, (u32)G),
-              bb = all_limbs(b, 0, (u32)G);
-    uniform_kernel<<<grid_for(N, (u32)G), 256, 0, stream>>>(T, ba, seed * 1000003 + 2 * j);
-    triangle_kernel<<<grid_for(N, (u32)G), 256, 0, stream>>>(T, be, seed * 1000003 + 2 * j + 1);
+    LimbBatch bb = all_limbs(b, 0, (u32)G);
+    sample_uniform(a, 0, (u32)G, (u32)j, id);
+    sample_triangle(e, 0, (u32)G, kPurposeError, (u32)j, id);
     ntt(e, 0, (u32)G);
     for (size_t g = 0; g < G; g++) {
       fac[g] = 0;
@@ -175,10 +324,10 @@ void Context::gen_switch_key(SwitchKey& key, const u64* new_key, const u64* old_
   cudaFree(dfac);
 }
 
-void Context::gen_relin_key(u64 seed) {  // new = s^2, old = s (ckks_key_generator.c:203-215)
+void Context::gen_relin_key() {  // new = s^2, old = s (ckks_key_generator.c:203-215)
   u64* s2 = alloc_limbs(G, false);
   launch_ew(T, EW_MUL, s2, sk_ntt, sk_ntt, 0, (u32)G, stream);
-  gen_switch_key(relin_key, s2, sk_ntt, seed);
+  gen_switch_key(relin_key, s2, sk_ntt, /*id*/ 2);
   free_limbs(s2);
 }
 
@@ -188,39 +337,67 @@ static u64 inv_mod_pow2(u64 a, u64 M) {  // odd a, M a power of two
   return x & (M - 1);
 }
 
-// "fast" rotation key for automorphism index k (ckks_key_generator.c:237-264):
+// "fast" rotation key for automorphism index k (ckks_key_generator.c:237-264; the conjugation
+// key of Generate_conj_key, :217-235, is k = 2N - 1):
 // old key = sigma_{k^-1}(s), new key = s, so that the automorphism is applied after the switch
-void Context::gen_auto_key(u32 k, u64 seed) {
+void Context::gen_auto_key(u32 k) {
   const u64 M = 2 * (u64)N;
   u32 kinv = (u32)inv_mod_pow2(k, M);
   const int64_t* order = auto_order(kinv);
   u64* rot = alloc_limbs(G, false);
   launch_gather(T, rot, sk_ntt, order, 0, (u32)G, stream);
-  gen_switch_key(rot_keys_[k], sk_ntt, rot, seed);
+  gen_switch_key(rot_keys_[k], sk_ntt, rot, ((u64)1 << 32) | k);
   free_limbs(rot);
 }
 
+// Alloc_ckks_key_generator (ckks_key_generator.c:13-37): secret, public, relinearisation key,
+// then the rotation keys in the order given (Generate_rot_maps skips repeated indices)
 void Context::keygen(u64 seed, const int32_t* rots, size_t n_rots) {
   ACE_CUDA(cudaSetDevice(device));
-  gen_secret_key(seed);
-  gen_public_key(seed + 1);
-  gen_relin_key(seed + 2);
+  if (seed != 0) rng_seed_for_tests(seed);  // 0: the operating system's entropy
+  gen_secret_key();
+  gen_public_key();
+  gen_relin_key();
+  keygen_rotations(rots, n_rots);
+}
+
+// Generate_rot_maps (ckks_key_generator.c:288-336).  The reference remembers ROTATION VALUES, not
+// automorphism indices: a second rotation value with the same automorphism (k and k + N/2, e.g.
+// -2 and slots-2 of the bootstrap's list) generates the key again and replaces the first one.
+// In reference mode this is reproduced (the streams must advance identically); otherwise a key
+// that exists is kept.
+void Context::keygen_rotations(const int32_t* rots, size_t n_rots) {
+  const bool ref_mode = rng()->reference;
   for (size_t i = 0; i < n_rots; i++) {
-    u32 k = auto_index(rots[i]);
-    if (!has_rot_key(k)) gen_auto_key(k, seed + 3 + i);
+    const u32 k = auto_index(rots[i]);
+    if (ref_mode) {
+      if (ref_rot_seen_.insert(rots[i]).second) gen_auto_key(k);
+    } else if (!has_rot_key(k)) {
+      gen_auto_key(k);
+    }
   }
 }
 
-// Encrypt_msg (ckks_encryptor.c:20-95): c0 = pk0 u + e1 + m, c1 = pk1 u + e2
-void Context::encrypt(u64* c0, u64* c1, const u64* pt, u32 level, u64 seed) {
+void Context::keygen_reference(const u32* seed16, u64 counter, u32 tri_base, const int32_t* rots,
+                               size_t n_rots) {
+  ACE_CUDA(cudaSetDevice(device));
+  rng_pin_reference(seed16, counter, tri_base);
+  ref_rot_seen_.clear();
+  gen_secret_key();
+  gen_public_key();
+  gen_relin_key();
+  keygen_rotations(rots, n_rots);
+}
+
+// Encrypt_msg (ckks_encryptor.c:20-95): c0 = pk0 u + e1 + m, c1 = pk1 u + e2; u, e1, e2 are
+// three triangle draws in this order.  id: unique per encryption (the caller counts).
+void Context::encrypt(u64* c0, u64* c1, const u64* pt, u32 level, u64 id) {
   if (!pk0) throw std::runtime_error("public key missing");
   u64* t = alloc_limbs(3 * (size_t)level, false);
   u64 *u = t, *e1 = t + (size_t)level * N, *e2 = t + 2 * (size_t)level * N;
-  LimbBatch bu = all_limbs(u, 0, level), b1 = all_limbs(e1, 0, level),
-            b2 = all_limbs(e2, 0, level);
-  triangle_kernel<<<grid_for(N, level), 256, 0, stream>>>(T, bu, seed * 7 + 1);
-  triangle_kernel<<<grid_for(N, level), 256, 0, stream>>>(T, b1, seed * 7 + 2);
-  triangle_kernel<<<grid_for(N, level), 256, 0, stream>>>(T, b2, seed * 7 + 3);
+  sample_triangle(u, 0, level, kPurposeEncU, 0, id);
+  sample_triangle(e1, 0, level, kPurposeEncE1, 0, id);
+  sample_triangle(e2, 0, level, kPurposeEncE2, 0, id);
   ntt(t, 0, level);
   ntt(e1, 0, level);
   ntt(e2, 0, level);

@@ -9,6 +9,8 @@
 
 #include <complex>
 #include <map>
+#include <set>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -157,15 +159,38 @@ class Context {
   u64* sk_ntt = nullptr;  // [G][N] secret key, NTT form over Q then P
   u64* pk0    = nullptr;  // [L][N]
   u64* pk1    = nullptr;  // [L][N]
+  // seed == 0: keys from the operating system's entropy (getrandom); anything else pins a
+  // reproducible stream and is for tests only.  Sampling: ChaCha20, domain-separated per key,
+  // digit and encryption (client.cu).
   void keygen(u64 seed, const int32_t* rots, size_t n_rots);
-  void gen_secret_key(u64 seed);
-  void gen_public_key(u64 seed);
-  void gen_relin_key(u64 seed);
-  void gen_auto_key(u32 auto_idx, u64 seed);
-  void gen_switch_key(SwitchKey& key, const u64* new_key, const u64* old_key, u64 seed);
+  // the reference's own generators (BLAKE2Xb PRNG + glibc rand(), refrng.h) consumed in the
+  // reference's order: the keys are bit-identical to the reference's from the same seeds
+  void keygen_reference(const u32* seed16, u64 counter, u32 tri_base, const int32_t* rots, size_t n_rots);
+  void keygen_rotations(const int32_t* rots, size_t n_rots);
+  std::set<int32_t> ref_rot_seen_;  // reference mode: rotation values that have a key (Generate_rot_maps)
+  void gen_secret_key();
+  void gen_public_key();
+  void gen_relin_key();
+  void gen_auto_key(u32 auto_idx);
+  void gen_switch_key(SwitchKey& key, const u64* new_key, const u64* old_key, u64 id);
+  struct RngState;
+  std::shared_ptr<RngState> rng_;  // shared with worker contexts
+  RngState* rng();
+  void rng_seed_for_tests(u64 seed);
+  void rng_pin_reference(const u32* seed16, u64 counter, u32 tri_base);
+  void sample_uniform(u64* dst, u32 g0, u32 n_limbs, u32 digit, u64 id);
+  void sample_triangle(u64* dst, u32 g0, u32 n_limbs, u32 purpose, u32 digit, u64 id);
+  void small_to_rns(u64* dst, u32 g0, u32 n_limbs, const int64_t* host_small);
   void import_secret_key(const u64* host_ntt_qp);
   void import_public_key(const u64* host_pk0, const u64* host_pk1);
-  void encrypt(u64* c0, u64* c1, const u64* pt, u32 level, u64 seed);
+  void encrypt(u64* c0, u64* c1, const u64* pt, u32 level, u64 id);  // id: unique per encryption
+  // key / ciphertext files (keyfile.cu)
+  void save_keys(const char* path, bool with_secret);
+  void load_keys(const char* path);
+  void save_ct(const char* path, const u64* c0, const u64* c1, u32 level, u32 slots, u32 sf_degree,
+               double scale);
+  void load_ct(const char* path, u64* c0, u64* c1, u32 max_level, u32* level, u32* slots,
+               u32* sf_degree, double* scale);
   void decrypt(u64* pt, const u64* c0, const u64* c1, u32 level);
   void encode(u64* out, const double* vals, size_t len, u32 level, u32 slots, u32 sf_degree,
               u32 p_cnt);

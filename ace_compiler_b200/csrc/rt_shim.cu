@@ -18,6 +18,7 @@
 #include <cstring>
 #include <ctime>
 #include <map>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -61,7 +62,7 @@ thread_local Evaluator* g_ev     = nullptr;
 thread_local Scheduler* g_queue  = nullptr;  // deferred execution of the polynomial-level API
 MODULUS*  g_mod    = nullptr;  // [G] Q then P, contiguous like the reference's arrays
 int       g_device = 0;
-thread_local uint64_t g_enc_seed = 1;
+std::atomic<uint64_t> g_enc_id{1};  // one id per encryption, process-wide (ChaCha20 nonce, client.cu)
 thread_local std::map<std::string, CIPHERTEXT*> g_inputs, g_outputs;
 std::map<u32, SWITCH_KEY*> g_swk;  // by automorphism index; 0 = relin key (guarded by g_mu)
 std::mutex g_mu;
@@ -149,7 +150,6 @@ void attach_worker() {
   g_ev    = new Evaluator(w, g_primary_ev);
   g_queue = new Scheduler(w);
   g_queue->eager = g_eager;
-  g_enc_seed = 1000003ull * (g_workers.size() + 1) + 1;
   g_workers.push_back(Worker{g_ctx, g_ev, g_queue});
 }
 Context* ctx_nf() {
@@ -262,15 +262,15 @@ void init_cipher(CIPHERTEXT* res, CIPHERTEXT* ciph, double sc, uint32_t deg) {  
 
 // Bootstrap_keygen (ckks_bootstrap_context.c:1194-1226): rotation keys of the linear
 // transforms plus the conjugation key (automorphism index 2N-1)
-void bootstrap_keygen(u32 slots, u64 seed) {
+void bootstrap_keygen(u32 slots) {
   Context* c = g_ctx;
   std::vector<int32_t> rots = g_ev->bootstrap_rot_indices(slots);
   for (size_t i = 0; i < rots.size(); i++) {
     u32 k = c->auto_index(rots[i]);
-    if (!c->has_rot_key(k)) c->gen_auto_key(k, seed + 100000 + i + slots);
+    if (!c->has_rot_key(k)) c->gen_auto_key(k);
   }
   u32 conj = 2 * c->N - 1;
-  if (!c->has_rot_key(conj)) c->gen_auto_key(conj, seed + 99999);
+  if (!c->has_rot_key(conj)) c->gen_auto_key(conj);
 }
 
 u32 mod_index(MODULUS* m) {
@@ -397,13 +397,16 @@ API void Prepare_context(void) {
     g_queue->eager = g_eager;
     const char* no_keys = getenv("ACE_B200_NO_KEYGEN");  // parity runs import the oracle's keys
     const bool  own_keys = !(no_keys && no_keys[0] == '1');
+    // keys come from the operating system's entropy (getrandom -> ChaCha20, client.cu), as the
+    // reference seeds its PRNG from /dev/urandom and the clock (prng.c:28-84).  ACE_B200_SEED
+    // pins a reproducible stream: TESTS ONLY -- whoever knows the seed can regenerate the keys.
     const char* seed_env = getenv("ACE_B200_SEED");
-    const u64   seed = seed_env ? strtoull(seed_env, nullptr, 10) : 20251017ull;
+    const u64   seed = seed_env ? strtoull(seed_env, nullptr, 10) : 0;
     if (own_keys) g_ctx->keygen(seed, p->_rot_idxs, p->_num_rot_idx);
     // Bootstrap_precom(N/2) (context.c:80-82, 162-185): plaintext tables + bootstrap keys
     if (g_ev->bootstrap_supported()) {
       g_ev->bootstrap_setup(g_ctx->N / 2);
-      if (own_keys) bootstrap_keygen(g_ctx->N / 2, seed);
+      if (own_keys) bootstrap_keygen(g_ctx->N / 2);
     }
   });
   if (Get_rt_data_info) {
@@ -485,7 +488,7 @@ API void Prepare_input(TENSOR* input, const char* name) {
     alloc_poly_data(&ct->_c0_poly, c->N, c->L, 0);
     alloc_poly_data(&ct->_c1_poly, c->N, c->L, 0);
     ctx();  // the recorded zero fills go first
-    c->encrypt(U(ct->_c0_poly._data), U(ct->_c1_poly._data), pt, (u32)c->L, g_enc_seed++);
+    c->encrypt(U(ct->_c0_poly._data), U(ct->_c1_poly._data), pt, (u32)c->L, g_enc_id.fetch_add(1));
     c->free_limbs(pt);
   });
   ct->_c0_poly._is_ntt = ct->_c1_poly._is_ntt = true;
@@ -967,7 +970,7 @@ API CIPHER Encrypt(CIPHER res, PLAIN plain) {  // cipher_eval.c:406-409
   init_poly(&res->_c0_poly, &plain->_poly);
   init_poly(&res->_c1_poly, &plain->_poly);
   ctx();  // issue what was recorded for these blocks (zero fills) before launching directly
-  guard([&] { c->encrypt(U(res->_c0_poly._data), U(res->_c1_poly._data), U(plain->_poly._data), level, g_enc_seed++); });
+  guard([&] { c->encrypt(U(res->_c0_poly._data), U(res->_c1_poly._data), U(plain->_poly._data), level, g_enc_id.fetch_add(1)); });
   res->_c0_poly._is_ntt = res->_c1_poly._is_ntt = true;
   return res;
 }
@@ -990,10 +993,7 @@ API CIPHER Bootstrap(CIPHER res, CIPHER ciph, uint32_t level_after_bts) {
     in.nq = (u32)ciph->_c0_poly._num_primes; in.np = 0; in.cap = in.nq;
     in.sf = ciph->_scaling_factor; in.sfd = ciph->_sf_degree; in.slots = ciph->_slots;
     const bool own_keys = !(getenv("ACE_B200_NO_KEYGEN") && getenv("ACE_B200_NO_KEYGEN")[0] == '1');
-    if (own_keys && in.slots != c->N / 2) {  // Bootstrap_precom(num_slots) on first use
-      const char* seed_env = getenv("ACE_B200_SEED");
-      bootstrap_keygen(in.slots, seed_env ? strtoull(seed_env, nullptr, 10) : 20251017ull);
-    }
+    if (own_keys && in.slots != c->N / 2) bootstrap_keygen(in.slots);  // Bootstrap_precom(num_slots) on first use
     Ct out;
     g_ev->bootstrap(out, in, level_after_bts);
     if (res != ciph) { free_poly_data(&res->_c0_poly); free_poly_data(&res->_c1_poly); }

@@ -92,7 +92,10 @@ int ace_ct_mul_relin(ace_ctx* ctx, int64_t* r0, int64_t* r1, const int64_t* a0, 
 int ace_ct_rescale(ace_ctx* ctx, int64_t* r0, int64_t* r1, const int64_t* c0, const int64_t* c1, uint32_t num_q);
 
 /* ---- client side: keys, encryption, CKKS encode/decode.
- *      keygen:  Alloc_ckks_key_generator (ant/src/util/ckks_key_generator.c:13-37): secret,
+ *      keygen:  seed == 0: entropy from the operating system (getrandom -> ChaCha20 streams,
+ *               domain-separated per key / digit / encryption); seed != 0 pins a reproducible
+ *               stream, TESTS ONLY.  ace_encrypt's last argument is a per-encryption id.
+ *               Alloc_ckks_key_generator (ant/src/util/ckks_key_generator.c:13-37): secret,
  *               public, relinearisation key and one rotation key per index.  Sampling uses the
  *               runtime's own generator (valid keys, not bit-identical to the reference's).
  *      import:  take the reference's keys instead (parity runs).
@@ -144,6 +147,41 @@ int ace_bootstrap(ace_ctx* ctx, int64_t* r0, int64_t* r1, uint32_t* out_level, d
 /* ---- timing helpers for the benchmark: CUDA events on the context's stream */
 int ace_timer_start(ace_ctx* ctx);
 int ace_timer_stop_ms(ace_ctx* ctx, float* ms);
+
+/* ---- exact key generation: the reference's generators (BLAKE2Xb PRNG seed words + counter,
+ *      prng.h:30-60; the k-th Sample_triangle draws from glibc rand() after srandom(tri_base + k))
+ *      consumed in the reference's order (Alloc_ckks_key_generator, ckks_key_generator.c:13-37):
+ *      secret, public, relinearisation key, rotation keys of rot_idxs.  Keys and later
+ *      ace_encrypt results are bit-identical to the reference's from the same seeds
+ *      (tests/test_gpu_keygen.py).  ace_keygen_autos continues the current stream for more
+ *      automorphism indices (Bootstrap_keygen: rotation keys, then 2N-1 = conjugation).
+ *      export: the counterparts of ace_sk_import / ace_pk_import / ace_swk_import. */
+int ace_keygen_reference(ace_ctx* ctx, const uint32_t* seed16, uint64_t counter, uint32_t tri_base,
+                         const int32_t* rot_idxs, size_t num_rot_idx);
+int ace_keygen_autos(ace_ctx* ctx, const uint32_t* auto_idx, size_t n);
+int ace_sk_export(ace_ctx* ctx, int64_t* host_sk_ntt_qp);
+int ace_pk_export(ace_ctx* ctx, int64_t* host_pk0, int64_t* host_pk1);
+int ace_swk_export(ace_ctx* ctx, int is_rot, uint32_t auto_idx, uint32_t part, int which, int64_t* host_poly);
+
+/* ---- key and ciphertext files (the reference has no serialisation).  Little-endian,
+ *      magic "ACEB200K" / "ACEB200C", version, the parameter set (N, L, K, dnum, every modulus: a
+ *      file only loads into a context with the same primes), then the limbs as stored in HBM.
+ *      with_secret = 0 writes the evaluation side only (public, relinearisation, rotation keys). */
+int ace_keys_save(ace_ctx* ctx, const char* path, int with_secret);
+int ace_keys_load(ace_ctx* ctx, const char* path);
+int ace_ct_save(ace_ctx* ctx, const char* path, const int64_t* c0, const int64_t* c1, uint32_t level,
+                uint32_t slots, uint32_t sf_degree, double scale);
+int ace_ct_load(ace_ctx* ctx, const char* path, int64_t* c0, int64_t* c1, uint32_t max_level, uint32_t* level,
+                uint32_t* slots, uint32_t* sf_degree, double* scale);
+
+/* ---- the reference's random sources restated on the host (csrc/refrng.h; no GPU needed): the
+ *      BLAKE2Xb word stream of prng.h:42-60 for a given seed (16 words) and counter; Sample_uniform,
+ *      Sample_ternary (random_sample.c:38-76, 99-152) on that stream; Sample_triangle (:78-97) on
+ *      glibc's rand() after srandom(seed).  Used by the exact key generation (ace_keygen_reference). */
+void ace_refrng_words(const uint32_t* seed16, uint64_t counter, uint32_t* out, size_t n);
+void ace_refrng_uniform(const uint32_t* seed16, uint64_t counter, int64_t* out, size_t n, uint64_t bound);
+void ace_refrng_ternary(const uint32_t* seed16, uint64_t counter, int64_t* out, size_t n, int64_t hamming_weight);
+void ace_refrng_triangle(uint32_t seed, int64_t* out, size_t n);
 
 /* ---- measurement: instruction-rate peaks of the device (csrc/peaks.cu), the roofline denominators
  *      of the integer-bound kernels (NTT, base conversion).  gops[0..6] = G thread-instructions/s of

@@ -35,14 +35,49 @@
 #include "util/crt.h"
 #include "util/ntt.h"
 #include "util/prng.h"
+#include "util/random_sample.h"
 
 /* ---- pinned randomness ------------------------------------------------- */
-void srand(unsigned seed) { (void)seed; } /* swallow srand(time) */
+/* mode 0 (default, what every golden vector was made with): srand() is swallowed, rand() keeps
+ * running from srandom(12345) -- its position then depends on every rand() call of the library,
+ * Is_prime's 200 trials per FMT_ASSERT included (number_theory.c:160-185).
+ * mode 1 (exact key generation tests): the k-th Sample_triangle of the run draws from
+ * srandom(Tri_base + k), i.e. a function of its own call number only.  Sample_triangle reaches
+ * srand through Srand_time() = gettimeofday() + srand() (random_sample.c:20-24), Is_prime
+ * through time() + srand(): the two wrappers below tell the callers apart.  Both return the
+ * real time (clock_gettime); mode 0 behaves exactly as before. */
+#include <time.h>
+#include <sys/time.h>
+static int      Pin_mode = 0, Srand_after_tod = 0;
+static uint32_t Tri_base = 0, Tri_count = 0;
+__attribute__((visibility("hidden"))) int gettimeofday(struct timeval* tv, void* tz) {
+  struct timespec ts;
+  (void)tz;
+  clock_gettime(CLOCK_REALTIME, &ts);
+  if (tv) { tv->tv_sec = ts.tv_sec; tv->tv_usec = ts.tv_nsec / 1000; }
+  Srand_after_tod = 1;
+  return 0;
+}
+__attribute__((visibility("hidden"))) time_t time(time_t* t) {
+  struct timespec ts;
+  clock_gettime(CLOCK_REALTIME, &ts);
+  if (t) *t = ts.tv_sec;
+  Srand_after_tod = 0;
+  return ts.tv_sec;
+}
+void srand(unsigned seed) { /* swallow srand(time) */
+  (void)seed;
+  if (Pin_mode == 1 && Srand_after_tod) srandom(Tri_base + Tri_count++);
+  Srand_after_tod = 0;
+}
+void ref_pin_mode(int mode, uint32_t tri_base) { Pin_mode = mode; Tri_base = tri_base; Tri_count = 0; }
+uint32_t ref_triangle_calls(void) { return Tri_count; }
 
 extern BLAKE2_PRNG* Prng;
 BLAKE2_PRNG*        Alloc_blake2_prng();
 
 static void Pin_random(void) {
+  Tri_count = 0;
   srandom(12345u);
   if (Prng == NULL) Prng = Alloc_blake2_prng();
   for (uint32_t i = 0; i < SEED_CNT; i++) {
@@ -549,6 +584,48 @@ size_t ref_coeff_collapse(uint32_t slots, uint32_t budget, int flag, int encodin
   Free_value_list(rot_group);
   Free_value_list(ksi_pows);
   return n;
+}
+
+/* ---- the raw random sources (tests of the runtime's restatement, csrc/refrng.h) ---------- */
+void ref_prng_words(const uint32_t* seed16, uint64_t counter, uint32_t* out, size_t n) {
+  BLAKE2_PRNG* saved = Prng;
+  Prng = Alloc_blake2_prng();
+  for (uint32_t i = 0; i < SEED_CNT; i++) Set_ui32_value(Prng->_seed, i, seed16[i]);
+  Prng->_counter = counter;
+  Prng->_buffer_idx = 0;
+  for (size_t i = 0; i < n; i++) out[i] = Get_prng_value(Prng);
+  Prng = saved;
+}
+void ref_sample_uniform(const uint32_t* seed16, uint64_t counter, int64_t* out, size_t n, uint64_t bound) {
+  BLAKE2_PRNG* saved = Prng;
+  Prng = Alloc_blake2_prng();
+  for (uint32_t i = 0; i < SEED_CNT; i++) Set_ui32_value(Prng->_seed, i, seed16[i]);
+  Prng->_counter = counter;
+  Prng->_buffer_idx = 0;
+  VALUE_LIST v;
+  Init_i64_value_list_no_copy(&v, n, out);
+  Sample_uniform(&v, bound);
+  Prng = saved;
+}
+void ref_sample_ternary(const uint32_t* seed16, uint64_t counter, int64_t* out, size_t n, int64_t hw) {
+  BLAKE2_PRNG* saved = Prng;
+  Prng = Alloc_blake2_prng();
+  for (uint32_t i = 0; i < SEED_CNT; i++) Set_ui32_value(Prng->_seed, i, seed16[i]);
+  Prng->_counter = counter;
+  Prng->_buffer_idx = 0;
+  VALUE_LIST v;
+  Init_i64_value_list_no_copy(&v, n, out);
+  Sample_ternary(&v, hw);
+  Prng = saved;
+}
+void ref_sample_triangle(uint32_t seed, int64_t* out, size_t n) { /* what mode 1 gives call k: seed = base + k */
+  int saved = Pin_mode;
+  Pin_mode  = 0;
+  srandom(seed);
+  VALUE_LIST v;
+  Init_i64_value_list_no_copy(&v, n, out);
+  Sample_triangle(&v);
+  Pin_mode = saved;
 }
 
 /* ---- CPU baseline: the chain HMult+relin -> rescale -> rotate on independent ciphertexts,
