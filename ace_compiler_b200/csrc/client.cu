@@ -346,7 +346,7 @@ void Context::gen_auto_key(u32 k) {
   const int64_t* order = auto_order(kinv);
   u64* rot = alloc_limbs(G, false);
   launch_gather(T, rot, sk_ntt, order, 0, (u32)G, stream);
-  gen_switch_key(rot_keys_[k], sk_ntt, rot, ((u64)1 << 32) | k);
+  gen_switch_key(rot_key(k), sk_ntt, rot, ((u64)1 << 32) | k);
   free_limbs(rot);
 }
 

@@ -33,7 +33,18 @@ Tp* Context::to_device(const std::vector<Tp>& v) {
   return d;
 }
 
+template <typename Tp>
+Tp* Context::to_device_shared(const std::vector<Tp>& v) {  // caller holds sh_->mu
+  Tp* d = nullptr;
+  dev_malloc(&d, v.size() * sizeof(Tp) + 16);
+  h2d_sync(d, v.data(), v.size() * sizeof(Tp));
+  sh_->owned.push_back(d);
+  return d;
+}
+
 Context::Context(const Params& p, int dev) : params(p), device(dev) {
+  sh_ = std::make_shared<Shared>();
+  sh_->device = dev;
   if (p.degree < 16 || (p.degree & (p.degree - 1)) || p.degree > (1u << 17))
     throw std::runtime_error("degree must be a power of two in [16, 2^17]");
   if (p.num_q_parts == 0) throw std::runtime_error("num_q_parts must be > 0");
@@ -270,11 +281,17 @@ Context::Context(const Params& p, int dev) : params(p), device(dev) {
   negqlinv_sh_ = to_device(nq_sh);
 }
 
+Context::Shared::~Shared() {
+  cudaSetDevice(device);
+  for (auto& kv : rot_keys) { cudaFree(kv.second.k0); cudaFree(kv.second.k1); }
+  for (auto& kv : auto_orders) cudaFree(kv.second);
+  for (void* p : owned) cudaFree(p);
+}
+
 Context::~Context() {
   cudaSetDevice(device);
   cudaStreamSynchronize(stream);
   if (!worker_) {
-    for (auto& kv : rot_keys_) { cudaFree(kv.second.k0); cudaFree(kv.second.k1); }
     cudaFree(relin_key.k0);
     cudaFree(relin_key.k1);
     cudaFree(sk_ntt); cudaFree(pk0); cudaFree(pk1);
@@ -282,13 +299,10 @@ Context::~Context() {
   }
   cudaFree(enc_buf_); cudaFree(enc_pow_);
   if (enc_host_) cudaFreeHost(enc_host_);
-  for (auto& kv : auto_orders_)
-    if (std::find(inherited_orders_.begin(), inherited_orders_.end(), (const void*)kv.second) ==
-        inherited_orders_.end())
-      cudaFree(kv.second);
-  for (size_t i = owned_inherited_; i < owned_.size(); i++) cudaFree(owned_[i]);
+  if (!worker_)
+    for (void* p : owned_) cudaFree(p);
   cudaStreamSynchronize(stream);
-  for (auto& kv : block_limbs_) cudaFreeAsync(const_cast<u64*>(kv.first), stream);
+  for (auto& kv : al_.block_limbs) cudaFreeAsync(const_cast<u64*>(kv.first), stream);
   cudaStreamSynchronize(stream);
   cudaStreamDestroy(stream);
 }
@@ -296,18 +310,18 @@ Context::~Context() {
 Context* Context::make_worker() {
   ACE_CUDA(cudaSetDevice(device));
   ACE_CUDA(cudaStreamSynchronize(stream));  // everything the worker shares is in place
-  Context* w = new Context(*this);          // memberwise: tables, keys, caches by pointer
+  // memberwise copy of what is immutable after set-up (tables, keys by pointer) plus the shared
+  // store; the allocator state copies as empty (AllocState) and the counters are reset.  The
+  // primary may be running: nothing it mutates at run time is read here (its allocator maps are
+  // not copied, lazily built entries live behind sh_->mu, counters are overwritten below).
+  Context* w = new Context(*this);
   w->worker_ = true;
+  w->owned_.clear();
   w->stream = nullptr;
   ACE_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
-  w->free_lists_.clear();
-  w->block_limbs_.clear();
   w->cached_bytes = w->live_bytes = w->peak_bytes = 0;
   w->launches = 0;
   memset(w->trace, 0, sizeof(w->trace));
-  w->owned_inherited_ = w->owned_.size();
-  w->inherited_orders_.clear();
-  for (auto& kv : w->auto_orders_) w->inherited_orders_.push_back(kv.second);
   w->enc_buf_ = nullptr; w->enc_pow_ = nullptr; w->enc_host_ = nullptr;  // scratch: per context
   return w;
 }
@@ -336,8 +350,8 @@ u64* Context::alloc_limbs(size_t n_limbs, bool zero) {
   n_limbs = size_class(std::max<size_t>(n_limbs, 1));
   const size_t bytes = n_limbs * N * sizeof(u64);
   u64* p = nullptr;
-  auto it = free_lists_.find(n_limbs);
-  if (it != free_lists_.end() && !it->second.empty()) {
+  auto it = al_.free_lists.find(n_limbs);
+  if (it != al_.free_lists.end() && !it->second.empty()) {
     p = it->second.back();
     it->second.pop_back();
     cached_bytes -= bytes;
@@ -356,7 +370,7 @@ u64* Context::alloc_limbs(size_t n_limbs, bool zero) {
       e = cudaMallocAsync(&p, bytes, stream);
     }
     ACE_CUDA(e);
-    block_limbs_[p] = n_limbs;
+    al_.block_limbs[p] = n_limbs;
   }
   live_bytes += bytes;
   if (live_bytes > peak_bytes) peak_bytes = live_bytes;
@@ -369,16 +383,16 @@ u64* Context::alloc_limbs(size_t n_limbs, bool zero) {
 void Context::free_limbs(u64* p) {
   if (!p) return;
   relieve_pressure();
-  auto it = block_limbs_.find(p);
-  if (it == block_limbs_.end()) throw std::runtime_error("free_limbs: unknown block");
+  auto it = al_.block_limbs.find(p);
+  if (it == al_.block_limbs.end()) throw std::runtime_error("free_limbs: unknown block");
   const size_t bytes = it->second * N * sizeof(u64);
   live_bytes -= bytes;
   if (cached_bytes + bytes > kCacheCapBytes) {  // enough idle blocks already: back to the pool
-    block_limbs_.erase(it);
+    al_.block_limbs.erase(it);
     ACE_CUDA(cudaFreeAsync(p, stream));
     return;
   }
-  free_lists_[it->second].push_back(p);
+  al_.free_lists[it->second].push_back(p);
   cached_bytes += bytes;
 }
 void Context::dev_malloc(void** p, size_t bytes) {
@@ -399,9 +413,9 @@ void Context::dev_malloc(void** p, size_t bytes) {
   ACE_CUDA(e);
 }
 void Context::trim_cache() {
-  for (auto& kv : free_lists_) {
+  for (auto& kv : al_.free_lists) {
     for (u64* p : kv.second) {
-      block_limbs_.erase(p);
+      al_.block_limbs.erase(p);
       cudaFreeAsync(p, stream);
     }
     kv.second.clear();
@@ -465,8 +479,9 @@ void Context::intt_from(u64* dst, const u64* src, u32 g0, u32 n) {
 // tables _l_hat_inv_modq[part][n_in-1] and _l_hat_modp[num_q-1][part] (crt.c:399-533)
 const Context::ModUpTab& Context::modup_tab(u32 num_q, u32 part) {
   auto key = std::make_pair(num_q, part);
-  auto it  = modup_tabs_.find(key);
-  if (it != modup_tabs_.end()) return it->second;
+  std::lock_guard<std::mutex> lk(sh_->mu);
+  auto it  = sh_->modup_tabs.find(key);
+  if (it != sh_->modup_tabs.end()) return it->second;
   ModUpTab t;
   u32 beta = (u32)num_decomp(num_q);
   t.start  = (u32)(part_size * part);
@@ -496,10 +511,10 @@ const Context::ModUpTab& Context::modup_tab(u32 num_q, u32 part) {
       hm_[(size_t)o * t.n_in + i] = pack_hat(hat);
     }
   }
-  t.hatinv    = to_device(hi);
-  t.hatinv_sh = to_device(his);
-  t.hatmod    = to_device(hm_);
-  return modup_tabs_.emplace(key, std::move(t)).first->second;
+  t.hatinv    = to_device_shared(hi);
+  t.hatinv_sh = to_device_shared(his);
+  t.hatmod    = to_device_shared(hm_);
+  return sh_->modup_tabs.emplace(key, std::move(t)).first->second;
 }
 
 void Context::fill_conv_desc(ConvDesc& d, const ModUpTab& t, const u64* x, u64* out) {
@@ -583,8 +598,9 @@ u32 Context::auto_index(int32_t rot) const {  // number_theory.c:187-199 with mo
 }
 
 const int64_t* Context::auto_order(u32 k) {  // number_theory.c:201-214 (is_ntt = TRUE)
-  auto it = auto_orders_.find(k);
-  if (it != auto_orders_.end()) return it->second;
+  std::lock_guard<std::mutex> lk(sh_->mu);
+  auto it = sh_->auto_orders.find(k);
+  if (it != sh_->auto_orders.end()) return it->second;
   std::vector<int64_t> ord(N);
   const u32 logm = logN + 1;
   for (u64 j = 0; j < N; j++) {
@@ -595,7 +611,7 @@ const int64_t* Context::auto_order(u32 k) {  // number_theory.c:201-214 (is_ntt 
   int64_t* d = nullptr;
   dev_malloc(&d, N * sizeof(int64_t));
   h2d_sync(d, ord.data(), N * sizeof(int64_t));
-  auto_orders_[k] = d;
+  sh_->auto_orders[k] = d;
   return d;
 }
 
@@ -724,7 +740,7 @@ void Context::ct_rotate(u64* r0, u64* r1, const u64* c0, const u64* c1, u32 num_
   const int64_t* order = auto_order(k);
   u64* s = alloc_limbs(2 * (size_t)num_q, false);
   u64 *s0 = s, *s1 = s + (size_t)num_q * N;
-  key_switch(s0, s1, c1, num_q, rot_keys_[k], c0);
+  key_switch(s0, s1, c1, num_q, rot_key(k), c0);
   launch_gather(T, r0, s0, order, 0, num_q, stream);
   launch_gather(T, r1, s1, order, 0, num_q, stream);
   tr(TR_LIMB_ROT, 0, 2 * num_q);

@@ -11,6 +11,7 @@
 #include <map>
 #include <set>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -88,8 +89,8 @@ class Context {
   void relieve_pressure();
   unsigned pressure_seen_ = 0;
   size_t block_limbs(const u64* p) const {
-    auto it = block_limbs_.find(p);
-    if (it == block_limbs_.end()) throw std::runtime_error("unknown limb block");
+    auto it = al_.block_limbs.find(p);
+    if (it == al_.block_limbs.end()) throw std::runtime_error("unknown limb block");
     return it->second;
   }
   size_t cached_bytes = 0, live_bytes = 0, peak_bytes = 0;
@@ -136,8 +137,21 @@ class Context {
   u32            auto_index(int32_t rot_idx) const;
   const int64_t* auto_order(u32 auto_idx);  // device table, built on first use
   const int64_t* auto_order_inv(u32 auto_idx);  // table of the inverse automorphism (scatter form)
-  SwitchKey&     rot_key(u32 auto_idx) { return rot_keys_[auto_idx]; }
-  bool           has_rot_key(u32 auto_idx) const { return rot_keys_.count(auto_idx) != 0; }
+  SwitchKey&     rot_key(u32 auto_idx) {
+    std::lock_guard<std::mutex> lk(sh_->mu);
+    return sh_->rot_keys[auto_idx];
+  }
+  bool           has_rot_key(u32 auto_idx) const {
+    std::lock_guard<std::mutex> lk(sh_->mu);
+    return sh_->rot_keys.count(auto_idx) != 0;
+  }
+  std::vector<u32> rot_key_indices() const {
+    std::lock_guard<std::mutex> lk(sh_->mu);
+    std::vector<u32> v;
+    for (auto& kv : sh_->rot_keys)
+      if (kv.second.k0) v.push_back(kv.first);
+    return v;
+  }
   SwitchKey      relin_key;
   void           import_key_limbs(SwitchKey& key, u32 part, int which, const u64* host);
 
@@ -225,15 +239,34 @@ class Context {
   }
   void             fill_conv_desc(ConvDesc& d, const ModUpTab& t, const u64* x, u64* out);
 
-  std::map<std::pair<u32, u32>, ModUpTab>  modup_tabs_;
-  std::unordered_map<u32, int64_t*>        auto_orders_;
-  std::unordered_map<u32, SwitchKey>       rot_keys_;
-  std::vector<void*>                       owned_;  // device tables freed in the destructor
+  // Tables and keys that are built lazily at run time (ModUp tables per (level, digit),
+  // automorphism tables, rotation keys of a Bootstrap at a new slot count) live in ONE store that
+  // the primary context and all its workers share, behind a mutex: whichever thread needs an
+  // entry first builds it, the others find it.  Entries are never removed and node addresses are
+  // stable, so references handed out stay valid after the lock is released.  The store frees
+  // its device memory when the last context that holds it goes away.
+  struct Shared {
+    std::mutex                               mu;
+    std::map<std::pair<u32, u32>, ModUpTab>  modup_tabs;
+    std::unordered_map<u32, int64_t*>        auto_orders;
+    std::unordered_map<u32, SwitchKey>       rot_keys;
+    std::vector<void*>                       owned;  // device tables behind the entries above
+    int                                      device = 0;
+    ~Shared();
+  };
+  std::shared_ptr<Shared>                  sh_;
+  std::vector<void*>                       owned_;  // device tables of the primary (freed by it)
   bool   worker_ = false;          // shares tables and keys with a primary context
-  size_t owned_inherited_ = 0;     // owned_[0 .. owned_inherited_) belong to the primary
-  std::vector<const void*> inherited_orders_;
-  std::unordered_map<size_t, std::vector<u64*>> free_lists_;  // by size in limbs
-  std::unordered_map<const u64*, size_t>        block_limbs_;
+  // limb allocator: strictly per context (its thread, its stream).  Copying a context for a
+  // worker must not even READ the primary's maps -- the primary may be inside alloc_limbs().
+  struct AllocState {
+    std::unordered_map<size_t, std::vector<u64*>> free_lists;  // by size in limbs
+    std::unordered_map<const u64*, size_t>        block_limbs;
+    AllocState() {}
+    AllocState(const AllocState&) {}             // a copy starts empty
+    AllocState& operator=(const AllocState&) { return *this; }
+  };
+  AllocState al_;
   // ModDown tables
   u64 *phat_inv_, *phat_inv_sh_, *phat_mod_q_;  // [K], [K], [L][K]
   u64 *pinv_mod_q_, *pinv_mod_q_sh_;            // [L]
@@ -261,6 +294,8 @@ class Context {
 
   template <typename Tp>
   Tp* to_device(const std::vector<Tp>& v);
+  template <typename Tp>
+  Tp* to_device_shared(const std::vector<Tp>& v);
 };
 
 }  // namespace ace

@@ -100,14 +100,12 @@ void Context::save_keys(const char* path, bool with_secret) {
     }
   };
   if (flags & 4) put_swk(relin_key);
-  std::vector<u32> idx;
-  for (auto& kv : rot_keys_)
-    if (kv.second.k0) idx.push_back(kv.first);
+  std::vector<u32> idx = rot_key_indices();
   std::sort(idx.begin(), idx.end());
   F.put<u32>((u32)idx.size());
   for (u32 k : idx) {
     F.put<u32>(k);
-    put_swk(rot_keys_[k]);
+    put_swk(rot_key(k));
   }
 }
 
@@ -141,7 +139,7 @@ void Context::load_keys(const char* path) {
   for (u32 i = 0; i < n_rot; i++) {
     const u32 k = F.get<u32>();
     if (k >= 2 * N || !(k & 1)) throw std::runtime_error("bad automorphism index in key file");
-    get_swk(rot_keys_[k]);
+    get_swk(rot_key(k));
   }
   sync();
 }

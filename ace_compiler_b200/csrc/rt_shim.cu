@@ -659,19 +659,32 @@ API POLY Decomp(POLY res, POLY poly, uint32_t part) {  // Decompose_poly, polyno
   res->_is_ntt = poly->_is_ntt;
   return res;
 }
+// The kernels take extended polynomials as [num_q Q limbs | K P limbs] back to back.  The
+// reference keeps the P part at _num_alloc_primes - _num_primes_p (Get_p_coeffs,
+// polynomial.h:214-217): the two agree unless a polynomial allocated at a higher level is reused
+// at a lower one.  No emitted program does that with an extended polynomial; refuse it loudly
+// instead of reading the wrong limbs.
+static void check_ext_layout(const char* who, POLY p) {
+  if (p->_num_primes_p != 0 && p->_num_alloc_primes != p->_num_primes + p->_num_primes_p)
+    die((std::string(who) + ": extended polynomial reused at a lower level (P limbs are not "
+         "adjacent to the Q limbs); not supported").c_str());
+}
 API POLY Mod_up(POLY new_poly, POLY old_poly, uint32_t part) {  // poly_eval.c:19-26
+  check_ext_layout("Mod_up", new_poly);
   guard([&] { ctx()->modup_from(U(new_poly->_data), U(old_poly->_data), (u32)new_poly->_num_primes, part); });
   new_poly->_is_ntt = old_poly->_is_ntt;
   return new_poly;
 }
 API POLY Decomp_modup(POLY res, POLY poly, uint32_t part) {  // poly_eval.c:28-34
   StatScope ss(ST_MODUP);
+  check_ext_layout("Decomp_modup", res);
   guard([&] { ctx_nf(); g_queue->modup(U(res->_data), U(poly->_data), (u32)poly->_num_primes, part); });
   res->_is_ntt = true;
   return res;
 }
 API POLY Mod_down(POLY res, POLY poly) {  // poly_eval.c:36-41
   StatScope ss(ST_MODDOWN);
+  check_ext_layout("Mod_down", poly);
   guard([&] { ctx_nf(); g_queue->moddown(U(res->_data), U(poly->_data), (u32)res->_num_primes); });
   res->_is_ntt = poly->_is_ntt;
   return res;
@@ -1080,7 +1093,7 @@ API bool Pt_mgr_init(const char* fname) {  // pt_mgr.c:35-110 (message files onl
     die("weight data file missing");
   }
   struct stat st;
-  fstat(fd, &st);
+  if (fstat(fd, &st) != 0 || st.st_size < (off_t)sizeof(DataFileHdr)) die("weight data file: cannot stat / too short");
   g_wfile.resize(st.st_size);
   size_t got = 0;
   while (got < (size_t)st.st_size) {
@@ -1093,11 +1106,19 @@ API bool Pt_mgr_init(const char* fname) {  // pt_mgr.c:35-110 (message files onl
   if (memcmp(h->magic, "!ANTFHE", 7) != 0) die("bad weight data file magic");
   g_etype = h->ent_type;
   g_nent  = h->ent_count;
+  // the header and the look-up table are untrusted input: every offset is checked against the
+  // file size before anything on the host or the device is addressed through it
+  if ((uint64_t)h->lut_ofst > g_wfile.size() ||
+      (uint64_t)g_nent * sizeof(LutEntry) > g_wfile.size() - (uint64_t)h->lut_ofst)
+    die("weight data file: look-up table outside the file");
   g_lut   = reinterpret_cast<const LutEntry*>(g_wfile.data() + h->lut_ofst);
   if (g_etype != DE_MSG_F32 && g_etype != DE_MSG_F64) die("only message data files are supported");
+  for (size_t i = 0; i < g_nent; i++)
+    if ((uint64_t)g_lut[i].ent_ofst > g_wfile.size() || (uint64_t)g_lut[i].size > g_wfile.size() - (uint64_t)g_lut[i].ent_ofst)
+      die("weight data file: entry outside the file");
   guard([&] {
     Context* c = ctx();
-    ACE_CUDA(cudaMalloc(&g_wfile_dev, g_wfile.size()));
+    c->dev_malloc(&g_wfile_dev, g_wfile.size());
     c->h2d_sync(g_wfile_dev, g_wfile.data(), g_wfile.size());
   });
   return true;
