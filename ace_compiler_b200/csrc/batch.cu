@@ -8,12 +8,23 @@
 // jobs.  Per polynomial the arithmetic is exactly that of Context::modup_from / mod_down /
 // rescale (context.cu), so results are bit-identical.
 #include <algorithm>
+#include <cstdlib>
 
 #include "context.h"
 #include "host_math.h"
 #include "prof.h"
 
 namespace ace {
+
+// Folding the Rescale / ModDown limb-wise steps into the transform removes two passes and two
+// launches per primitive -- and was measured SLOWER in its first form (Mod_down at l = 34: 124.8
+// against 111.6 us, ResNet-20 0.978 against 0.955 s per image): the operand of the epilogue is
+// loaded at the very end of the second kernel, its latency is not hidden, and the prologue's
+// Switch_modulus sits on the transform's critical path.  Off unless ACE_B200_FUSED_TAILS=1.
+bool fused_tails() {
+  static const bool on = getenv("ACE_B200_FUSED_TAILS") != nullptr;
+  return on;
+}
 
 namespace {
 typedef uint16_t u16;
@@ -37,6 +48,33 @@ struct PtrBatcher {
     if (b.n == 0) return;
     if (inverse) launch_intt(T, b, s); else launch_ntt(T, b, s);
     *launches += per_launch;
+    b.n = 0;
+  }
+};
+
+// forward transforms with the Rescale / ModDown limb-wise steps folded in (ntt16.cu)
+struct FusedBatcher {
+  const DeviceTables& T;
+  cudaStream_t        s;
+  size_t*             launches;
+  NttFusedBatch       b;
+  FusedBatcher(const DeviceTables& t, cudaStream_t st, size_t* l, int pre, int post, const u64* pre_w,
+               const u64* pre_w_sh, u32 pre_stride, const u64* post_w, const u64* post_w_sh, u32 post_stride)
+      : T(t), s(st), launches(l) {
+    b.n = 0; b.pre = (uint8_t)pre; b.post = (uint8_t)post;
+    b.pre_w = pre_w; b.pre_w_sh = pre_w_sh; b.post_w = post_w; b.post_w_sh = post_w_sh;
+    b.pre_stride = pre_stride; b.post_stride = post_stride;
+  }
+  void add(u64* dst, const u64* src, const u64* aux, const u64* addend, u32 g, u32 g_from) {
+    if (b.n == (u32)kMaxFused) flush();
+    b.dst[b.n] = dst; b.src[b.n] = src; b.aux[b.n] = aux; b.add[b.n] = addend;
+    b.g[b.n] = (u16)g; b.g_from[b.n] = (u16)g_from;
+    b.n++;
+  }
+  void flush() {
+    if (b.n == 0) return;
+    launch_ntt16_fused(T, b, s);
+    *launches += 2;
     b.n = 0;
   }
 };
@@ -135,7 +173,7 @@ void Context::modup_batch(const ModupJob* jobs, size_t n) {
 // ---------------------------------------------------------------------------- ModDown
 void Context::moddown_batch(const ModdownJob* jobs, size_t n) {
   if (n == 0) return;
-  if (n == 1) { mod_down(jobs[0].out, jobs[0].in, jobs[0].num_q); return; }
+  if (n == 1 && !(ntt16_usable(T) && fused_tails())) { mod_down(jobs[0].out, jobs[0].in, jobs[0].num_q); return; }
   size_t total_q = 0;
   for (size_t j = 0; j < n; j++) { total_q += jobs[j].num_q; tr(TR_MODDOWN_POLY, jobs[j].num_q); }
   u64* pc   = alloc_limbs(n * K, false);
@@ -162,6 +200,22 @@ void Context::moddown_batch(const ModdownJob* jobs, size_t n) {
       if (nd == (u32)kMaxConvPack) { launch_base_conv(T, descs, nd, stream); launches++; nd = 0; }
     }
     if (nd) { launch_base_conv(T, descs, nd, stream); launches++; }
+  }
+  bool md_aliased = false;  // in-place Mod_down: the fused transform would overwrite its own operand
+  for (size_t j = 0; j < n; j++)
+    md_aliased |= jobs[j].out + (size_t)jobs[j].num_q * N > jobs[j].in &&
+                  jobs[j].out < jobs[j].in + (size_t)(jobs[j].num_q + K) * N;
+  if (ntt16_usable(T) && fused_tails() && !md_aliased) {
+    // NTT of the converted limbs with the tail (old - conv) * P^-1 folded into its last store
+    FusedBatcher fb(T, stream, &launches, 0, 2, nullptr, nullptr, 0, pinv_mod_q_, pinv_mod_q_sh_, 0);
+    size_t off = 0;
+    for (size_t j = 0; j < n; j++)
+      for (u32 o = 0; o < jobs[j].num_q; o++, off++)
+        fb.add(jobs[j].out + (size_t)o * N, conv + off * N, jobs[j].in + (size_t)o * N, nullptr, o, 0);
+    fb.flush();
+    free_limbs(pc);
+    free_limbs(conv);
+    return;
   }
   {
     PtrBatcher nb(T, stream, false, &launches);
@@ -192,7 +246,7 @@ void Context::moddown_batch(const ModdownJob* jobs, size_t n) {
 // ---------------------------------------------------------------------------- Rescale
 void Context::rescale_batch(const RescaleJob* jobs, size_t n) {
   if (n == 0) return;
-  if (n == 1) { rescale(jobs[0].out, jobs[0].in, jobs[0].num_q); return; }
+  if (n == 1 && !(ntt16_usable(T) && fused_tails())) { rescale(jobs[0].out, jobs[0].in, jobs[0].num_q); return; }
   size_t total = 0;
   for (size_t j = 0; j < n; j++) {
     if (jobs[j].num_q < 2) throw std::runtime_error("Rescale: level not enough");
@@ -200,7 +254,6 @@ void Context::rescale_batch(const RescaleJob* jobs, size_t n) {
     tr(TR_RESCALE_POLY, jobs[j].num_q);
   }
   u64* last = alloc_limbs(n, false);
-  u64* tmp  = alloc_limbs(total, false);
   {
     PtrBatcher ib(T, stream, true, &launches);
     for (size_t j = 0; j < n; j++) {
@@ -209,6 +262,22 @@ void Context::rescale_batch(const RescaleJob* jobs, size_t n) {
     }
     ib.flush();
   }
+  bool aliased = false;  // in-place Rescale: the fused transform would overwrite its own operand
+  for (size_t j = 0; j < n; j++) aliased |= jobs[j].out == jobs[j].in;
+  if (ntt16_usable(T) && fused_tails() && !aliased) {
+    // one fused transform per remaining limb: lift of the dropped limb (prologue), NTT,
+    // c * q_l^-1 + t (epilogue)
+    FusedBatcher fb(T, stream, &launches, 1, 1, negqlinv_, negqlinv_sh_, (u32)L, qlinv_, qlinv_sh_, (u32)L);
+    for (size_t j = 0; j < n; j++) {
+      const u32 l = jobs[j].num_q - 1;
+      for (u32 i = 0; i < l; i++)
+        fb.add(jobs[j].out + (size_t)i * N, last + j * N, jobs[j].in + (size_t)i * N, nullptr, i, l);
+    }
+    fb.flush();
+    free_limbs(last);
+    return;
+  }
+  u64* tmp  = alloc_limbs(total, false);
   {
     P3Batcher pb;
     size_t    off = 0;

@@ -551,6 +551,11 @@ void Context::modup_from(u64* out, const u64* digit, u32 num_q, u32 part) {
 
 // Mod_down (poly_eval.c:36-41).  Unlike the reference the P part of `in` is left intact.
 void Context::mod_down(u64* out, const u64* in, u32 num_q) {
+  if (ntt16_usable(T) && fused_tails()) {  // fused tail (batch.cu; falls back by itself when out overlaps in)
+    ModdownJob j{out, in, num_q};
+    moddown_batch(&j, 1);
+    return;
+  }
   tr(TR_MODDOWN_POLY, num_q);
   u64* pc   = alloc_limbs(K, false);
   u64* conv = alloc_limbs(num_q, false);
@@ -572,6 +577,11 @@ void Context::mod_down(u64* out, const u64* in, u32 num_q) {
 // Rescale (poly_eval.c:43-49): out gets num_q - 1 limbs
 void Context::rescale(u64* out, const u64* in, u32 num_q) {
   if (num_q < 2) throw std::runtime_error("Rescale: level not enough");
+  if (ntt16_usable(T) && fused_tails()) {  // fused prologue / epilogue (batch.cu; falls back when out == in)
+    RescaleJob j{out, in, num_q};
+    rescale_batch(&j, 1);
+    return;
+  }
   tr(TR_RESCALE_POLY, num_q);
   const u32 l = num_q - 1;
   u64* last = alloc_limbs(1, false);
@@ -704,6 +714,30 @@ void Context::mod_down_pair(u64* out0, u64* out1, const u64* a0, const u64* a1, 
     for (u32 o = 0; o < num_q; o++) { c.g_out[o] = (u16)o; c.out_slot[o] = (u16)o; }
   }
   launch_base_conv(T, md, np, stream);
+  // out must not overlap the Q limbs of the inputs for the fused form (it reads them last)
+  auto overlaps = [&](const u64* o, const u64* a) { return o && a && o + (size_t)num_q * N > a && o < a + (size_t)num_q * N; };
+  if (ntt16_usable(T) && fused_tails() && !overlaps(out0, a0) && !overlaps(out0, a1) && !overlaps(out1, a0) &&
+      !overlaps(out1, a1) && np * num_q <= (u32)kMaxFused) {
+    // NTT of the converted limbs with the tail (old - conv) * P^-1 (+ add) in its last store
+    NttFusedBatch fb;
+    fb.n = 0; fb.pre = 0; fb.post = 2;
+    fb.pre_w = fb.pre_w_sh = nullptr; fb.pre_stride = 0;
+    fb.post_w = pinv_mod_q_; fb.post_w_sh = pinv_mod_q_sh_; fb.post_stride = 0;
+    for (u32 h = 0; h < np; h++)
+      for (u32 o = 0; o < num_q; o++) {
+        const u32 k = fb.n++;
+        fb.dst[k] = (h ? out1 : out0) + (size_t)o * N;
+        fb.src[k] = conv + ((size_t)h * num_q + o) * N;
+        fb.aux[k] = (h ? a1 : a0) + (size_t)o * N;
+        const u64* ad = h ? add1 : add0;
+        fb.add[k] = ad ? ad + (size_t)o * N : nullptr;
+        fb.g[k] = (u16)o; fb.g_from[k] = 0;
+      }
+    launch_ntt16_fused(T, fb, stream);
+    launches += 1 + 2;
+    free_limbs(pc); free_limbs(conv);
+    return;
+  }
   LimbBatch cb;
   cb.base = conv; cb.src = nullptr; cb.n = np * num_q;
   for (u32 i = 0; i < np * num_q; i++) { cb.slot[i] = (u16)i; cb.g[i] = (u16)(i % num_q); }

@@ -52,6 +52,8 @@ struct ModdownJob { u64* out; const u64* in; u32 num_q; };            // in: [nu
 struct RescaleJob { u64* out; const u64* in; u32 num_q; };
 struct EncodeJob  { u64* out; const void* src; int kind; u32 len, level, slots, sf_degree, p_cnt; };
 
+bool fused_tails();  // batch.cu: Rescale / ModDown steps folded into the forward transform (opt-in)
+
 class Context {
  public:
   Context(const Params& p, int device);

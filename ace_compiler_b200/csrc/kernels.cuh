@@ -45,6 +45,28 @@ struct DeviceTables {
   u64           fp64_max_q;
 };
 
+// Forward NTT with the neighbouring limb-wise steps of Rescale / Mod_down folded in (ntt16.cu):
+//   prologue (pre = 1, Rescale_poly, polynomial.c:1123-1140): the input of limb i is
+//       Switch_modulus(src, q_from, q_g) * pre_w[g_from * pre_stride + g]   (src = INTT of the dropped limb)
+//   epilogue post = 1 (Rescale_poly, :1141-1161):  dst = aux * post_w[...] + NTT(x)
+//            post = 2 (Reduce_rns_base tail, :953-965): dst = (aux - NTT(x)) * post_w[g] (+ add)
+// so a Rescale is INTT(1 limb) + ONE fused transform instead of INTT + pre + NTT + post, and the
+// tail of a ModDown disappears into its NTT: two passes over every limb less, two launches less.
+constexpr int kMaxFused = 128;
+struct NttFusedBatch {
+  u32        n;
+  u64*       dst[kMaxFused];
+  const u64* src[kMaxFused];
+  const u64* aux[kMaxFused];
+  const u64* add[kMaxFused];   // post = 2 only; nullptr: none
+  uint16_t   g[kMaxFused];
+  uint16_t   g_from[kMaxFused];
+  uint8_t    pre, post;
+  const u64 *pre_w, *pre_w_sh, *post_w, *post_w_sh;
+  u32        pre_stride, post_stride;  // table index = g_from * stride + g
+};
+void launch_ntt16_fused(const DeviceTables& T, const NttFusedBatch& b, cudaStream_t s);
+
 // N = 2^16 only (ntt16.cu); launch_ntt / launch_intt route here when ntt16_usable()
 bool ntt16_usable(const DeviceTables& T);
 double ntt16_bfly_peak(const DeviceTables& T, int form, int ctas_per_sm, cudaStream_t st);

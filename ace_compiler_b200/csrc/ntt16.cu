@@ -40,6 +40,8 @@
 //          u is brought below 4q first.
 // Twiddles: {w, w'} interleaved (one 16-byte load per butterfly) for the integer forms, one double
 // for the FP64 form.
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 #include "kernels.cuh"
@@ -58,7 +60,53 @@ __device__ __forceinline__ const u64* b_src(const LimbBatch& b, u32 i, u32 N) {
 __device__ __forceinline__ u64* b_dst(const LimbPtrBatch& b, u32 i, u32) { return b.dst[i]; }
 __device__ __forceinline__ const u64* b_src(const LimbPtrBatch& b, u32 i, u32) { return b.src[i]; }
 
+__device__ __forceinline__ u64* b_dst(const NttFusedBatch& b, u32 i, u32) { return b.dst[i]; }
+__device__ __forceinline__ const u64* b_src(const NttFusedBatch& b, u32 i, u32) { return b.src[i]; }
+
 __device__ __forceinline__ u64 csub64(u64 a, u64 m) { return a >= m ? a - m : a; }
+
+// What is folded into the first load / the last store of a forward transform (NttFusedBatch).
+// NoHook: nothing, the calls vanish at compile time.
+struct NoHook {
+  static constexpr bool kActive = false;
+  __device__ __forceinline__ u64 pre(u64 v) const { return v; }
+  __device__ __forceinline__ u64 post(u64 y, u32) const { return y; }
+};
+struct FusedHook {
+  static constexpr bool kActive = true;
+  u32        pre_mode, post_mode;
+  u64        q, q_from, pw, pwsh, ew, ewsh;
+  const u64* aux;
+  const u64* add;
+  __device__ __forceinline__ FusedHook(const DeviceTables& T, const NttFusedBatch& b, u32 limb) {
+    const u32 g = b.g[limb], gf = b.g_from[limb];
+    pre_mode = b.pre; post_mode = b.post;
+    q = T.mod[g].q;
+    q_from = pre_mode ? T.mod[gf].q : 0;
+    pw = pwsh = ew = ewsh = 0;
+    if (pre_mode) { pw = b.pre_w[(size_t)gf * b.pre_stride + g]; pwsh = b.pre_w_sh[(size_t)gf * b.pre_stride + g]; }
+    if (post_mode) { ew = b.post_w[(size_t)gf * b.post_stride + g]; ewsh = b.post_w_sh[(size_t)gf * b.post_stride + g]; }
+    aux = b.aux[limb];
+    add = b.add[limb];
+  }
+  __device__ __forceinline__ u64 pre(u64 v) const {
+    return pre_mode ? mul_shoup(switch_modulus(v, q_from, q), pw, pwsh, q) : v;
+  }
+  __device__ __forceinline__ u64 post(u64 y, u32 idx) const {
+    if (post_mode == 1) return add_mod(mul_shoup(aux[idx], ew, ewsh, q), y, q);
+    if (post_mode == 2) {
+      u64 v = mul_shoup(sub_mod(aux[idx], y, q), ew, ewsh, q);
+      if (add != nullptr) v = add_mod(v, add[idx], q);
+      return v;
+    }
+    return y;
+  }
+};
+template <class B> struct HookOf { typedef NoHook type; static __device__ __forceinline__ NoHook make(const DeviceTables&, const B&, u32) { return NoHook(); } };
+template <> struct HookOf<NttFusedBatch> {
+  typedef FusedHook type;
+  static __device__ __forceinline__ FusedHook make(const DeviceTables& T, const NttFusedBatch& b, u32 limb) { return FusedHook(T, b, limb); }
+};
 
 // ------------------------------------------------------------------------------------------
 // integer arithmetic
@@ -265,21 +313,25 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 #define ACE_TW_GET_B(PTR, i, h) ((PRE & 2) ? twb_[(1 << (i)) - 1 + (h)] : A::ld(PTR(i, h)))
 
 // ---------------- forward K1: stages 0-7 along r, 16 columns per CTA -------------------------
-template <class A, int PRE>
-__device__ __forceinline__ void fwd_cols_body(const DeviceTables& T, u32 g, u64* sm, const u64* in, u64* out) {
+// XCH = 1 (cluster form, one launch per transform): the 16 CTAs of a cluster own one limb; the
+// first phase hands its results to the CTA that needs them in the second phase through
+// distributed shared memory (`xin` of the peer) instead of global memory.
+template <class A, int PRE, class H, int XCH = 0>
+__device__ __forceinline__ void fwd_cols_body(const DeviceTables& T, u32 g, u64* sm, const u64* in, u64* out, const H& hook,
+                                              u64* xin = nullptr) {
   typedef typename A::E E;
   const typename A::Mod M = A::make(T.mod[g]);
   const typename A::TW* __restrict__ tw = A::fwd_table(T, g);
   const u32 t = threadIdx.x, c = t & 15, j = t >> 4;
   const u32 col = blockIdx.x * 16 + c;
-  pdl_launch_dependents();
+  if (!XCH) pdl_launch_dependents();
 #define PA(i, h) (tw + (1 << (i)) + (h))
 #define PB(i, h) (tw + (16 << (i)) + (j << (i)) + (h))
   ACE_TW_DECL;
   ACE_TW_PRELOAD(PA, PB, 15)
   E x[16];
 #pragma unroll
-  for (int k = 0; k < 16; k++) x[k] = A::from_canonical(in[(j + 16 * k) * 256 + col], M);
+  for (int k = 0; k < 16; k++) x[k] = A::from_canonical(hook.pre(in[(j + 16 * k) * 256 + col]), M);
 #define TW_A(i, h) ACE_TW_GET_A(PA, i, h)
   ACE_R16_FWD(x, TW_A)
 #undef TW_A
@@ -293,13 +345,23 @@ __device__ __forceinline__ void fwd_cols_body(const DeviceTables& T, u32 g, u64*
 #undef TW_B
 #undef PA
 #undef PB
+  if (XCH) {
+    // rows 16j .. 16j+15 belong to CTA j of the cluster: row k of its tile, columns 16 s + c
+    cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+    u64* peer = cl.map_shared_rank(xin, j);
+    cl.barrier_wait();  // (arrived at kernel start) every CTA of the cluster is running
+#pragma unroll
+    for (int k = 0; k < 16; k++) peer[k * kRowPad + 17 * blockIdx.x + c] = A::to_mid(x[k]);
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < 16; k++) out[(16 * j + k) * 256 + col] = A::to_mid(x[k]);
 }
 
 // ---------------- forward K2: stages 8-15 inside a row, 16 rows per CTA ----------------------
-template <class A, int PRE>
-__device__ __forceinline__ void fwd_rows_body(const DeviceTables& T, u32 g, u64* sm, u64* data) {
+template <class A, int PRE, class H, int XCH = 0>
+__device__ __forceinline__ void fwd_rows_body(const DeviceTables& T, u32 g, u64* sm, u64* data, const H& hook,
+                                              const u64* xin = nullptr) {
   typedef typename A::E E;
   const typename A::Mod M = A::make(T.mod[g]);
   const typename A::TW* __restrict__ tw = A::fwd_table(T, g);
@@ -311,10 +373,15 @@ __device__ __forceinline__ void fwd_rows_body(const DeviceTables& T, u32 g, u64*
 #define PB(i, h) (tw + (4096 << (i)) + ((16 * r + j) << (i)) + (h))
   ACE_TW_DECL;
   ACE_TW_PRELOAD(PA, PB, 15)
-  pdl_wait();  // the coefficients come from the first kernel
   E x[16];
+  if (XCH) {
 #pragma unroll
-  for (int k = 0; k < 16; k++) x[k] = A::from_mid(row[j + 16 * k]);
+    for (int k = 0; k < 16; k++) x[k] = A::from_mid(xin[rho * kRowPad + 17 * k + j]);
+  } else {
+    pdl_wait();  // the coefficients come from the first kernel
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = A::from_mid(row[j + 16 * k]);
+  }
 #define TW_A(i, h) ACE_TW_GET_A(PA, i, h)
   ACE_R16_FWD(x, TW_A)
 #undef TW_A
@@ -330,20 +397,24 @@ __device__ __forceinline__ void fwd_rows_body(const DeviceTables& T, u32 g, u64*
 #undef PB
   ulonglong2* o = reinterpret_cast<ulonglong2*>(row + 16 * j);
 #pragma unroll
-  for (int k = 0; k < 8; k++)
-    o[k] = make_ulonglong2(A::to_canonical(x[2 * k], M), A::to_canonical(x[2 * k + 1], M));
+  for (int k = 0; k < 8; k++) {
+    const u32 at = r * 256 + 16 * j + 2 * k;
+    o[k] = make_ulonglong2(hook.post(A::to_canonical(x[2 * k], M), at),
+                           hook.post(A::to_canonical(x[2 * k + 1], M), at + 1));
+  }
 }
 
 // ---------------- inverse K1: DIT stages m = 1 .. 128 inside a row ---------------------------
-template <class A, int PRE>
-__device__ __forceinline__ void inv_rows_body(const DeviceTables& T, u32 g, u64* sm, const u64* in, u64* out) {
+template <class A, int PRE, class H, int XCH = 0>
+__device__ __forceinline__ void inv_rows_body(const DeviceTables& T, u32 g, u64* sm, const u64* in, u64* out, const H&,
+                                              u64* xin = nullptr) {
   typedef typename A::E E;
   const typename A::Mod M = A::make(T.mod[g]);
   const typename A::TW* __restrict__ tw = A::inv_table(T, g);
   const u32 t = threadIdx.x, j = t & 15, rho = t >> 4;
   const u32 r = blockIdx.x * 16 + rho;
   u64* srow = sm + rho * kRowPad;
-  pdl_launch_dependents();
+  if (!XCH) pdl_launch_dependents();
 #define PA(i, e) (tw + (1 << (i)) + (e))
 #define PB(i, e) (tw + (16 << (i)) + j + 16 * (e))
   ACE_TW_DECL;
@@ -368,14 +439,23 @@ __device__ __forceinline__ void inv_rows_body(const DeviceTables& T, u32 g, u64*
 #undef TW_B
 #undef PA
 #undef PB
+  if (XCH) {
+    // columns 16k .. 16k+15 belong to CTA k of the cluster: row r of its 256 x 16 slab
+    cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+    cl.barrier_wait();
+#pragma unroll
+    for (int k = 0; k < 16; k++) cl.map_shared_rank(xin, k)[r * 16 + j] = A::to_mid(x[k]);
+    return;
+  }
   u64* orow = out + r * 256;
 #pragma unroll
   for (int k = 0; k < 16; k++) orow[j + 16 * k] = A::to_mid(x[k]);
 }
 
 // ---------------- inverse K2: DIT stages m = 256 .. 32768 along r, then * psi^-n N^-1 ---------
-template <class A, int PRE>
-__device__ __forceinline__ void inv_cols_body(const DeviceTables& T, u32 g, u64* sm, u64* data) {
+template <class A, int PRE, class H, int XCH = 0>
+__device__ __forceinline__ void inv_cols_body(const DeviceTables& T, u32 g, u64* sm, u64* data, const H&,
+                                              const u64* xin = nullptr) {
   typedef typename A::E E;
   const typename A::Mod M = A::make(T.mod[g]);
   const typename A::TW* __restrict__ tw = A::inv_table(T, g);
@@ -386,10 +466,15 @@ __device__ __forceinline__ void inv_cols_body(const DeviceTables& T, u32 g, u64*
 #define PB(i, e) (tw + (4096 << (i)) + (j + 16 * (e)) * 256 + col)
   ACE_TW_DECL;
   ACE_TW_PRELOAD(PA, PB, 15)
-  pdl_wait();  // the coefficients come from the first kernel
   E x[16];
+  if (XCH) {
 #pragma unroll
-  for (int k = 0; k < 16; k++) x[k] = A::from_mid(data[(16 * j + k) * 256 + col]);
+    for (int k = 0; k < 16; k++) x[k] = A::from_mid(xin[(16 * j + k) * 16 + c]);
+  } else {
+    pdl_wait();  // the coefficients come from the first kernel
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = A::from_mid(data[(16 * j + k) * 256 + col]);
+  }
 #define TW_A(i, e) ACE_TW_GET_A(PA, i, e)
   ACE_R16_DIT(x, TW_A)
 #undef TW_A
@@ -428,14 +513,51 @@ __global__ void __launch_bounds__(kThreads, PRE ? 1 : 3) ntt16_kernel(DeviceTabl
   const u64* src = b_src(b, limb, 65536);
   u64* dst = b_dst(b, limb, 65536);
   constexpr int PD = PRE ? 3 : 2, PI = PRE ? 3 : 0;  // what is preloaded: FP64 / integer form
+  typedef typename HookOf<B>::type H;
+  const H hook = HookOf<B>::make(T, b, limb);
 #define ACE_DISPATCH(BODY, ...)                                                  \
-  if (ar == 0) BODY<ArithDP, PD>(__VA_ARGS__);                                   \
-  else if (ar == 1) BODY<ArithInt<false>, PI>(__VA_ARGS__);                      \
-  else BODY<ArithInt<true>, PI>(__VA_ARGS__);
+  if (ar == 0) BODY<ArithDP, PD, H>(__VA_ARGS__, hook);                          \
+  else if (ar == 1) BODY<ArithInt<false>, PI, H>(__VA_ARGS__, hook);             \
+  else BODY<ArithInt<true>, PI, H>(__VA_ARGS__, hook);
   if (KIND == FWD_COLS) { ACE_DISPATCH(fwd_cols_body, T, g, sm, src, dst) }
   if (KIND == FWD_ROWS) { ACE_DISPATCH(fwd_rows_body, T, g, sm, dst) }
   if (KIND == INV_ROWS) { ACE_DISPATCH(inv_rows_body, T, g, sm, src, dst) }
   if (KIND == INV_COLS) { ACE_DISPATCH(inv_cols_body, T, g, sm, dst) }
+#undef ACE_DISPATCH
+}
+
+// ---------------- one launch per transform: clusters of 16 CTAs, hand-over through DSMEM ------
+// grid (16, limbs), cluster (16, 1, 1): cluster = limb, CTA rank = slab (first phase) = row group
+// (second phase).  Saves the write + read of the intermediate limb through L2 and the second
+// launch.  16 CTAs per cluster is above the portable limit of 8 (opt-in,
+// cudaFuncAttributeNonPortableClusterSizeAllowed).  MEASURED AND NOT USED BY DEFAULT: bit-exact,
+// but 51.4 us against 38.5 us per 45 limbs and 14.5 against 12.4 us for one limb (16-CTA
+// clusters constrain placement to one GPC at a time and the remote stores are slower than the
+// L2 round trip they replace; ResNet-20 1.108 s against 0.951 s per image).  Kept behind
+// ACE_B200_NTT_CLUSTER=1 as the record of the experiment (profiles/r2_ntt_bench_v4.txt).
+template <int DIR, class B, bool PRE>
+__global__ void __launch_bounds__(kThreads, PRE ? 1 : 3) ntt16_cluster_kernel(DeviceTables T, const __grid_constant__ B b) {
+  extern __shared__ __align__(16) u64 dyn_sm[];
+  u64* sm  = dyn_sm;                  // exchange between the two passes of a phase
+  u64* xin = dyn_sm + 16 * kRowPad;   // what the peers hand over for the second phase
+  cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+  cl.barrier_arrive();  // matched by the barrier_wait() before the first remote store
+  const u32 limb = gridDim.y - 1 - blockIdx.y, g = b.g[limb];
+  const int ar = arith_of(T, T.mod[g]);
+  const u64* src = b_src(b, limb, 65536);
+  u64* dst = b_dst(b, limb, 65536);
+  constexpr int PD = PRE ? 3 : 2, PI = PRE ? 3 : 0;
+  typedef typename HookOf<B>::type H;
+  const H hook = HookOf<B>::make(T, b, limb);
+#define ACE_DISPATCH(BODY, ...)                                                     \
+  if (ar == 0) BODY<ArithDP, PD, H, 1>(__VA_ARGS__);                                \
+  else if (ar == 1) BODY<ArithInt<false>, PI, H, 1>(__VA_ARGS__);                   \
+  else BODY<ArithInt<true>, PI, H, 1>(__VA_ARGS__);
+  if (DIR == 0) { ACE_DISPATCH(fwd_cols_body, T, g, sm, src, dst, hook, xin) }
+  else { ACE_DISPATCH(inv_rows_body, T, g, sm, src, dst, hook, xin) }
+  cl.sync();  // release / acquire: every slab has arrived
+  if (DIR == 0) { ACE_DISPATCH(fwd_rows_body, T, g, sm, dst, hook, xin) }
+  else { ACE_DISPATCH(inv_cols_body, T, g, sm, dst, hook, xin) }
 #undef ACE_DISPATCH
 }
 
@@ -518,6 +640,35 @@ static void launch_pair(const DeviceTables& T, const B& b, cudaStream_t s) {
   cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, ntt16_kernel<K2, B, PRE>, T, b);
 }
+constexpr size_t kClusterSmem = 2 * 16 * kRowPad * sizeof(u64);  // 69 632 bytes
+// 0: not probed, 1: clusters of 16 can be placed, -1: they cannot (or ACE_B200_NTT_NO_CLUSTER)
+template <int DIR, class B, bool PRE>
+static bool launch_cluster(const DeviceTables& T, const B& b, cudaStream_t s) {
+  static int state = 0;
+  auto kern = ntt16_cluster_kernel<DIR, B, PRE>;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(16, b.n);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kClusterSmem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (state == 0) {
+    state = -1;
+    if (getenv("ACE_B200_NTT_CLUSTER") != nullptr &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem) == cudaSuccess &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) state = 1;
+    }
+    cudaGetLastError();
+  }
+  if (state < 0) return false;
+  return cudaLaunchKernelEx(&cfg, kern, T, b) == cudaSuccess;
+}
 // batches of at most kSmallBatch limbs (<= 2 CTAs per SM) take the latency-oriented variant
 constexpr u32 kSmallBatch = 18;
 static bool no_pre() {
@@ -527,13 +678,23 @@ static bool no_pre() {
 }
 template <class B>
 static void ntt16_fwd_impl(const DeviceTables& T, const B& b, cudaStream_t s) {
-  if (b.n <= kSmallBatch && !no_pre()) launch_pair<FWD_COLS, FWD_ROWS, B, true>(T, b, s);
-  else launch_pair<FWD_COLS, FWD_ROWS, B, false>(T, b, s);
+  if (b.n <= kSmallBatch && !no_pre()) {
+    if (!launch_cluster<0, B, true>(T, b, s)) launch_pair<FWD_COLS, FWD_ROWS, B, true>(T, b, s);
+  } else if (!launch_cluster<0, B, false>(T, b, s)) {
+    launch_pair<FWD_COLS, FWD_ROWS, B, false>(T, b, s);
+  }
 }
 template <class B>
 static void ntt16_inv_impl(const DeviceTables& T, const B& b, cudaStream_t s) {
-  if (b.n <= kSmallBatch && !no_pre()) launch_pair<INV_ROWS, INV_COLS, B, true>(T, b, s);
-  else launch_pair<INV_ROWS, INV_COLS, B, false>(T, b, s);
+  if (b.n <= kSmallBatch && !no_pre()) {
+    if (!launch_cluster<1, B, true>(T, b, s)) launch_pair<INV_ROWS, INV_COLS, B, true>(T, b, s);
+  } else if (!launch_cluster<1, B, false>(T, b, s)) {
+    launch_pair<INV_ROWS, INV_COLS, B, false>(T, b, s);
+  }
+}
+void launch_ntt16_fused(const DeviceTables& T, const NttFusedBatch& b, cudaStream_t s) {
+  if (b.n == 0) return;
+  ntt16_fwd_impl(T, b, s);
 }
 void launch_ntt16(const DeviceTables& T, const LimbBatch& b, cudaStream_t s) { ntt16_fwd_impl(T, b, s); }
 void launch_ntt16(const DeviceTables& T, const LimbPtrBatch& b, cudaStream_t s) { ntt16_fwd_impl(T, b, s); }

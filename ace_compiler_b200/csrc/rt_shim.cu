@@ -20,6 +20,7 @@
 #include <map>
 #include <atomic>
 #include <mutex>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -320,6 +321,48 @@ struct LutEntry {
   uint64_t ent_ofst;
 };
 std::vector<char> g_wfile;
+// per host thread: plaintexts already encoded on this thread's stream, by (entry, level, degree)
+thread_local std::unordered_map<u64, u64*> g_pt_cache;
+thread_local size_t                        g_pt_cache_bytes = 0;
+static size_t pt_cache_limit() {
+  static const size_t lim = [] {
+    const char* e = getenv("ACE_B200_PT_CACHE_GB");
+    return (size_t)(e ? atof(e) : 24.0) << 30;
+  }();
+  return lim;
+}
+// the cache only takes memory nobody needs: it stops growing for good once less than 40 GB of the
+// device would stay free (keys and the working sets of the images in flight come first)
+thread_local bool g_pt_cache_full = false;
+static bool pt_cache_has_room(size_t bytes) {
+  if (g_pt_cache_full) return false;
+  static thread_local unsigned calls = 0;
+  if ((calls++ & 63) == 0) {  // cudaMemGetInfo is not free: look every 64th insertion
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess || fr < bytes + ((size_t)40 << 30)) g_pt_cache_full = true;
+  }
+  return !g_pt_cache_full;
+}
+// cache memory comes in 1 GiB slabs (6 044 cudaMalloc calls cost 17 s on the first image)
+thread_local std::vector<char*> g_pt_slabs;
+thread_local size_t             g_pt_slab_left = 0;
+static u64* pt_cache_take(size_t bytes) {
+  constexpr size_t kSlab = (size_t)1 << 30;
+  if (bytes > kSlab) return nullptr;
+  if (g_pt_slab_left < bytes) {
+    char* p = nullptr;
+    if (cudaMalloc(&p, kSlab) != cudaSuccess) {
+      cudaGetLastError();
+      g_pt_cache_full = true;
+      return nullptr;
+    }
+    g_pt_slabs.push_back(p);
+    g_pt_slab_left = kSlab;
+  }
+  char* at = g_pt_slabs.back() + (((size_t)1 << 30) - g_pt_slab_left);
+  g_pt_slab_left -= bytes;
+  return reinterpret_cast<u64*>(at);
+}
 char*             g_wfile_dev = nullptr;  // the same bytes in HBM: Pt_from_msg encodes from there
 const LutEntry*   g_lut   = nullptr;
 uint64_t          g_nent  = 0;
@@ -1124,6 +1167,11 @@ API bool Pt_mgr_init(const char* fname) {  // pt_mgr.c:35-110 (message files onl
   return true;
 }
 API void Pt_mgr_fini(void) {
+  for (char* p : g_pt_slabs) cudaFree(p);  // the calling thread's plaintext cache
+  g_pt_slabs.clear();
+  g_pt_slab_left = 0;
+  g_pt_cache.clear();
+  g_pt_cache_bytes = 0;
   if (g_wfile_dev) cudaFree(g_wfile_dev);
   g_wfile_dev = nullptr;
   g_wfile.clear();
@@ -1150,7 +1198,32 @@ API void Pt_from_msg(void* pt, uint32_t index, size_t len, uint32_t scale, uint3
   if (level == 0) level = (uint32_t)c->L;
   init_plain(plain, c->N / 2, level, pow(Get_default_sc(), scale), scale);
   guard([&] {
-    g_queue->encode(EncodeJob{U(plain->_poly._data), g_wfile_dev + e.ent_ofst,
+    // Plaintext cache (the "encode cache" alternative to pre-encoded weight files):
+    // the weights are constants of the model, so the plaintext of (entry, level, degree) is the
+    // same for every image.  Each host thread keeps what it has encoded in HBM (its own stream
+    // orders producer and consumers) and hands it out by renaming the caller's limbs -- no
+    // copy, no encode; 11.5 GB per thread for ResNet-20.  ACE_B200_PT_CACHE_GB (default 24, 0 =
+    // off) bounds it; beyond the bound plaintexts are encoded as before.
+    const u64 key = (u64)index | ((u64)level << 32) | ((u64)scale << 48);
+    const size_t bytes = (size_t)level * c->N * sizeof(u64);
+    auto it = g_pt_cache.find(key);
+    if (it != g_pt_cache.end()) {
+      g_queue->alias(U(plain->_poly._data), it->second, level);
+      c->tr(Context::TR_ENCODE, level);  // the reference would encode: keep the op trace complete
+      return;
+    }
+    u64* dst = U(plain->_poly._data);
+    u64* keep = nullptr;
+    if (!g_eager && g_pt_cache_bytes + bytes <= pt_cache_limit() && pt_cache_has_room(bytes)) {
+      keep = pt_cache_take(bytes);  // nullptr only means "do not cache", it must not disturb the run
+      if (keep) {
+        g_pt_cache[key] = keep;
+        g_pt_cache_bytes += bytes;
+        dst = keep;
+      }
+    }
+    g_queue->encode(EncodeJob{dst, g_wfile_dev + e.ent_ofst,
                               g_etype == DE_MSG_F32 ? 0 : 1, (u32)len, level, 0, scale, 0});
+    if (keep) g_queue->alias(U(plain->_poly._data), keep, level);
   });
 }

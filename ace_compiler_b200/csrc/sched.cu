@@ -264,6 +264,21 @@ void Scheduler::free(u64* block) {
   maybe_flush();
 }
 
+void Scheduler::alias(u64* dst, const u64* src, size_t n_limbs) {
+  if (live_ + n_limbs + 8 > table_.size() / 2) grow();
+  if (eager) { copy(dst, src, n_limbs); return; }
+  for (size_t i = 0; i < n_limbs; i++) {
+    u64* o = dst + i * c_->N();
+    Limb& l = limb(o);
+    kill_if_unread(l);
+    if (!l.alias) aliased_.push_back(o);
+    l.alias = src + i * c_->N();
+    l.is_zero = 0;
+  }
+  n_ops += n_limbs;
+  maybe_flush();
+}
+
 void Scheduler::zero(u64* r, size_t n_limbs) {
   if (live_ + n_limbs + 8 > table_.size() / 2) grow();
   for (size_t i = 0; i < n_limbs; i++) {

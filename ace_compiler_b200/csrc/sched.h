@@ -108,6 +108,9 @@ class Scheduler {
   void rescale(u64* out, const u64* in, u32 num_q);           // Rescale
   u64* alloc(size_t n_limbs, bool zeroed);                    // zero fill is a recorded op
   void free(u64* block);                                      // deferred
+  // reads of the n limbs at dst are served from src from now on (until dst is written or freed):
+  // how a cached, read-only result is handed out without a copy (plaintext cache of rt_shim.cu)
+  void alias(u64* dst, const u64* src, size_t n_limbs);
   // the caller is about to use the stream itself: issue everything recorded so far
   void flush();
   bool empty() const { return ops_.empty() && frees_.empty(); }

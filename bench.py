@@ -404,6 +404,10 @@ def run_ours(args):
         json.dump({"model": MODEL, "classes": TRACE_CLASSES, "per_image": trace_to_json(trace)},
                   open(path, "w"), indent=0)
         print("trace written to", path, file=sys.stderr)
+        out_dir = os.path.join(ROOT, "gpurun_out")  # the GPU box only brings this directory back
+        if os.path.isdir(out_dir):
+            json.dump({"model": MODEL, "classes": TRACE_CLASSES, "per_image": trace_to_json(trace)},
+                      open(os.path.join(out_dir, MODEL + ".trace.json"), "w"), indent=0)
     m.close()
 
     # ---- rooflines, all measured live: the dominant kernel family (batched forward NTT over all
