@@ -69,8 +69,10 @@ __device__ __forceinline__ u64 csub64(u64 a, u64 m) { return a >= m ? a - m : a;
 // NoHook: nothing, the calls vanish at compile time.
 struct NoHook {
   static constexpr bool kActive = false;
+  static constexpr u32  post_mode = 0;
+  const u64*            aux = nullptr;
   __device__ __forceinline__ u64 pre(u64 v) const { return v; }
-  __device__ __forceinline__ u64 post(u64 y, u32) const { return y; }
+  __device__ __forceinline__ u64 post(u64 y, u64, u32) const { return y; }
 };
 struct FusedHook {
   static constexpr bool kActive = true;
@@ -92,16 +94,39 @@ struct FusedHook {
   __device__ __forceinline__ u64 pre(u64 v) const {
     return pre_mode ? mul_shoup(switch_modulus(v, q_from, q), pw, pwsh, q) : v;
   }
-  __device__ __forceinline__ u64 post(u64 y, u32 idx) const {
-    if (post_mode == 1) return add_mod(mul_shoup(aux[idx], ew, ewsh, q), y, q);
+  // a = the epilogue operand aux[idx], fetched by the caller (staged through shared memory)
+  __device__ __forceinline__ u64 post(u64 y, u64 a, u32 idx) const {
+    if (post_mode == 1) return add_mod(mul_shoup(a, ew, ewsh, q), y, q);
     if (post_mode == 2) {
-      u64 v = mul_shoup(sub_mod(aux[idx], y, q), ew, ewsh, q);
+      u64 v = mul_shoup(sub_mod(a, y, q), ew, ewsh, q);
       if (add != nullptr) v = add_mod(v, add[idx], q);
       return v;
     }
     return y;
   }
 };
+// The epilogue operand of a tile (16 rows x 256 coefficients of `aux`) is copied into shared
+// memory with cp.async at the START of the second kernel -- coalesced 16-byte chunks, no
+// registers, in flight during both passes -- in groups of 16 coefficients 144 bytes apart, so
+// that each thread later reads its 16 consecutive coefficients without bank conflicts.  (Loading
+// it at the end with per-thread strided loads made the fused transform SLOWER than transform +
+// separate tail kernel: 124.8 vs 111.6 us for a Mod_down at l = 34.)
+constexpr u32 kAuxGroup = 18, kAuxRow = 16 * kAuxGroup;  // words
+constexpr size_t kAuxSmem = 16 * kAuxRow * sizeof(u64);  // 36 864 bytes
+__device__ __forceinline__ void stage_aux(u64* saux, const u64* aux_tile) {
+  const u32 t = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const u32 id = t + 256 * i, row = id >> 7, p = (id & 127) * 2;
+    const u32 dst = (u32)__cvta_generic_to_shared(saux + row * kAuxRow + kAuxGroup * (p >> 4) + (p & 15));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(aux_tile + row * 256 + p) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void stage_aux_wait() {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+}
 template <class B> struct HookOf { typedef NoHook type; static __device__ __forceinline__ NoHook make(const DeviceTables&, const B&, u32) { return NoHook(); } };
 template <> struct HookOf<NttFusedBatch> {
   typedef FusedHook type;
@@ -371,6 +396,8 @@ __device__ __forceinline__ void fwd_rows_body(const DeviceTables& T, u32 g, u64*
   u64* srow = sm + rho * kRowPad;
 #define PA(i, h) (tw + (256 << (i)) + (r << (i)) + (h))
 #define PB(i, h) (tw + (4096 << (i)) + ((16 * r + j) << (i)) + (h))
+  u64* saux = sm + 16 * kRowPad;  // (fused batches only: the launch provides the room)
+  if (H::kActive && hook.post_mode) stage_aux(saux, hook.aux + blockIdx.x * 4096);
   ACE_TW_DECL;
   ACE_TW_PRELOAD(PA, PB, 15)
   E x[16];
@@ -396,12 +423,21 @@ __device__ __forceinline__ void fwd_rows_body(const DeviceTables& T, u32 g, u64*
 #undef PA
 #undef PB
   ulonglong2* o = reinterpret_cast<ulonglong2*>(row + 16 * j);
+  if (H::kActive && hook.post_mode) {
+    stage_aux_wait();
+    const ulonglong2* sa = reinterpret_cast<const ulonglong2*>(saux + rho * kAuxRow + kAuxGroup * j);
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    const u32 at = r * 256 + 16 * j + 2 * k;
-    o[k] = make_ulonglong2(hook.post(A::to_canonical(x[2 * k], M), at),
-                           hook.post(A::to_canonical(x[2 * k + 1], M), at + 1));
+    for (int k = 0; k < 8; k++) {
+      const u32 at = r * 256 + 16 * j + 2 * k;
+      const ulonglong2 a = sa[k];
+      o[k] = make_ulonglong2(hook.post(A::to_canonical(x[2 * k], M), a.x, at),
+                             hook.post(A::to_canonical(x[2 * k + 1], M), a.y, at + 1));
+    }
+    return;
   }
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    o[k] = make_ulonglong2(A::to_canonical(x[2 * k], M), A::to_canonical(x[2 * k + 1], M));
 }
 
 // ---------------- inverse K1: DIT stages m = 1 .. 128 inside a row ---------------------------
@@ -505,7 +541,7 @@ enum { FWD_COLS = 0, FWD_ROWS = 1, INV_ROWS = 2, INV_COLS = 3 };
 
 template <int KIND, class B, bool PRE>
 __global__ void __launch_bounds__(kThreads, PRE ? 1 : 3) ntt16_kernel(DeviceTables T, const __grid_constant__ B b) {
-  __shared__ u64 sm[(KIND == FWD_COLS || KIND == INV_COLS) ? 4096 : 16 * kRowPad];
+  extern __shared__ __align__(16) u64 sm[];  // kSmem<KIND, B>() bytes
   // last limbs first: the special primes (slowest arithmetic) sit at the end of a batch and
   // should not be the tail of the launch
   const u32 limb = gridDim.y - 1 - blockIdx.y, g = b.g[limb];
@@ -538,8 +574,8 @@ __global__ void __launch_bounds__(kThreads, PRE ? 1 : 3) ntt16_kernel(DeviceTabl
 template <int DIR, class B, bool PRE>
 __global__ void __launch_bounds__(kThreads, PRE ? 1 : 3) ntt16_cluster_kernel(DeviceTables T, const __grid_constant__ B b) {
   extern __shared__ __align__(16) u64 dyn_sm[];
-  u64* sm  = dyn_sm;                  // exchange between the two passes of a phase
-  u64* xin = dyn_sm + 16 * kRowPad;   // what the peers hand over for the second phase
+  u64* sm  = dyn_sm;                             // exchange between the two passes (+ epilogue operand)
+  u64* xin = dyn_sm + 16 * kRowPad + 16 * kAuxRow;  // what the peers hand over for the second phase
   cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
   cl.barrier_arrive();  // matched by the barrier_wait() before the first remote store
   const u32 limb = gridDim.y - 1 - blockIdx.y, g = b.g[limb];
@@ -624,14 +660,26 @@ bool ntt16_usable(const DeviceTables& T) { return T.logN == 16 && T.ftw2 != null
 
 // first kernel: plain launch; second kernel: programmatic dependent launch (it may start, and
 // fetch its twiddles, before the first has finished; pdl_wait() orders the data)
+template <int KIND, class B>
+constexpr size_t kernel_smem() {
+  return (KIND == FWD_COLS || KIND == INV_COLS)
+             ? 4096 * sizeof(u64)
+             : 16 * kRowPad * sizeof(u64) + (HookOf<B>::type::kActive && KIND == FWD_ROWS ? kAuxSmem : 0);
+}
 template <int K1, int K2, class B, bool PRE>
 static void launch_pair(const DeviceTables& T, const B& b, cudaStream_t s) {
   dim3 grid(16, b.n);
-  ntt16_kernel<K1, B, PRE><<<grid, kThreads, 0, s>>>(T, b);
+  static bool attr = false;
+  if (!attr) {  // the fused second kernel needs more than the 48 KB that are available by default
+    cudaFuncSetAttribute(ntt16_kernel<K2, B, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)kernel_smem<K2, B>());
+    attr = true;
+  }
+  ntt16_kernel<K1, B, PRE><<<grid, kThreads, kernel_smem<K1, B>(), s>>>(T, b);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = kernel_smem<K2, B>();
   cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -640,7 +688,7 @@ static void launch_pair(const DeviceTables& T, const B& b, cudaStream_t s) {
   cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, ntt16_kernel<K2, B, PRE>, T, b);
 }
-constexpr size_t kClusterSmem = 2 * 16 * kRowPad * sizeof(u64);  // 69 632 bytes
+constexpr size_t kClusterSmem = 2 * 16 * kRowPad * sizeof(u64) + kAuxSmem;  // exchange + hand-over + epilogue operand
 // 0: not probed, 1: clusters of 16 can be placed, -1: they cannot (or ACE_B200_NTT_NO_CLUSTER)
 template <int DIR, class B, bool PRE>
 static bool launch_cluster(const DeviceTables& T, const B& b, cudaStream_t s) {
