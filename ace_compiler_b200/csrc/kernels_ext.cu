@@ -181,21 +181,71 @@ void launch_mul_scalar_add(const DeviceTables& T, u64* r, const u64* acc, const 
 // memory and writes (and, when accumulating, reads) the destination block with coalesced accesses
 // instead of 8-byte scattered ones (round 1: 0.54 of the HBM peak, top stall long_scoreboard).
 template <bool STAGED>
-__global__ void __launch_bounds__(256) ksw_inner_rot_kernel(
+__global__ void __launch_bounds__(STAGED ? 128 : 256) ksw_inner_rot_kernel(
     DeviceTables T, u64* __restrict__ out0, u64* __restrict__ out1, const u64* __restrict__ ext,
     const u64* __restrict__ own, u32 part_size, const u64* __restrict__ key0,
     const u64* __restrict__ key1, u32 beta, u32 num_q, u32 L, u32 K, const u64* __restrict__ c0,
     const u64* __restrict__ pmodq, const u64* __restrict__ pmodq_sh,
     const int64_t* __restrict__ scatter, int acc0_flag, int acc1_flag) {
-  __shared__ u64 st0[STAGED ? 256 : 1], st1[STAGED ? 256 : 1];
   const u32     o = blockIdx.y;
   const u32     g = o < num_q ? o : L + (o - num_q);
   const u32     W = num_q + K;
   const Modulus m = T.mod[g];
-  const u32     n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (!STAGED && n >= T.N) return;
-  u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+  if (STAGED) {
+    // 128 threads x 2 consecutive coefficients: every stream (beta digits, two key polynomials)
+    // is read with 16-byte loads; the block of 256 results is permuted in shared memory
+    __shared__ u64 st0[256], st1[256];
+    __shared__ u32 blk;
+    const u32 n = blockIdx.x * 256 + 2 * threadIdx.x;
+    u64 lo0[2] = {0, 0}, hi0[2] = {0, 0}, lo1[2] = {0, 0}, hi1[2] = {0, 0};
 #pragma unroll 3
+    for (u32 j = 0; j < beta; j++) {
+      const bool mine = own != nullptr && o < num_q && o / part_size == j;
+      const u64* ep = mine ? own + (size_t)o * T.N + n : ext + ((size_t)j * W + o) * T.N + n;
+      const ulonglong2 e  = *reinterpret_cast<const ulonglong2*>(ep);
+      const ulonglong2 k0 = *reinterpret_cast<const ulonglong2*>(key0 + ((size_t)j * (L + K) + g) * T.N + n);
+      const ulonglong2 k1 = *reinterpret_cast<const ulonglong2*>(key1 + ((size_t)j * (L + K) + g) * T.N + n);
+      mac128(lo0[0], hi0[0], e.x, k0.x); mac128(lo0[1], hi0[1], e.y, k0.y);
+      mac128(lo1[0], hi1[0], e.x, k1.x); mac128(lo1[1], hi1[1], e.y, k1.y);
+    }
+    u64 v0[2], v1[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      v0[h] = reduce128(lo0[h], hi0[h], m);
+      v1[h] = reduce128(lo1[h], hi1[h], m);
+    }
+    if (c0 != nullptr && o < num_q) {
+      const ulonglong2 c = *reinterpret_cast<const ulonglong2*>(c0 + (size_t)o * T.N + n);
+      v0[0] = add_mod(v0[0], mul_shoup(c.x, pmodq[o], pmodq_sh[o], m.q), m.q);
+      v0[1] = add_mod(v0[1], mul_shoup(c.y, pmodq[o], pmodq_sh[o], m.q), m.q);
+    }
+    u32 tg[2] = {n, n + 1};
+    if (scatter) {
+      const longlong2 sc = *reinterpret_cast<const longlong2*>(scatter + n);
+      tg[0] = (u32)sc.x; tg[1] = (u32)sc.y;
+    }
+    st0[tg[0] & 255] = v0[0]; st0[tg[1] & 255] = v0[1];
+    st1[tg[0] & 255] = v1[0]; st1[tg[1] & 255] = v1[1];
+    if (threadIdx.x == 0) blk = tg[0] & ~255u;
+    __syncthreads();
+    const size_t pos = (size_t)o * T.N + blk + 2 * threadIdx.x;
+    ulonglong2 r0 = make_ulonglong2(st0[2 * threadIdx.x], st0[2 * threadIdx.x + 1]);
+    ulonglong2 r1 = make_ulonglong2(st1[2 * threadIdx.x], st1[2 * threadIdx.x + 1]);
+    if (acc0_flag) {
+      const ulonglong2 p = *reinterpret_cast<const ulonglong2*>(out0 + pos);
+      r0.x = add_mod(p.x, r0.x, m.q); r0.y = add_mod(p.y, r0.y, m.q);
+    }
+    if (acc1_flag) {
+      const ulonglong2 p = *reinterpret_cast<const ulonglong2*>(out1 + pos);
+      r1.x = add_mod(p.x, r1.x, m.q); r1.y = add_mod(p.y, r1.y, m.q);
+    }
+    *reinterpret_cast<ulonglong2*>(out0 + pos) = r0;
+    *reinterpret_cast<ulonglong2*>(out1 + pos) = r1;
+    return;
+  }
+  const u32 n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= T.N) return;
+  u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
   for (u32 j = 0; j < beta; j++) {
     const bool mine = own != nullptr && o < num_q && o / part_size == j;
     const u64 e = mine ? own[(size_t)o * T.N + n] : ext[((size_t)j * W + o) * T.N + n];
@@ -207,22 +257,6 @@ __global__ void __launch_bounds__(256) ksw_inner_rot_kernel(
   u64 v0 = reduce128(lo0, hi0, m), v1 = reduce128(lo1, hi1, m);
   if (c0 != nullptr && o < num_q)
     v0 = add_mod(v0, mul_shoup(c0[(size_t)o * T.N + n], pmodq[o], pmodq_sh[o], m.q), m.q);
-  if (STAGED) {
-    const u32 target = scatter ? (u32)scatter[n] : n;
-    st0[target & 255] = v0;
-    st1[target & 255] = v1;
-    __shared__ u32 blk;
-    if (threadIdx.x == 0) blk = target & ~255u;
-    __syncthreads();
-    const size_t pos = (size_t)o * T.N + blk + threadIdx.x;
-    v0 = st0[threadIdx.x];
-    v1 = st1[threadIdx.x];
-    if (acc0_flag) v0 = add_mod(out0[pos], v0, m.q);
-    if (acc1_flag) v1 = add_mod(out1[pos], v1, m.q);
-    out0[pos] = v0;
-    out1[pos] = v1;
-    return;
-  }
   const size_t pos = (size_t)o * T.N + (scatter ? (u32)scatter[n] : n);
   if (acc0_flag) v0 = add_mod(out0[pos], v0, m.q);
   if (acc1_flag) v1 = add_mod(out1[pos], v1, m.q);
@@ -238,7 +272,7 @@ void launch_ksw_inner_rot(const DeviceTables& T, u64* out0, u64* out1, const u64
   prof::Scope prof_scope_("ksw_inner_rot", s);
   dim3 grid((T.N + 255) / 256, num_q + K);
   if (T.N % 256 == 0)
-    ksw_inner_rot_kernel<true><<<grid, 256, 0, s>>>(T, out0, out1, ext, own, part_size, key0, key1, beta,
+    ksw_inner_rot_kernel<true><<<grid, 128, 0, s>>>(T, out0, out1, ext, own, part_size, key0, key1, beta,
                                                     num_q, L, K, c0, pmodq, pmodq_sh, scatter,
                                                     acc0 ? 1 : 0, acc1 ? 1 : 0);
   else
