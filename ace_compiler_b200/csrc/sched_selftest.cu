@@ -184,6 +184,15 @@ std::vector<uint64_t> run_program(uint64_t seed, u32 n_ops, u32 sync_permille, b
   int64_t last_mu_in = -1;  // the source block of the previous Decomp_modup: repeated now and then
   u32 last_mu_nq = 0, last_mu_part = 0;
   for (int i = 0; i < 6; i++) new_block(2 + rng.below(9), rng.below(2));
+  // read-only blocks (cached plaintexts): written once here, only ever the source of an alias
+  std::vector<Block> cblk;
+  for (int i = 0; i < 3; i++) {
+    be->next_tag = 1000 + i;
+    Block c{S.alloc(8, false), 8, -1};
+    S.encode(EncodeJob{c.p, (const void*)(uintptr_t)(7 + i), 0, 1, 8, 0, 1, 0});
+    cblk.push_back(c);
+  }
+  S.flush();
   auto pick = [&](size_t min_limbs) -> int {  // a live block with at least min_limbs, or -1
     for (int tries = 0; tries < 16; tries++) {
       int b = (int)rng.below((u32)blk.size());
@@ -227,7 +236,17 @@ std::vector<uint64_t> run_program(uint64_t seed, u32 n_ops, u32 sync_permille, b
 #define TR(...) do { if (trace) fprintf(stderr, __VA_ARGS__); } while (0)
   for (u32 op = 0; op < n_ops; op++) {
     const u32 kind = rng.below(100);
-    if (kind < 40) {  // limb add / sub / mul; operands share the limb index (one modulus per index,
+    if (kind >= 37 && kind < 40) {  // Scheduler::alias: reads of a block are served from another one
+                                    // (the plaintext cache of rt_shim.cu): later writes to either
+                                    // side, frees and block consumers must all see the right data
+      // (the source of an alias must stay unwritten while the alias lives: the constant blocks)
+      int bd = pick(1);
+      const Block& cs = cblk[rng.below((u32)cblk.size())];
+      u32 n = 1 + rng.below((u32)std::min(blk[bd].n, cs.n));
+      TR("%u alias %s <- const x%u\n", op, where(limb(bd, 0)), n);
+      if (eager) S.copy(limb(bd, 0), cs.p, n);  // reference semantics: the data is there
+      else S.alias(limb(bd, 0), cs.p, n);
+    } else if (kind < 40) {  // limb add / sub / mul; operands share the limb index (one modulus per index,
                       // as in real programs: residues stay canonical), blocks may alias
       int br = pick(1), ba = pick(1), bb = pick(1);
       u32 l = rng.below((u32)std::min(blk[br].n, std::min(blk[ba].n, blk[bb].n)));
@@ -325,6 +344,7 @@ std::vector<uint64_t> run_program(uint64_t seed, u32 n_ops, u32 sync_permille, b
     stats[6] = S.n_modup; stats[7] = S.n_modup_shared;
   }
   for (const Block& b : blk) S.free(b.p);
+  for (const Block& b : cblk) S.free(b.p);
   S.flush();
   return hashes;
 }
