@@ -36,8 +36,12 @@
 //          values grow by at most 4q per stage, 16 stages stay below 65 q < 2^64; one Barrett step
 //          at the end.  5 IMAD.WIDE.U32 + 4 IMAD per butterfly (w v and -est q accumulate into one
 //          64-bit value: t = v w + est (2^64 - q)).
-//   INT/CS q < 2^61 (the 60-bit special primes): the same estimate with the invariant [0, 8q):
-//          u is brought below 4q first.
+//   INT/CS q < 2^61 (the 60-bit special primes): exact Shoup quotient (t < 2q, +2q per stage) and
+//          ONE conditional subtraction per coefficient per radix-16 pass instead of one per
+//          butterfly: a pass starts below 8q and ends below 16q <= 2^64 (q < 2^60; for
+//          2^60 <= q < 2^61 the bounds are 4q / 8q with a second subtraction mid-pass).
+//          Arithmetic ceiling 0.95 T butterflies/s against 0.79 T/s for round 2's first form
+//          (conditional subtraction in every butterfly).
 // Twiddles: {w, w'} interleaved (one 16-byte load per butterfly) for the integer forms, one double
 // for the FP64 form.
 #include <cooperative_groups.h>
@@ -136,15 +140,9 @@ template <> struct HookOf<NttFusedBatch> {
 // ------------------------------------------------------------------------------------------
 // integer arithmetic
 // ------------------------------------------------------------------------------------------
-struct ModK {  // per-CTA constants of the integer butterfly
-  u64 q;
-  u32 nq0, nq1;  // 2^64 - q
-  u64 q4;        // 4q
-  u64 mu;        // floor(2^64 / q)
-};
-
 // t = v w - est q  (mod 2^64),  est = floor(v w' / 2^64) - {0,1,2}:   0 <= t < 4q for any v < 2^64
-__device__ __forceinline__ u64 mul_lazy4(u64 v, const ulonglong2 tw, const ModK& M) {
+template <class MK>
+__device__ __forceinline__ u64 mul_lazy4(u64 v, const ulonglong2 tw, const MK& M) {
   const u32 v0 = (u32)v, v1 = (u32)(v >> 32);
   const u32 w0 = (u32)tw.x, w1 = (u32)(tw.x >> 32);
   const u32 s0 = (u32)tw.y, s1 = (u32)(tw.y >> 32);
@@ -156,46 +154,72 @@ __device__ __forceinline__ u64 mul_lazy4(u64 v, const ulonglong2 tw, const ModK&
   return ((u64)hi << 32) | (u32)t;
 }
 
+// CSUB = false: q < 2^57, short quotient estimate, nothing is ever subtracted (65 q < 2^64).
+// CSUB = true : q < 2^61, exact quotient (t < 2q, +2q per stage) and ONE conditional subtraction
+//               per coefficient per pass -- when it enters the pass (from_mid) -- instead of one per
+//               butterfly: q < 2^60: in < 8q, four stages, < 16q <= 2^64;  2^60 <= q < 2^61: in
+//               < 4q and a second subtraction after the second stage (< 8q <= 2^64).
 template <bool CSUB>
 struct ArithInt {
   typedef u64        E;   // a coefficient in registers
   typedef ulonglong2 TW;  // a twiddle
-  typedef ModK       Mod;
+  struct Mod {
+    u64 q;
+    u32 nq0, nq1;  // 2^64 - q
+    u64 q4;        // 4q
+    u64 mu;        // floor(2^64 / q)
+    u64 top;       // CSUB: bound enforced at the start of a pass (8q, or 4q for q >= 2^60)
+    u64 q2;        // 2q
+    bool mid;      // CSUB: q >= 2^60, subtract again after the second stage
+  };
   static __device__ __forceinline__ Mod make(const Modulus& m) {
     const u64 nq = 0 - m.q;
-    return ModK{m.q, (u32)nq, (u32)(nq >> 32), 4 * m.q, m.mu_hi};
+    const bool big = (m.q >> 60) != 0;
+    return Mod{m.q, (u32)nq, (u32)(nq >> 32), 4 * m.q, m.mu_hi, big ? 4 * m.q : 8 * m.q, 2 * m.q, big};
   }
   static __device__ __forceinline__ const TW* fwd_table(const DeviceTables& T, u32 g) { return T.ftw2 + (size_t)g * 65536; }
   static __device__ __forceinline__ const TW* inv_table(const DeviceTables& T, u32 g) { return T.itw2 + (size_t)g * 65536; }
   static __device__ __forceinline__ const TW* scale_table(const DeviceTables& T, u32 g) { return T.ips2 + (size_t)g * 65536; }
   static __device__ __forceinline__ TW ld(const TW* p) { return __ldg(p); }
   static __device__ __forceinline__ E from_canonical(u64 x, const Mod&) { return x; }
-  static __device__ __forceinline__ E from_mid(u64 x) { return x; }
+  // a value that went through shared or global memory: the start of a pass
+  static __device__ __forceinline__ E from_mid(u64 x, const Mod& M) { return CSUB ? csub64(x, M.top) : x; }
   static __device__ __forceinline__ u64 to_mid(E x) { return x; }
-  // (u, v) -> (u + w v, u - w v).  lazy: +4q per stage.  CSUB: in/out in [0, 8q).
+  // (u, v) -> (u + w v, u - w v)
   static __device__ __forceinline__ void bfly(E& u, E& v, const TW tw, const Mod& M) {
-    const u64 t = mul_lazy4(v, tw, M);
-    const u64 a = CSUB ? csub64(u, M.q4) : u;
-    u = a + t;
-    v = a - t + M.q4;
+    if (CSUB) {
+      const u64 t = v * tw.x - __umul64hi(v, tw.y) * M.q;  // exact Shoup: t < 2q for any v
+      const u64 a = u;
+      u = a + t;
+      v = a - t + M.q2;
+    } else {
+      const u64 t = mul_lazy4(v, tw, M);  // t < 4q
+      const u64 a = u;
+      u = a + t;
+      v = a - t + M.q4;
+    }
   }
   static __device__ __forceinline__ void bfly_first(E& u, E& v, const Mod& M) {  // canonical in, w = 1
     const u64 a = u;
     u = a + v;
     v = a + M.q - v;
   }
-  static __device__ __forceinline__ void bfly_one(E& u, E& v, const Mod& M) {  // v < 4q, w = 1
-    const u64 a = CSUB ? csub64(u, M.q4) : u, t = v;
+  static __device__ __forceinline__ void bfly_one(E& u, E& v, const Mod& M) {  // v < 2q, w = 1
+    const u64 a = u, t = v;
     u = a + t;
-    v = a - t + M.q4;
+    v = a - t + (CSUB ? M.q2 : M.q4);
   }
-  static __device__ __forceinline__ void fold16(E (&)[16], const Mod&) {}
+  static __device__ __forceinline__ void fold_after(E (&x)[16], const Mod& M, int stage) {
+    if (CSUB && stage == 1 && M.mid) {
+#pragma unroll
+      for (int k = 0; k < 16; k++) x[k] = csub64(x[k], M.q4);
+    }
+  }
   static __device__ __forceinline__ u64 to_canonical(E x, const Mod& M) {
-    if (CSUB) return csub64(csub64(csub64(x, M.q4), 2 * M.q), M.q);
     return csub64(x - __umul64hi(x, M.mu) * M.q, M.q);  // the estimate is short by at most 1
   }
   static __device__ __forceinline__ u64 scale_to_canonical(E x, const TW tw, const Mod& M) {
-    const u64 y = mul_lazy4(x, tw, M);  // < 4q
+    const u64 y = mul_lazy4(x, tw, M);  // < 4q for any x
     return csub64(csub64(y, 2 * M.q), M.q);
   }
 };
@@ -231,7 +255,7 @@ struct ArithDP {
   static __device__ __forceinline__ E from_canonical(u64 x, const Mod&) {  // x < 2^52
     return __dadd_rn(__longlong_as_double((long long)(x | 0x4330000000000000ull)), -kTwo52);
   }
-  static __device__ __forceinline__ E from_mid(u64 x) { return __longlong_as_double((long long)x); }
+  static __device__ __forceinline__ E from_mid(u64 x, const Mod&) { return __longlong_as_double((long long)x); }
   static __device__ __forceinline__ u64 to_mid(E x) { return (u64)__double_as_longlong(x); }
   // |u| <= 1.5 q and |v| <= 1.5 q < 2^51 in; |out| <= |u| + q
   static __device__ __forceinline__ void bfly(E& u, E& v, const TW w, const Mod& M) {
@@ -250,9 +274,11 @@ struct ArithDP {
     const double c = __dadd_rn(__fma_rn(x, M.qinv, kMagic), -kMagic);
     return __fma_rn(-c, M.q, x);
   }
-  static __device__ __forceinline__ void fold16(E (&x)[16], const Mod& M) {
+  static __device__ __forceinline__ void fold_after(E (&x)[16], const Mod& M, int stage) {
+    if (stage == 0 || stage == 2) {
 #pragma unroll
-    for (int k = 0; k < 16; k++) x[k] = fold(x[k], M);
+      for (int k = 0; k < 16; k++) x[k] = fold(x[k], M);
+    }
   }
   static __device__ __forceinline__ u64 nonneg_to_u64(double y, const Mod& M) {  // |y| < q
     const double z = y < 0.0 ? __dadd_rn(y, M.q) : y;
@@ -279,7 +305,7 @@ struct ArithDP {
       _Pragma("unroll") for (int e_ = 0; e_ < tr_; e_++)              \
         A::bfly(x[2 * tr_ * h_ + e_], x[2 * tr_ * h_ + e_ + tr_], tw_, M); \
     }                                                                 \
-    if (i_ == 0 || i_ == 2) A::fold16(x, M);                          \
+    A::fold_after(x, M, i_);                                          \
   }
 
 // decimation in time: stage i pairs (k, k + (1 << i)); TW(i, e) = twiddle of offset e (0 <= e < 2^i)
@@ -291,13 +317,13 @@ struct ArithDP {
       _Pragma("unroll") for (int h_ = 0; h_ < 8 / m_; h_++)           \
         A::bfly(x[2 * m_ * h_ + e_], x[2 * m_ * h_ + e_ + m_], tw_, M); \
     }                                                                 \
-    if (i_ == 0 || i_ == 2) A::fold16(x, M);                          \
+    A::fold_after(x, M, i_);                                          \
   }
 // the very first pass of the inverse transform: canonical input, stage m = 1 and half of stage
 // m = 2 multiply by omega^0 = 1
 #define ACE_R16_DIT_HEAD(x, TWF)                                      \
   _Pragma("unroll") for (int h_ = 0; h_ < 8; h_++) A::bfly_first(x[2 * h_], x[2 * h_ + 1], M); \
-  A::fold16(x, M);                                                    \
+  A::fold_after(x, M, 0);                                             \
   _Pragma("unroll") for (int h_ = 0; h_ < 4; h_++) A::bfly_one(x[4 * h_], x[4 * h_ + 2], M); \
   {                                                                   \
     const typename A::TW tw_ = TWF(1, 1);                             \
@@ -310,7 +336,7 @@ struct ArithDP {
       _Pragma("unroll") for (int h_ = 0; h_ < 8 / m_; h_++)           \
         A::bfly(x[2 * m_ * h_ + e_], x[2 * m_ * h_ + e_ + m_], tw_, M); \
     }                                                                 \
-    if (i_ == 2) A::fold16(x, M);                                     \
+    if (i_ == 2) A::fold_after(x, M, 2);                              \
   }
 
 constexpr int kThreads = 256;
@@ -364,7 +390,7 @@ __device__ __forceinline__ void fwd_cols_body(const DeviceTables& T, u32 g, u64*
   for (int k = 0; k < 16; k++) sm[(j + 16 * k) * 16 + c] = A::to_mid(x[k]);
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < 16; k++) x[k] = A::from_mid(sm[(16 * j + k) * 16 + c]);
+  for (int k = 0; k < 16; k++) x[k] = A::from_mid(sm[(16 * j + k) * 16 + c], M);
 #define TW_B(i, h) ACE_TW_GET_B(PB, i, h)
   ACE_R16_FWD(x, TW_B)
 #undef TW_B
@@ -403,11 +429,11 @@ __device__ __forceinline__ void fwd_rows_body(const DeviceTables& T, u32 g, u64*
   E x[16];
   if (XCH) {
 #pragma unroll
-    for (int k = 0; k < 16; k++) x[k] = A::from_mid(xin[rho * kRowPad + 17 * k + j]);
+    for (int k = 0; k < 16; k++) x[k] = A::from_mid(xin[rho * kRowPad + 17 * k + j], M);
   } else {
     pdl_wait();  // the coefficients come from the first kernel
 #pragma unroll
-    for (int k = 0; k < 16; k++) x[k] = A::from_mid(row[j + 16 * k]);
+    for (int k = 0; k < 16; k++) x[k] = A::from_mid(row[j + 16 * k], M);
   }
 #define TW_A(i, h) ACE_TW_GET_A(PA, i, h)
   ACE_R16_FWD(x, TW_A)
@@ -416,7 +442,7 @@ __device__ __forceinline__ void fwd_rows_body(const DeviceTables& T, u32 g, u64*
   for (int k = 0; k < 16; k++) srow[17 * k + j] = A::to_mid(x[k]);
   __syncwarp();
 #pragma unroll
-  for (int k = 0; k < 16; k++) x[k] = A::from_mid(srow[17 * j + k]);
+  for (int k = 0; k < 16; k++) x[k] = A::from_mid(srow[17 * j + k], M);
 #define TW_B(i, h) ACE_TW_GET_B(PB, i, h)
   ACE_R16_FWD(x, TW_B)
 #undef TW_B
@@ -469,7 +495,7 @@ __device__ __forceinline__ void inv_rows_body(const DeviceTables& T, u32 g, u64*
   for (int k = 0; k < 16; k++) srow[17 * j + k] = A::to_mid(x[k]);
   __syncwarp();
 #pragma unroll
-  for (int k = 0; k < 16; k++) x[k] = A::from_mid(srow[17 * k + j]);
+  for (int k = 0; k < 16; k++) x[k] = A::from_mid(srow[17 * k + j], M);
 #define TW_B(i, e) ACE_TW_GET_B(PB, i, e)
   ACE_R16_DIT(x, TW_B)
 #undef TW_B
@@ -505,11 +531,11 @@ __device__ __forceinline__ void inv_cols_body(const DeviceTables& T, u32 g, u64*
   E x[16];
   if (XCH) {
 #pragma unroll
-    for (int k = 0; k < 16; k++) x[k] = A::from_mid(xin[(16 * j + k) * 16 + c]);
+    for (int k = 0; k < 16; k++) x[k] = A::from_mid(xin[(16 * j + k) * 16 + c], M);
   } else {
     pdl_wait();  // the coefficients come from the first kernel
 #pragma unroll
-    for (int k = 0; k < 16; k++) x[k] = A::from_mid(data[(16 * j + k) * 256 + col]);
+    for (int k = 0; k < 16; k++) x[k] = A::from_mid(data[(16 * j + k) * 256 + col], M);
   }
 #define TW_A(i, e) ACE_TW_GET_A(PA, i, e)
   ACE_R16_DIT(x, TW_A)
@@ -518,7 +544,7 @@ __device__ __forceinline__ void inv_cols_body(const DeviceTables& T, u32 g, u64*
   for (int k = 0; k < 16; k++) sm[(16 * j + k) * 16 + c] = A::to_mid(x[k]);
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < 16; k++) x[k] = A::from_mid(sm[(j + 16 * k) * 16 + c]);
+  for (int k = 0; k < 16; k++) x[k] = A::from_mid(sm[(j + 16 * k) * 16 + c], M);
 #define TW_B(i, e) ACE_TW_GET_B(PB, i, e)
   ACE_R16_DIT(x, TW_B)
 #undef TW_B
@@ -724,9 +750,13 @@ static bool no_pre() {
   if (v < 0) v = getenv("ACE_B200_NTT_NO_PRE") ? 1 : 0;
   return v != 0;
 }
+// Forward transforms never take it: measured on B200 (profiles/r2_ntt_nopre.txt) the preloading
+// variant costs 16.2 against 12.4 us at 8 limbs, 20.5 against 18.5 us at 18 and 24.4 against 21.2 us
+// for the 11 special primes; the inverse gains 0.4 us at 8-9 limbs from it.
 template <class B>
 static void ntt16_fwd_impl(const DeviceTables& T, const B& b, cudaStream_t s) {
-  if (b.n <= kSmallBatch && !no_pre()) {
+  static const bool fwd_pre = getenv("ACE_B200_NTT_FWD_PRE") != nullptr;
+  if (b.n <= kSmallBatch && fwd_pre) {
     if (!launch_cluster<0, B, true>(T, b, s)) launch_pair<FWD_COLS, FWD_ROWS, B, true>(T, b, s);
   } else if (!launch_cluster<0, B, false>(T, b, s)) {
     launch_pair<FWD_COLS, FWD_ROWS, B, false>(T, b, s);
