@@ -74,6 +74,7 @@ SIGNATURES = {
                                 vp, vp, u32, u32, C.c_double, u32, u32]),
     "ace_measure_pipe_peaks": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.c_int]),
     "ace_keygen_reference": (C.c_int, [vp, vp, C.c_uint64, u32, vp, sz]),
+    "ace_keygen_reference_stream": (C.c_int, [vp, vp, C.c_uint64, u32, vp, sz, vp, sz]),
     "ace_keygen_autos": (C.c_int, [vp, vp, sz]),
     "ace_sk_export": (C.c_int, [vp, vp]),
     "ace_pk_export": (C.c_int, [vp, vp, vp]),
@@ -341,6 +342,15 @@ class Context:
         sd = (C.c_uint32 * 16)(*[int(x) & 0xFFFFFFFF for x in seed16])
         r = (C.c_int32 * max(1, len(rots)))(*rots)
         self._ck(self.lib.ace_keygen_reference(self.h, sd, counter, tri_base, r, len(rots)))
+
+    def keygen_reference_stream(self, seed16, counter, srandom_seed, tri_pos, rots):
+        """as keygen_reference, for a reference whose rand() is seeded once: the k-th
+        Sample_triangle starts tri_pos[k] draws into the stream (the golden runs' pinning)"""
+        sd = (C.c_uint32 * 16)(*[int(x) & 0xFFFFFFFF for x in seed16])
+        r = (C.c_int32 * max(1, len(rots)))(*rots)
+        tp = (C.c_uint64 * max(1, len(tri_pos)))(*tri_pos)
+        self._ck(self.lib.ace_keygen_reference_stream(self.h, sd, counter, srandom_seed, tp, len(tri_pos),
+                                                      r, len(rots)))
 
     def keygen_autos(self, autos):
         """more switch keys by automorphism index on the current stream (Bootstrap_keygen)"""

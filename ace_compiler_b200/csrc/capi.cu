@@ -289,6 +289,10 @@ int ace_keygen_reference(ace_ctx* ctx, const uint32_t* seed16, uint64_t counter,
                          const int32_t* rots, size_t n) {
   ACE_TRY(ctx->c->keygen_reference(seed16, counter, tri_base, rots, n))
 }
+int ace_keygen_reference_stream(ace_ctx* ctx, const uint32_t* seed16, uint64_t counter, uint32_t srandom_seed,
+                                const uint64_t* tri_pos, size_t n_pos, const int32_t* rots, size_t n) {
+  ACE_TRY(ctx->c->keygen_reference_stream(seed16, counter, srandom_seed, tri_pos, n_pos, rots, n))
+}
 int ace_keygen_autos(ace_ctx* ctx, const uint32_t* auto_idx, size_t n) {
   ACE_TRY(for (size_t i = 0; i < n; i++)
             if (!ctx->c->has_rot_key(auto_idx[i])) ctx->c->gen_auto_key(auto_idx[i]);)

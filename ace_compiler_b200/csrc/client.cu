@@ -133,7 +133,11 @@ struct Context::RngState {
   bool               reference = false;
   refrng::BulkPrng   prng;           // reference mode: BLAKE2Xb stream (uniform, ternary)
   u32                tri_base = 0;   // reference mode: Sample_triangle call k draws from
-  u32                tri_calls = 0;  //   glibc random() after srandom(tri_base + k)
+  u32                tri_calls = 0;  //   glibc random() after srandom(tri_base + k), or -- stream
+  bool               tri_stream = false;  // mode -- from ONE random() stream seeded once, call k
+  refrng::GlibcRandom tri_gen;            // starting tri_pos[k] draws after the seeding (the
+  u64                tri_at = 0;          // reference's harness in pin mode 0: srand() swallowed;
+  std::vector<u64>   tri_pos;             // positions recorded by tests/golden/make_tri_positions.py)
   std::vector<int64_t> host;         // staging for host-sampled values
 };
 
@@ -183,6 +187,15 @@ void Context::rng_pin_reference(const u32* seed16, u64 counter, u32 tri_base) {
   rng_->prng.pin(seed16, counter);
   rng_->tri_base = tri_base;
   rng_->tri_calls = 0;
+  rng_->tri_stream = false;
+}
+void Context::rng_pin_reference_stream(const u32* seed16, u64 counter, u32 srandom_seed, const u64* tri_pos,
+                                       size_t n_pos) {
+  rng_pin_reference(seed16, counter, 0);
+  rng_->tri_stream = true;
+  rng_->tri_gen.srandom(srandom_seed);
+  rng_->tri_at = 0;
+  rng_->tri_pos.assign(tri_pos, tri_pos + n_pos);
 }
 
 // ---- the two samplers behind every key / encryption ------------------------------------------
@@ -209,9 +222,18 @@ void Context::sample_triangle(u64* dst, u32 g0, u32 n_limbs, u32 purpose, u32 di
     return;
   }
   R->host.resize(N);
-  refrng::GlibcRandom g;
-  g.srandom(R->tri_base + R->tri_calls++);
-  g.sample_triangle(R->host.data(), N);
+  if (R->tri_stream) {
+    const u32 k = R->tri_calls++;
+    if (k >= R->tri_pos.size() || R->tri_pos[k] < R->tri_at)
+      throw std::runtime_error("reference stream: no (or an earlier) position recorded for this Sample_triangle call");
+    for (; R->tri_at < R->tri_pos[k]; R->tri_at++) R->tri_gen.random();
+    R->tri_gen.sample_triangle(R->host.data(), N);
+    R->tri_at += N;
+  } else {
+    refrng::GlibcRandom g;
+    g.srandom(R->tri_base + R->tri_calls++);
+    g.sample_triangle(R->host.data(), N);
+  }
   small_to_rns(dst, g0, n_limbs, R->host.data());
 }
 
@@ -382,6 +404,17 @@ void Context::keygen_reference(const u32* seed16, u64 counter, u32 tri_base, con
                                size_t n_rots) {
   ACE_CUDA(cudaSetDevice(device));
   rng_pin_reference(seed16, counter, tri_base);
+  ref_rot_seen_.clear();
+  gen_secret_key();
+  gen_public_key();
+  gen_relin_key();
+  keygen_rotations(rots, n_rots);
+}
+
+void Context::keygen_reference_stream(const u32* seed16, u64 counter, u32 srandom_seed, const u64* tri_pos,
+                                      size_t n_pos, const int32_t* rots, size_t n_rots) {
+  ACE_CUDA(cudaSetDevice(device));
+  rng_pin_reference_stream(seed16, counter, srandom_seed, tri_pos, n_pos);
   ref_rot_seen_.clear();
   gen_secret_key();
   gen_public_key();

@@ -182,6 +182,8 @@ class Context {
   // the reference's own generators (BLAKE2Xb PRNG + glibc rand(), refrng.h) consumed in the
   // reference's order: the keys are bit-identical to the reference's from the same seeds
   void keygen_reference(const u32* seed16, u64 counter, u32 tri_base, const int32_t* rots, size_t n_rots);
+  void keygen_reference_stream(const u32* seed16, u64 counter, u32 srandom_seed, const u64* tri_pos, size_t n_pos,
+                               const int32_t* rots, size_t n_rots);
   void keygen_rotations(const int32_t* rots, size_t n_rots);
   std::set<int32_t> ref_rot_seen_;  // reference mode: rotation values that have a key (Generate_rot_maps)
   void gen_secret_key();
@@ -194,6 +196,7 @@ class Context {
   RngState* rng();
   void rng_seed_for_tests(u64 seed);
   void rng_pin_reference(const u32* seed16, u64 counter, u32 tri_base);
+  void rng_pin_reference_stream(const u32* seed16, u64 counter, u32 srandom_seed, const u64* tri_pos, size_t n_pos);
   void sample_uniform(u64* dst, u32 g0, u32 n_limbs, u32 digit, u64 id);
   void sample_triangle(u64* dst, u32 g0, u32 n_limbs, u32 purpose, u32 digit, u64 id);
   void small_to_rns(u64* dst, u32 g0, u32 n_limbs, const int64_t* host_small);

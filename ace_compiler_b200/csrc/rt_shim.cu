@@ -399,6 +399,27 @@ API int Ace_bootstrap_rot_indices(uint32_t slots, int32_t* out, size_t cap) {
   for (size_t i = 0; i < v.size() && i < cap; i++) out[i] = v[i];
   return (int)v.size();
 }
+// TEST SUPPORT (whole-model parity against the golden runs, tests/model_case.py): after a
+// Prepare_context with ACE_B200_NO_KEYGEN=1, generate the key set the REFERENCE's Prepare_context
+// generates from the same pinned random streams (context.c:56-82: Alloc_ckks_key_generator, then
+// Bootstrap_precom(N/2) -> Bootstrap_keygen: rotation keys by VALUE, then the conjugation key).
+// Later encryptions (Prepare_input) continue the same streams.
+API int Ace_keygen_reference_stream(const uint32_t* seed16, uint64_t counter, uint32_t srandom_seed,
+                                    const uint64_t* tri_pos, size_t n_pos) {
+  Context* c = ctx();
+  if (c != g_ctx) die("Ace_keygen_reference_stream: call it from the thread that prepared the context");
+  CKKS_PARAMS* p = Get_context_params();
+  guard([&] {
+    c->keygen_reference_stream(seed16, counter, srandom_seed, tri_pos, n_pos, p->_rot_idxs, p->_num_rot_idx);
+    if (g_ev->bootstrap_supported()) {
+      std::vector<int32_t> rots = g_ev->bootstrap_rot_indices(c->N / 2);
+      c->keygen_rotations(rots.data(), rots.size());
+      c->gen_auto_key(2 * c->N - 1);
+    }
+    c->sync();
+  });
+  return 0;
+}
 // op trace so far: out[class * 72 + level], classes in the order of Context::TraceClass
 // (modup digit, moddown poly, rescale poly, encode, limb mul, limb add, limb rotate, limb ntt)
 API int Ace_trace(uint64_t* out, size_t cap) {
@@ -556,6 +577,11 @@ API void Ace_set_input(const char* name, size_t idx, const int64_t* c0, const in
   ct->_c0_poly._is_ntt = ct->_c1_poly._is_ntt = true;
   ct->_slots = slots; ct->_scaling_factor = scale; ct->_sf_degree = sf_degree;
   g_inputs[io_key(name, idx)] = ct;
+}
+
+API CIPHER Ace_peek_input(const char* name, size_t idx) {  // test support: look, do not take
+  auto it = g_inputs.find(io_key(name, idx));
+  return it == g_inputs.end() ? nullptr : it->second;
 }
 
 API CIPHERTEXT Get_input_data(const char* name, size_t idx) {  // rtlib.c:74-80
@@ -1127,7 +1153,153 @@ API void Encode_plain_from_double(PLAIN plain, double* input, size_t len, uint32
 }
 API void Free_plain_poly(PLAIN plain) { free_poly_data(&plain->_poly); }
 
-API bool Pt_mgr_init(const char* fname) {  // pt_mgr.c:35-110 (message files only)
+// ---- pre-encoded weights (DE_PLAINTEXT files) -----------------------------------
+// Reference: Pt_mgr_init / Pt_get / Pt_free / Pt_prefetch (pt_mgr.c:35-176), Rt_data_prefetch
+// (rt_data_file.c:61-80), PLAINTEXT_BUFFER and Cast_buffer_to_plain (rt_encode_api.h:22-27,
+// plain_eval.c:132-160).  An entry is {magic "ANTPLAIN", version, size} + the PLAINTEXT struct with
+// _poly._data == NULL + the limbs.  The reference keeps PT_ENTRY_COUNT (default 8) host buffers,
+// slot = index % count, and returns a PLAINTEXT* into the slot; emitted code copies the struct
+// (`dest = *(PLAIN)Pt_get(...)`, ir2c_ctx.h:84-91) and uses it until the slot comes round again.
+// Here the limbs of a slot live in HBM: Pt_get reads the entry into pinned memory, validates it
+// like Cast_buffer_to_plain, and copies the limbs to a FRESH block on the calling thread's
+// stream; the block a slot held before is released through the scheduler's deferred free, so
+// operations recorded against the previous occupant still read its limbs (the reference's
+// synchronous semantics: what was returned stays valid for every call made before the slot
+// is reused).  File and look-up table are shared, the ring is per host thread (as the I/O tables).
+struct PlainBufHdr {  // PLAINTEXT_BUFFER without the flexible member
+  char     magic[8];
+  uint32_t version;
+  uint32_t size;
+};
+constexpr uint32_t kRtVersionFull = 1;  // rt_version.h:15-22 (0.0.0 build 1)
+int                   g_pt_fd = -1;
+uint64_t              g_pt_fsize = 0;
+std::vector<LutEntry> g_pt_lut;
+uint32_t              g_pt_slots = 8, g_pt_prefetch = 2;
+size_t                g_pt_max_entry = 0;
+struct PtSlot {
+  uint32_t    idx = (uint32_t)-1;
+  PLAINTEXT   pt;
+  char*       stage = nullptr;  // pinned
+  cudaEvent_t copied = nullptr;
+};
+thread_local std::vector<PtSlot> g_pt_ring;
+
+API void Pt_prefetch(uint32_t index);
+static bool pt_file_open(int fd, uint64_t fsize, const DataFileHdr& h) {
+  if (h.rt_ver != kRtVersionFull) die("rt data file version mismatch");
+  if (h.lut_ofst > fsize || h.ent_count > (fsize - h.lut_ofst) / sizeof(LutEntry))
+    die("weight data file: look-up table outside the file");
+  g_pt_lut.resize(h.ent_count);
+  const size_t lut_bytes = h.ent_count * sizeof(LutEntry);
+  if (pread(fd, g_pt_lut.data(), lut_bytes, h.lut_ofst) != (ssize_t)lut_bytes) die("failed to read rt data file lookup table");
+  g_pt_max_entry = 0;
+  for (const LutEntry& e : g_pt_lut) {
+    if (e.ent_ofst > fsize || e.size > fsize - e.ent_ofst) die("weight data file: entry outside the file");
+    if (e.size < sizeof(PlainBufHdr) + sizeof(PLAINTEXT)) die("weight data file: plaintext entry too small");
+    g_pt_max_entry = std::max(g_pt_max_entry, (size_t)e.size);
+  }
+  const char* ce = getenv("PT_ENTRY_COUNT");     // rt_env.h:25
+  const char* pe = getenv("PT_PREFETCH_COUNT");  // rt_env.h:27
+  g_pt_slots    = ce && atoi(ce) > 0 ? (uint32_t)atoi(ce) : 8;
+  g_pt_prefetch = pe && atoi(pe) >= 0 ? (uint32_t)atoi(pe) : 2;
+  g_pt_fd = fd;
+  g_pt_fsize = fsize;
+  g_etype = h.ent_type;
+  g_nent  = h.ent_count;
+  for (uint32_t i = 0; i < g_pt_prefetch; i++) Pt_prefetch(i);
+  return true;
+}
+static void pt_ring_drop() {  // the calling thread's ring
+  for (PtSlot& sl : g_pt_ring) {
+    if (sl.idx != (uint32_t)-1 && sl.pt._poly._data) free_poly_data(&sl.pt._poly);
+    if (sl.copied) { cudaEventSynchronize(sl.copied); cudaEventDestroy(sl.copied); }
+    if (sl.stage) cudaFreeHost(sl.stage);
+  }
+  g_pt_ring.clear();
+}
+static void pt_file_close() {
+  if (g_pt_fd < 0) return;
+  pt_ring_drop();
+  close(g_pt_fd);
+  g_pt_fd = -1;
+  g_pt_lut.clear();
+}
+// Pt_prefetch (pt_mgr.c:116-126): the reference starts an asynchronous read into the slot; here
+// the page cache is asked to read ahead, the slot itself is only written by Pt_get
+API void Pt_prefetch(uint32_t index) {
+  if (g_pt_fd < 0 || index >= g_pt_lut.size()) return;  // rt_data_file.c:64: beyond the table is not an error
+  posix_fadvise(g_pt_fd, (off_t)g_pt_lut[index].ent_ofst, (off_t)g_pt_lut[index].size, POSIX_FADV_WILLNEED);
+}
+API void* Pt_get(uint32_t index, size_t len, uint32_t scale, uint32_t level) {
+  (void)len; (void)scale; (void)level;  // as in the reference: what was encoded at compile time counts
+  if (g_pt_fd < 0) die("bad entry type");  // rt_data_file.c:63
+  if (index >= g_pt_lut.size()) die("index out of entry range");
+  StatScope ss(ST_ENCODE);
+  Context* c = ctx_nf();
+  if (g_pt_ring.empty()) g_pt_ring.resize(g_pt_slots);
+  PtSlot& sl = g_pt_ring[index % g_pt_slots];
+  const LutEntry& e = g_pt_lut[index];
+  guard([&] {
+    if (!sl.stage) {
+      ACE_CUDA(cudaMallocHost(&sl.stage, g_pt_max_entry));
+      ACE_CUDA(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
+    } else {
+      ACE_CUDA(cudaEventSynchronize(sl.copied));  // the previous occupant has left the staging buffer
+    }
+    size_t got = 0;
+    while (got < e.size) {
+      ssize_t r = pread(g_pt_fd, sl.stage + got, e.size - got, (off_t)(e.ent_ofst + got));
+      if (r <= 0) die("failed to read rt data entry");
+      got += (size_t)r;
+    }
+  });
+  // Cast_buffer_to_plain (plain_eval.c:132-160), plus what a device copy has to know
+  const PlainBufHdr* bh = reinterpret_cast<const PlainBufHdr*>(sl.stage);
+  if (memcmp(bh->magic, "ANTPLAIN", 8) != 0) die("Plaintext buffer magic mismatch");
+  if (bh->version != kRtVersionFull) die("Plaintext buffer version mismatch");
+  if ((uint64_t)bh->size + sizeof(PlainBufHdr) > e.size) die("Plaintext buffer too small");
+  PLAINTEXT pt;
+  memcpy(&pt, sl.stage + sizeof(PlainBufHdr), sizeof(PLAINTEXT));
+  if (pt._poly._data != nullptr) die("Plaintext poly data is not NULL");
+  const uint64_t data_sz = sizeof(int64_t) * (uint64_t)pt._poly._num_alloc_primes * pt._poly._ring_degree;
+  if (bh->size != data_sz + sizeof(PLAINTEXT)) die("Plaintext size mismatch");
+  if (pt._poly._ring_degree != c->N || pt._poly._num_primes_p != 0 || pt._poly._num_primes == 0 ||
+      pt._poly._num_primes > c->L || pt._poly._num_alloc_primes != pt._poly._num_primes)
+    die("Plaintext does not fit the context (degree / number of primes)");
+  // (the residues themselves are not range-checked: a value >= q gives a wrong product, never an
+  // out-of-bounds access -- every address is derived from the checked sizes above)
+  const size_t limbs = pt._poly._num_alloc_primes;
+  const int64_t* src = reinterpret_cast<const int64_t*>(sl.stage + sizeof(PlainBufHdr) + sizeof(PLAINTEXT));
+  if (sl.idx != (uint32_t)-1 && sl.pt._poly._data) free_poly_data(&sl.pt._poly);  // deferred: recorded readers go first
+  guard([&] {
+    ctx_nf();
+    u64* dev = g_queue->alloc(limbs, false);
+    ACE_CUDA(cudaMemcpyAsync(dev, src, data_sz, cudaMemcpyHostToDevice, c->stream));
+    ACE_CUDA(cudaEventRecord(sl.copied, c->stream));
+    pt._poly._data = reinterpret_cast<int64_t*>(dev);
+  });
+  sl.pt = pt;
+  sl.idx = index;
+  if (g_pt_prefetch > 0) Pt_prefetch(index + g_pt_prefetch);
+  return &sl.pt;
+}
+API void* Pt_get_validate(float* buf, uint32_t index, size_t len, uint32_t scale, uint32_t level) {
+  (void)buf; (void)index; (void)len; (void)scale; (void)level;
+  die("TODO: not implemented");  // pt_mgr.c:161-164, word for word
+  return nullptr;
+}
+// Pt_free (pt_mgr.c:166-176): the slot is given back; its limbs go once their readers are issued
+API void Pt_free(uint32_t index) {
+  if (g_pt_fd < 0 || g_pt_ring.empty()) return;
+  PtSlot& sl = g_pt_ring[index % g_pt_slots];
+  if (sl.idx != index) die("BLOCK_INFO state is not ready");
+  if (sl.pt._poly._data) free_poly_data(&sl.pt._poly);
+  sl.idx = (uint32_t)-1;
+  if (g_pt_prefetch > 0) Pt_prefetch(index + g_pt_prefetch);
+}
+
+API bool Pt_mgr_init(const char* fname) {  // pt_mgr.c:35-110
   const char* override_path = getenv("ACE_B200_DATA_FILE");
   if (override_path && override_path[0]) fname = override_path;
   int fd = open(fname, O_RDONLY);
@@ -1137,6 +1309,11 @@ API bool Pt_mgr_init(const char* fname) {  // pt_mgr.c:35-110 (message files onl
   }
   struct stat st;
   if (fstat(fd, &st) != 0 || st.st_size < (off_t)sizeof(DataFileHdr)) die("weight data file: cannot stat / too short");
+  {
+    DataFileHdr h0;
+    if (pread(fd, &h0, sizeof(h0), 0) != (ssize_t)sizeof(h0)) die("failed to read rt data file header");
+    if (memcmp(h0.magic, "!ANTFHE", 7) == 0 && h0.ent_type == DE_PLAINTEXT) return pt_file_open(fd, (uint64_t)st.st_size, h0);
+  }
   g_wfile.resize(st.st_size);
   size_t got = 0;
   while (got < (size_t)st.st_size) {
@@ -1167,6 +1344,7 @@ API bool Pt_mgr_init(const char* fname) {  // pt_mgr.c:35-110 (message files onl
   return true;
 }
 API void Pt_mgr_fini(void) {
+  pt_file_close();
   for (char* p : g_pt_slabs) cudaFree(p);  // the calling thread's plaintext cache
   g_pt_slabs.clear();
   g_pt_slab_left = 0;
@@ -1182,6 +1360,7 @@ API void Pt_mgr_fini(void) {
 // Pt_from_msg (pt_mgr.c:182-191): look the message up and encode it at run time.  The message
 // is read from the HBM copy of the weight file: no host->device copy, no synchronisation.
 API void Pt_from_msg(void* pt, uint32_t index, size_t len, uint32_t scale, uint32_t level) {
+  if (g_pt_fd >= 0) die("bad entry type");  // pt_mgr.c:184: a plaintext file has no messages
   if (!g_lut || index >= g_nent) die("Pt_from_msg: index out of range");
   const LutEntry& e = g_lut[index];
   const size_t esz = g_etype == DE_MSG_F32 ? sizeof(float) : sizeof(double);

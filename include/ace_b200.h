@@ -158,6 +158,13 @@ int ace_timer_stop_ms(ace_ctx* ctx, float* ms);
  *      export: the counterparts of ace_sk_import / ace_pk_import / ace_swk_import. */
 int ace_keygen_reference(ace_ctx* ctx, const uint32_t* seed16, uint64_t counter, uint32_t tri_base,
                          const int32_t* rot_idxs, size_t num_rot_idx);
+/*      _stream: the same, for a reference whose rand() is seeded ONCE (srandom(srandom_seed)) and
+ *      never re-seeded: the k-th Sample_triangle starts tri_pos[k] draws into that stream (other
+ *      callers of rand() -- Is_prime, number_theory.c:160-185 -- advance it in between).  This is
+ *      how the whole-model golden runs pinned the reference (oracle/ref_harness.c, mode 0). */
+int ace_keygen_reference_stream(ace_ctx* ctx, const uint32_t* seed16, uint64_t counter, uint32_t srandom_seed,
+                                const uint64_t* tri_pos, size_t n_pos, const int32_t* rot_idxs,
+                                size_t num_rot_idx);
 int ace_keygen_autos(ace_ctx* ctx, const uint32_t* auto_idx, size_t n);
 int ace_sk_export(ace_ctx* ctx, int64_t* host_sk_ntt_qp);
 int ace_pk_export(ace_ctx* ctx, int64_t* host_pk0, int64_t* host_pk1);

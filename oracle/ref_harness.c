@@ -65,19 +65,38 @@ __attribute__((visibility("hidden"))) time_t time(time_t* t) {
   Srand_after_tod = 0;
   return ts.tv_sec;
 }
+/* rand() is random() in glibc; counting the calls gives the position of the (mode 0) stream.
+ * Tri_pos[k] = how many values had been drawn since srandom(12345) when the k-th
+ * Sample_triangle of the run started: with these positions the B200 runtime's exact key
+ * generation (csrc/refrng.h) consumes the same stream without the reference having to run
+ * (tests/golden/make_tri_positions.py stores them next to a model's golden values). */
+#define TRI_LOG_MAX 8192
+static uint64_t Rand_count = 0, Tri_pos[TRI_LOG_MAX];
+static uint32_t Tri_logged = 0;
+__attribute__((visibility("hidden"))) int rand(void) {
+  Rand_count++;
+  return (int)random();
+}
 void srand(unsigned seed) { /* swallow srand(time) */
   (void)seed;
+  if (Srand_after_tod && Tri_logged < TRI_LOG_MAX) Tri_pos[Tri_logged++] = Rand_count;
   if (Pin_mode == 1 && Srand_after_tod) srandom(Tri_base + Tri_count++);
   Srand_after_tod = 0;
 }
 void ref_pin_mode(int mode, uint32_t tri_base) { Pin_mode = mode; Tri_base = tri_base; Tri_count = 0; }
 uint32_t ref_triangle_calls(void) { return Tri_count; }
+uint32_t ref_triangle_positions(uint64_t* out, uint32_t cap) {
+  for (uint32_t i = 0; i < Tri_logged && i < cap; i++) out[i] = Tri_pos[i];
+  return Tri_logged;
+}
 
 extern BLAKE2_PRNG* Prng;
 BLAKE2_PRNG*        Alloc_blake2_prng();
 
 static void Pin_random(void) {
   Tri_count = 0;
+  Tri_logged = 0;
+  Rand_count = 0;
   srandom(12345u);
   if (Prng == NULL) Prng = Alloc_blake2_prng();
   for (uint32_t i = 0; i < SEED_CNT; i++) {

@@ -37,6 +37,16 @@ def build_all(verbose=False):
             built.append(exe)
             if verbose:
                 print("built", exe)
+    # our own emitted-style unit for the pre-encoded weight path (no reference program uses it)
+    src = os.path.join(ROOT, "tests", "emitted", "pt_get_case.c")
+    exe = os.path.join(OUT, "pt_get_case")
+    r = subprocess.run(["gcc", "-O2", "-w", "-std=gnu11", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                        "-L", os.path.join(ROOT, "ace_compiler_b200"), "-lace_b200",
+                        "-Wl,-rpath,$ORIGIN/../../ace_compiler_b200", "-lm"], capture_output=True, text=True)
+    if r.returncode != 0:
+        print("FAILED pt_get_case", r.stderr[:2000])
+    else:
+        built.append(exe)
     built += build_models(verbose)
     return built
 
