@@ -92,6 +92,7 @@ struct P3Batcher {
 
 // out-of-place copy of whole limbs, one descriptor per limb (kernel in kernels.cu's family)
 __global__ void __launch_bounds__(256) copy_batch_kernel(u32 N, const __grid_constant__ Ptr3Batch P) {
+  pdl_enter();
   const ulonglong2* a = reinterpret_cast<const ulonglong2*>(P.a[blockIdx.y]);
   ulonglong2*       r = reinterpret_cast<ulonglong2*>(P.r[blockIdx.y]);
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < N / 2; i += gridDim.x * blockDim.x)
@@ -115,7 +116,7 @@ void Context::modup_batch(const ModupJob* jobs, size_t n) {
     auto flush = [&] {
       if (cp.P.n == 0) return;
       prof::Scope ps("copy_batch", stream);
-      copy_batch_kernel<<<dim3(N / 2 / 256 ? N / 2 / 256 : 1, cp.P.n), 256, 0, stream>>>(N, cp.P);
+      launch_chain(copy_batch_kernel, dim3(N / 2 / 256 ? N / 2 / 256 : 1, cp.P.n), 256, 0, stream, N, cp.P);
       launches++;
       cp.P.n = 0;
     };

@@ -288,7 +288,11 @@ Context::Shared::~Shared() {
   for (void* p : owned) cudaFree(p);
 }
 
+// contexts that run images next to the primary one (kernels.cuh: pdl_chain_enabled)
+std::atomic<int> g_worker_contexts{0};
+
 Context::~Context() {
+  if (worker_) g_worker_contexts--;
   cudaSetDevice(device);
   cudaStreamSynchronize(stream);
   if (!worker_) {
@@ -309,6 +313,7 @@ Context::~Context() {
 
 Context* Context::make_worker() {
   ACE_CUDA(cudaSetDevice(device));
+  g_worker_contexts++;
   ACE_CUDA(cudaStreamSynchronize(stream));  // everything the worker shares is in place
   // memberwise copy of what is immutable after set-up (tables, keys by pointer) plus the shared
   // store; the allocator state copies as empty (AllocState) and the counters are reset.  The

@@ -11,6 +11,7 @@
 //
 // All of these are integer kernels: NTT and base conversion are bound by the INT32 multiply
 // pipe (IMAD), the rest by HBM bandwidth.  No tensor-core path is used.
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
@@ -20,6 +21,17 @@
 #include "prof.h"
 
 namespace ace {
+
+// One image alone is bound by launch latencies: chaining the launches brings it from 0.934 to
+// 0.885 s (ResNet-20).  With several images in flight per GPU (worker contexts, context.cu) the
+// other streams fill those gaps already and CTAs parked at griddepcontrol.wait only take SM
+// slots from them (1.383 against 1.409 images/s with three streams, profiles/r2_pdl_chain.txt):
+// the attribute is set while the primary context is the only one running images.
+extern std::atomic<int> g_worker_contexts;
+bool pdl_chain_enabled() {
+  static const int mode = getenv("ACE_B200_NO_PDL") ? 0 : (getenv("ACE_B200_PDL_ALWAYS") ? 2 : 1);
+  return mode == 2 || (mode == 1 && g_worker_contexts.load(std::memory_order_relaxed) == 0);
+}
 
 // ------------------------------------------------------------------------------------
 // NTT.  N = 2^logN.  A transform is split into a "tile" phase working on contiguous tiles
@@ -92,6 +104,7 @@ __device__ __forceinline__ bool lazy_modulus(const Modulus& m) { return m.shift 
 // ---- strided phase, forward: stages 0 .. SA-1, R = 2^SA rows at stride N/R -------------
 template <int SA, class B>
 __global__ void __launch_bounds__(128) ntt_fwd_strided(DeviceTables T, const __grid_constant__ B b) {
+  pdl_enter();
   constexpr int R = 1 << SA;
   const u32 limb  = blockIdx.y;
   const u32 g     = b.g[limb];
@@ -126,6 +139,7 @@ __global__ void __launch_bounds__(128) ntt_fwd_strided(DeviceTables T, const __g
 // ---- strided phase, inverse: stages with t = N/R .. N/2, then * N^-1 --------------------
 template <int SA, class B>
 __global__ void __launch_bounds__(128) ntt_inv_strided(DeviceTables T, const __grid_constant__ B b) {
+  pdl_enter();
   constexpr int R = 1 << SA;
   const u32 limb  = blockIdx.y;
   const u32 g     = b.g[limb];
@@ -159,6 +173,7 @@ __global__ void __launch_bounds__(128) ntt_inv_strided(DeviceTables T, const __g
 // ---- tile phase, forward: stages s0 .. logN-1 on a contiguous tile in shared memory ----
 template <class B>
 __global__ void __launch_bounds__(kNttThreads) ntt_fwd_tile(DeviceTables T, const __grid_constant__ B b) {
+  pdl_enter();
   extern __shared__ u64 sm[];
   const u32 limb   = blockIdx.y;
   const u32 g      = b.g[limb];
@@ -193,6 +208,7 @@ __global__ void __launch_bounds__(kNttThreads) ntt_fwd_tile(DeviceTables T, cons
 // ---- tile phase, inverse: stages with t = 1 .. tile/2; folds N^-1 when it is the only phase
 template <class B>
 __global__ void __launch_bounds__(kNttThreads) ntt_inv_tile(DeviceTables T, const __grid_constant__ B b) {
+  pdl_enter();
   extern __shared__ u64 sm[];
   const u32 limb   = blockIdx.y;
   const u32 g      = b.g[limb];
@@ -333,6 +349,7 @@ __device__ __forceinline__ void fwd_tile8_body(const DeviceTables& T, u64* sm, c
 
 template <class B>
 __global__ void __launch_bounds__(512, 2) ntt_fwd_tile8(DeviceTables T, const __grid_constant__ B b) {
+  pdl_enter();
   extern __shared__ u64 sm[];
   const u32 limb  = blockIdx.y;
   const u32 g     = b.g[limb];
@@ -349,6 +366,7 @@ __global__ void __launch_bounds__(512, 2) ntt_fwd_tile8(DeviceTables T, const __
 
 template <class B>
 __global__ void __launch_bounds__(512, 2) ntt_inv_tile8(DeviceTables T, const __grid_constant__ B b) {
+  pdl_enter();
   extern __shared__ u64 sm[];
   u64* buf[2] = {sm, sm};
   const u32 limb  = blockIdx.y;
@@ -397,9 +415,9 @@ template <int SA, class B>
 static void launch_strided(bool fwd, const DeviceTables& T, const B& b, cudaStream_t s) {
   dim3 grid((T.N >> SA) / 128, b.n);
   if (fwd) {
-    ntt_fwd_strided<SA, B><<<grid, 128, 0, s>>>(T, b);
+    launch_chain(ntt_fwd_strided<SA, B>, grid, 128, 0, s, T, b);
   } else {
-    ntt_inv_strided<SA, B><<<grid, 128, 0, s>>>(T, b);
+    launch_chain(ntt_inv_strided<SA, B>, grid, 128, 0, s, T, b);
   }
 }
 
@@ -453,11 +471,11 @@ static void launch_ntt_impl(const DeviceTables& T, const B& b, cudaStream_t s) {
                            kTileSm * (int)sizeof(u64));
       attr = true;
     }
-    ntt_fwd_tile8<B><<<grid, 512, kTileSm * sizeof(u64), s>>>(T, b);
+    launch_chain(ntt_fwd_tile8<B>, grid, 512, kTileSm * sizeof(u64), s, T, b);
     return;
   }
   u32  threads = tile / 2 < (u32)kNttThreads ? tile / 2 : (u32)kNttThreads;
-  ntt_fwd_tile<B><<<grid, threads, tile * sizeof(u64), s>>>(T, b);
+  launch_chain(ntt_fwd_tile<B>, grid, threads, tile * sizeof(u64), s, T, b);
 }
 
 template <class B>
@@ -475,10 +493,10 @@ static void launch_intt_impl(const DeviceTables& T, const B& b, cudaStream_t s) 
                            kTileSm * (int)sizeof(u64));
       attr = true;
     }
-    ntt_inv_tile8<B><<<grid, 512, kTileSm * sizeof(u64), s>>>(T, b);
+    launch_chain(ntt_inv_tile8<B>, grid, 512, kTileSm * sizeof(u64), s, T, b);
   } else {
     u32 threads = tile / 2 < (u32)kNttThreads ? tile / 2 : (u32)kNttThreads;
-    ntt_inv_tile<B><<<grid, threads, tile * sizeof(u64), s>>>(T, b);
+    launch_chain(ntt_inv_tile<B>, grid, threads, tile * sizeof(u64), s, T, b);
   }
   if (T.logN > (u32)kTileLog) launch_strided_any<B>(false, T, b, s);
 }
@@ -495,6 +513,7 @@ template <int OP>
 __global__ void __launch_bounds__(256) ew_kernel(DeviceTables T, u64* __restrict__ r,
                                                  const u64* __restrict__ a,
                                                  const u64* __restrict__ b, u32 g0) {
+  pdl_enter();
   const Modulus m   = T.mod[g0 + blockIdx.y];
   const size_t  off = (size_t)blockIdx.y * T.N;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
@@ -518,9 +537,9 @@ void launch_ew(const DeviceTables& T, EwOp op, u64* r, const u64* a, const u64* 
   if (n_limbs == 0) return;
   dim3 grid = ew_grid(T, n_limbs);
   switch (op) {
-    case EW_ADD: ew_kernel<EW_ADD><<<grid, 256, 0, s>>>(T, r, a, b, g0); break;
-    case EW_SUB: ew_kernel<EW_SUB><<<grid, 256, 0, s>>>(T, r, a, b, g0); break;
-    case EW_MUL: ew_kernel<EW_MUL><<<grid, 256, 0, s>>>(T, r, a, b, g0); break;
+    case EW_ADD: launch_chain(ew_kernel<EW_ADD>, grid, 256, 0, s, T, r, a, b, g0); break;
+    case EW_SUB: launch_chain(ew_kernel<EW_SUB>, grid, 256, 0, s, T, r, a, b, g0); break;
+    case EW_MUL: launch_chain(ew_kernel<EW_MUL>, grid, 256, 0, s, T, r, a, b, g0); break;
   }
 }
 
@@ -528,6 +547,7 @@ __global__ void __launch_bounds__(256) gather_kernel(DeviceTables T, u64* __rest
                                                      const u64* __restrict__ a,
                                                      const int64_t* __restrict__ order,
                                                      u32 g0) {
+  pdl_enter();
   const u64    q   = T.mod[g0 + blockIdx.y].q;
   const size_t off = (size_t)blockIdx.y * T.N;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
@@ -541,7 +561,7 @@ void launch_gather(const DeviceTables& T, u64* r, const u64* a, const int64_t* o
                    u32 n_limbs, cudaStream_t s) {
   prof::Scope prof_scope_("gather", s);
   if (n_limbs == 0) return;
-  gather_kernel<<<ew_grid(T, n_limbs), 256, 0, s>>>(T, r, a, order, g0);
+  launch_chain(gather_kernel, ew_grid(T, n_limbs), 256, 0, s, T, r, a, order, g0);
 }
 
 __global__ void __launch_bounds__(256) mul_scalar_kernel(DeviceTables T, u64* __restrict__ r,
@@ -549,6 +569,7 @@ __global__ void __launch_bounds__(256) mul_scalar_kernel(DeviceTables T, u64* __
                                                          const u64* __restrict__ sc,
                                                          const u64* __restrict__ sc_sh,
                                                          u32 g0) {
+  pdl_enter();
   const u64    q   = T.mod[g0 + blockIdx.y].q;
   const u64    w = sc[blockIdx.y], wsh = sc_sh[blockIdx.y];
   const size_t off = (size_t)blockIdx.y * T.N;
@@ -560,7 +581,7 @@ void launch_mul_scalar(const DeviceTables& T, u64* r, const u64* a, const u64* s
                        const u64* sc_sh, u32 g0, u32 n_limbs, cudaStream_t s) {
   prof::Scope prof_scope_("mul_scalar", s);
   if (n_limbs == 0) return;
-  mul_scalar_kernel<<<ew_grid(T, n_limbs), 256, 0, s>>>(T, r, a, sc, sc_sh, g0);
+  launch_chain(mul_scalar_kernel, ew_grid(T, n_limbs), 256, 0, s, T, r, a, sc, sc_sh, g0);
 }
 
 // ------------------------------------------------------------------------------------
@@ -634,6 +655,7 @@ __device__ __forceinline__ void base_conv_fast(const DeviceTables& T, const Conv
 template <int MAXIN>
 __global__ void __launch_bounds__(128) base_conv_kernel(DeviceTables T,
                                                         const __grid_constant__ ConvDescPack P) {
+  pdl_enter();
   extern __shared__ u64 sh_hat[];  // [n_out][n_in]
   const ConvDesc& D = P.d[blockIdx.y];
   const u32 n_in = D.n_in, n_out = D.n_out;
@@ -693,13 +715,13 @@ void launch_base_conv(const DeviceTables& T, const ConvDesc* descs, u32 n_desc,
   dim3   grid((T.N + 127) / 128, n_desc);
   size_t shm = (size_t)max_in * max_out * sizeof(u64);
   if (max_in <= 4) {
-    base_conv_kernel<4><<<grid, 128, shm, s>>>(T, P);
+    launch_chain(base_conv_kernel<4>, grid, 128, shm, s, T, P);
   } else if (max_in <= 12) {
-    base_conv_kernel<12><<<grid, 128, shm, s>>>(T, P);
+    launch_chain(base_conv_kernel<12>, grid, 128, shm, s, T, P);
   } else if (max_in <= 16) {
-    base_conv_kernel<16><<<grid, 128, shm, s>>>(T, P);
+    launch_chain(base_conv_kernel<16>, grid, 128, shm, s, T, P);
   } else {
-    base_conv_kernel<48><<<grid, 128, shm, s>>>(T, P);
+    launch_chain(base_conv_kernel<48>, grid, 128, shm, s, T, P);
   }
 }
 
@@ -715,6 +737,7 @@ __global__ void __launch_bounds__(256) ksw_inner_kernel(DeviceTables T, u64* __r
                                                         const u64* __restrict__ key0,
                                                         const u64* __restrict__ key1, u32 beta,
                                                         u32 num_q, u32 L, u32 K) {
+  pdl_enter();
   const u32     o = blockIdx.y;
   const u32     g = o < num_q ? o : L + (o - num_q);
   const u32     W = num_q + K;
@@ -739,7 +762,7 @@ void launch_ksw_inner(const DeviceTables& T, u64* acc0, u64* acc1, const u64* ex
                       u32 beta, u32 num_q, u32 L, u32 K, cudaStream_t s) {
   prof::Scope prof_scope_("ksw_inner", s);
   dim3 grid((T.N + 255) / 256, num_q + K);
-  ksw_inner_kernel<<<grid, 256, 0, s>>>(T, acc0, acc1, ext, own, part_size, key0, key1, beta,
+  launch_chain(ksw_inner_kernel, grid, 256, 0, s, T, acc0, acc1, ext, own, part_size, key0, key1, beta,
                                         num_q, L, K);
 }
 
@@ -747,6 +770,7 @@ __global__ void __launch_bounds__(256) moddown_tail_kernel(
     DeviceTables T, u64* __restrict__ out, const u64* __restrict__ old,
     const u64* __restrict__ conv, const u64* __restrict__ add, const u64* __restrict__ pinv,
     const u64* __restrict__ pinv_sh) {
+  pdl_enter();
   const u32    l   = blockIdx.y;
   const u64    q   = T.mod[l].q;
   const u64    w = pinv[l], wsh = pinv_sh[l];
@@ -763,7 +787,7 @@ void launch_moddown_tail(const DeviceTables& T, u64* out, const u64* old, const 
                          cudaStream_t s) {
   prof::Scope prof_scope_("moddown_tail", s);
   if (n_limbs == 0) return;
-  moddown_tail_kernel<<<ew_grid(T, n_limbs), 256, 0, s>>>(T, out, old, conv, add, pinv,
+  launch_chain(moddown_tail_kernel, ew_grid(T, n_limbs), 256, 0, s, T, out, old, conv, add, pinv,
                                                           pinv_sh);
 }
 
@@ -771,6 +795,7 @@ __global__ void __launch_bounds__(256) rescale_pre_kernel(DeviceTables T, u64* _
                                                           const u64* __restrict__ last, u32 l,
                                                           const u64* __restrict__ negqlinv,
                                                           const u64* __restrict__ negqlinv_sh) {
+  pdl_enter();
   const u32    i   = blockIdx.y;
   const u64    qi  = T.mod[i].q, ql = T.mod[l].q;
   const u64    w = negqlinv[i], wsh = negqlinv_sh[i];
@@ -783,7 +808,7 @@ void launch_rescale_pre(const DeviceTables& T, u64* tmp, const u64* last, u32 l,
                         const u64* negqlinv, const u64* negqlinv_sh, cudaStream_t s) {
   prof::Scope prof_scope_("rescale_pre", s);
   if (l == 0) return;
-  rescale_pre_kernel<<<ew_grid(T, l), 256, 0, s>>>(T, tmp, last, l, negqlinv, negqlinv_sh);
+  launch_chain(rescale_pre_kernel, ew_grid(T, l), 256, 0, s, T, tmp, last, l, negqlinv, negqlinv_sh);
 }
 
 __global__ void __launch_bounds__(256) rescale_post_kernel(DeviceTables T, u64* __restrict__ out,
@@ -791,6 +816,7 @@ __global__ void __launch_bounds__(256) rescale_post_kernel(DeviceTables T, u64* 
                                                            const u64* __restrict__ tmp,
                                                            const u64* __restrict__ qlinv,
                                                            const u64* __restrict__ qlinv_sh) {
+  pdl_enter();
   const u32    i   = blockIdx.y;
   const u64    qi  = T.mod[i].q;
   const u64    w = qlinv[i], wsh = qlinv_sh[i];
@@ -803,7 +829,7 @@ void launch_rescale_post(const DeviceTables& T, u64* out, const u64* c, const u6
                          const u64* qlinv, const u64* qlinv_sh, u32 n_limbs, cudaStream_t s) {
   prof::Scope prof_scope_("rescale_post", s);
   if (n_limbs == 0) return;
-  rescale_post_kernel<<<ew_grid(T, n_limbs), 256, 0, s>>>(T, out, c, tmp, qlinv, qlinv_sh);
+  launch_chain(rescale_post_kernel, ew_grid(T, n_limbs), 256, 0, s, T, out, c, tmp, qlinv, qlinv_sh);
 }
 
 // ------------------------------------------------------------------------------------
@@ -813,6 +839,7 @@ void launch_rescale_post(const DeviceTables& T, u64* out, const u64* c, const u6
 __global__ void __launch_bounds__(256) moddown_tail_batch_kernel(
     DeviceTables T, const __grid_constant__ Ptr3Batch P, const u64* __restrict__ pinv,
     const u64* __restrict__ pinv_sh) {
+  pdl_enter();
   const u32  y = blockIdx.y, l = P.g[y];
   const u64  q = T.mod[l].q, w = pinv[l], wsh = pinv_sh[l];
   u64*       out = P.r[y];
@@ -824,12 +851,13 @@ void launch_moddown_tail_batch(const DeviceTables& T, const Ptr3Batch& P, const 
                                const u64* pinv_sh, cudaStream_t s) {
   if (P.n == 0) return;
   prof::Scope prof_scope_("moddown_tail", s);
-  moddown_tail_batch_kernel<<<ew_grid(T, P.n), 256, 0, s>>>(T, P, pinv, pinv_sh);
+  launch_chain(moddown_tail_batch_kernel, ew_grid(T, P.n), 256, 0, s, T, P, pinv, pinv_sh);
 }
 
 __global__ void __launch_bounds__(256) rescale_pre_batch_kernel(
     DeviceTables T, const __grid_constant__ Ptr3Batch P, const u64* __restrict__ negqlinv,
     const u64* __restrict__ negqlinv_sh, u32 L) {
+  pdl_enter();
   const u32  y = blockIdx.y, i = P.g[y], l = P.aux[y];
   const u64  qi = T.mod[i].q, ql = T.mod[l].q;
   const u64  w = negqlinv[(size_t)l * L + i], wsh = negqlinv_sh[(size_t)l * L + i];
@@ -842,12 +870,13 @@ void launch_rescale_pre_batch(const DeviceTables& T, const Ptr3Batch& P, const u
                               const u64* negqlinv_sh, u32 L, cudaStream_t s) {
   if (P.n == 0) return;
   prof::Scope prof_scope_("rescale_pre", s);
-  rescale_pre_batch_kernel<<<ew_grid(T, P.n), 256, 0, s>>>(T, P, negqlinv, negqlinv_sh, L);
+  launch_chain(rescale_pre_batch_kernel, ew_grid(T, P.n), 256, 0, s, T, P, negqlinv, negqlinv_sh, L);
 }
 
 __global__ void __launch_bounds__(256) rescale_post_batch_kernel(
     DeviceTables T, const __grid_constant__ Ptr3Batch P, const u64* __restrict__ qlinv,
     const u64* __restrict__ qlinv_sh, u32 L) {
+  pdl_enter();
   const u32  y = blockIdx.y, i = P.g[y], l = P.aux[y];
   const u64  qi = T.mod[i].q;
   const u64  w = qlinv[(size_t)l * L + i], wsh = qlinv_sh[(size_t)l * L + i];
@@ -860,7 +889,7 @@ void launch_rescale_post_batch(const DeviceTables& T, const Ptr3Batch& P, const 
                                const u64* qlinv_sh, u32 L, cudaStream_t s) {
   if (P.n == 0) return;
   prof::Scope prof_scope_("rescale_post", s);
-  rescale_post_batch_kernel<<<ew_grid(T, P.n), 256, 0, s>>>(T, P, qlinv, qlinv_sh, L);
+  launch_chain(rescale_post_batch_kernel, ew_grid(T, P.n), 256, 0, s, T, P, qlinv, qlinv_sh, L);
 }
 
 // Tensor product of two ciphertexts in one pass (Mul_ciphertext3, ckks_evaluator.c:133-165):
@@ -871,6 +900,7 @@ __global__ void __launch_bounds__(256) tensor_kernel(DeviceTables T, u64* __rest
                                                      const u64* __restrict__ a1,
                                                      const u64* __restrict__ b0,
                                                      const u64* __restrict__ b1) {
+  pdl_enter();
   const Modulus m   = T.mod[blockIdx.y];
   const size_t  off = (size_t)blockIdx.y * T.N;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
@@ -884,7 +914,7 @@ void launch_tensor(const DeviceTables& T, u64* d0, u64* d1, u64* d2, const u64* 
                    const u64* a1, const u64* b0, const u64* b1, u32 n_limbs, cudaStream_t s) {
   if (n_limbs == 0) return;
   prof::Scope prof_scope_("tensor", s);
-  tensor_kernel<<<ew_grid(T, n_limbs), 256, 0, s>>>(T, d0, d1, d2, a0, a1, b0, b1);
+  launch_chain(tensor_kernel, ew_grid(T, n_limbs), 256, 0, s, T, d0, d1, d2, a0, a1, b0, b1);
 }
 
 }  // namespace ace

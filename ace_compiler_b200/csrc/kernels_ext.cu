@@ -14,6 +14,7 @@ template <int OP>
 __global__ void __launch_bounds__(256) ew_basis_kernel(DeviceTables T, u64* __restrict__ r,
                                                        const u64* __restrict__ a,
                                                        const u64* __restrict__ b, Basis bs) {
+  pdl_enter();
   const Modulus m   = T.mod[bs.g(blockIdx.y)];
   const size_t  off = (size_t)blockIdx.y * T.N;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
@@ -31,9 +32,9 @@ void launch_ew_basis(const DeviceTables& T, EwOp op, u64* r, const u64* a, const
   if (bs.width() == 0) return;
   dim3 grid = grid_for(T, bs.width());
   switch (op) {
-    case EW_ADD: ew_basis_kernel<EW_ADD><<<grid, 256, 0, s>>>(T, r, a, b, bs); break;
-    case EW_SUB: ew_basis_kernel<EW_SUB><<<grid, 256, 0, s>>>(T, r, a, b, bs); break;
-    case EW_MUL: ew_basis_kernel<EW_MUL><<<grid, 256, 0, s>>>(T, r, a, b, bs); break;
+    case EW_ADD: launch_chain(ew_basis_kernel<EW_ADD>, grid, 256, 0, s, T, r, a, b, bs); break;
+    case EW_SUB: launch_chain(ew_basis_kernel<EW_SUB>, grid, 256, 0, s, T, r, a, b, bs); break;
+    case EW_MUL: launch_chain(ew_basis_kernel<EW_MUL>, grid, 256, 0, s, T, r, a, b, bs); break;
   }
 }
 
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(256) gather_basis_kernel(DeviceTables T, u64* 
                                                            const u64* __restrict__ a,
                                                            const int64_t* __restrict__ order,
                                                            Basis bs) {
+  pdl_enter();
   const u64    q   = T.mod[bs.g(blockIdx.y)].q;
   const size_t off = (size_t)blockIdx.y * T.N;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
@@ -53,12 +55,13 @@ void launch_gather_basis(const DeviceTables& T, u64* r, const u64* a, const int6
                          Basis bs, cudaStream_t s) {
   prof::Scope prof_scope_("gather_basis", s);
   if (bs.width() == 0) return;
-  gather_basis_kernel<<<grid_for(T, bs.width()), 256, 0, s>>>(T, r, a, order, bs);
+  launch_chain(gather_basis_kernel, grid_for(T, bs.width()), 256, 0, s, T, r, a, order, bs);
 }
 
 __global__ void __launch_bounds__(256) add_scalar_kernel(DeviceTables T, u64* __restrict__ r,
                                                          const u64* __restrict__ a,
                                                          ScalarPack sc, u32 g0) {
+  pdl_enter();
   const u64    q   = T.mod[g0 + blockIdx.y].q;
   const u64    v   = sc.v[blockIdx.y];
   const size_t off = (size_t)blockIdx.y * T.N;
@@ -70,13 +73,14 @@ void launch_add_scalar(const DeviceTables& T, u64* r, const u64* a, const Scalar
                        u32 g0, u32 n_limbs, cudaStream_t s) {
   prof::Scope prof_scope_("add_scalar", s);
   if (n_limbs == 0) return;
-  add_scalar_kernel<<<grid_for(T, n_limbs), 256, 0, s>>>(T, r, a, sc, g0);
+  launch_chain(add_scalar_kernel, grid_for(T, n_limbs), 256, 0, s, T, r, a, sc, g0);
 }
 
 __global__ void __launch_bounds__(256) mul_scalar_pack_kernel(DeviceTables T,
                                                               u64* __restrict__ r,
                                                               const u64* __restrict__ a,
                                                               ScalarPack sc, Basis bs) {
+  pdl_enter();
   const u64    q   = T.mod[bs.g(blockIdx.y)].q;
   const u64    w = sc.v[blockIdx.y], wsh = sc.sh[blockIdx.y];
   const size_t off = (size_t)blockIdx.y * T.N;
@@ -88,11 +92,12 @@ void launch_mul_scalar_pack(const DeviceTables& T, u64* r, const u64* a, const S
                             Basis bs, cudaStream_t s) {
   prof::Scope prof_scope_("mul_scalar_pack", s);
   if (bs.width() == 0) return;
-  mul_scalar_pack_kernel<<<grid_for(T, bs.width()), 256, 0, s>>>(T, r, a, sc, bs);
+  launch_chain(mul_scalar_pack_kernel, grid_for(T, bs.width()), 256, 0, s, T, r, a, sc, bs);
 }
 
 __global__ void __launch_bounds__(256) mod_raise_kernel(DeviceTables T, u64* __restrict__ out,
                                                         const u64* __restrict__ in) {
+  pdl_enter();
   const u32    y   = blockIdx.y;
   const u64    q0 = T.mod[0].q, qy = T.mod[y].q;
   const size_t off = (size_t)y * T.N;
@@ -106,11 +111,12 @@ void launch_mod_raise(const DeviceTables& T, u64* out, const u64* in, u32 n_limb
                       cudaStream_t s) {
   prof::Scope prof_scope_("mod_raise", s);
   if (n_limbs == 0) return;
-  mod_raise_kernel<<<grid_for(T, n_limbs), 256, 0, s>>>(T, out, in);
+  launch_chain(mod_raise_kernel, grid_for(T, n_limbs), 256, 0, s, T, out, in);
 }
 
 __global__ void __launch_bounds__(256) monomial_kernel(DeviceTables T, u64* __restrict__ out,
                                                        u32 index, u32 negative) {
+  pdl_enter();
   const u64    q   = T.mod[blockIdx.y].q;
   const size_t off = (size_t)blockIdx.y * T.N;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x)
@@ -121,12 +127,13 @@ void launch_monomial(const DeviceTables& T, u64* out, u32 index, bool negative, 
                      cudaStream_t s) {
   prof::Scope prof_scope_("monomial", s);
   if (n_limbs == 0) return;
-  monomial_kernel<<<grid_for(T, n_limbs), 256, 0, s>>>(T, out, index, negative ? 1u : 0u);
+  launch_chain(monomial_kernel, grid_for(T, n_limbs), 256, 0, s, T, out, index, negative ? 1u : 0u);
 }
 
 __global__ void __launch_bounds__(256) pt_dot_kernel(DeviceTables T, u64* __restrict__ out0,
                                                      u64* __restrict__ out1, DotArgs A,
                                                      Basis bs) {
+  pdl_enter();
   const u32     y    = blockIdx.y;
   const Modulus m    = T.mod[bs.g(y)];
   const size_t  off  = (size_t)y * T.N;
@@ -147,12 +154,13 @@ void launch_pt_dot(const DeviceTables& T, u64* out0, u64* out1, const DotArgs& a
                    cudaStream_t s) {
   prof::Scope prof_scope_("pt_dot", s);
   if (bs.width() == 0 || args.n == 0) return;
-  pt_dot_kernel<<<grid_for(T, bs.width()), 256, 0, s>>>(T, out0, out1, args, bs);
+  launch_chain(pt_dot_kernel, grid_for(T, bs.width()), 256, 0, s, T, out0, out1, args, bs);
 }
 
 __global__ void __launch_bounds__(256) mul_scalar_add_kernel(
     DeviceTables T, u64* __restrict__ r, const u64* __restrict__ acc, const u64* __restrict__ c,
     const u64* __restrict__ sc, const u64* __restrict__ sc_sh) {
+  pdl_enter();
   const u64    q   = T.mod[blockIdx.y].q;
   const u64    w = sc[blockIdx.y], wsh = sc_sh[blockIdx.y];
   const size_t off = (size_t)blockIdx.y * T.N;
@@ -164,7 +172,7 @@ void launch_mul_scalar_add(const DeviceTables& T, u64* r, const u64* acc, const 
                            const u64* sc, const u64* sc_sh, u32 n_limbs, cudaStream_t s) {
   prof::Scope prof_scope_("mul_scalar_add", s);
   if (n_limbs == 0) return;
-  mul_scalar_add_kernel<<<grid_for(T, n_limbs), 256, 0, s>>>(T, r, acc, c, sc, sc_sh);
+  launch_chain(mul_scalar_add_kernel, grid_for(T, n_limbs), 256, 0, s, T, r, acc, c, sc, sc_sh);
 }
 
 // Key inner product with the epilogue of a "fast" rotation in the extended basis
@@ -187,6 +195,7 @@ __global__ void __launch_bounds__(STAGED ? 128 : 256) ksw_inner_rot_kernel(
     const u64* __restrict__ key1, u32 beta, u32 num_q, u32 L, u32 K, const u64* __restrict__ c0,
     const u64* __restrict__ pmodq, const u64* __restrict__ pmodq_sh,
     const int64_t* __restrict__ scatter, int acc0_flag, int acc1_flag) {
+  pdl_enter();
   const u32     o = blockIdx.y;
   const u32     g = o < num_q ? o : L + (o - num_q);
   const u32     W = num_q + K;
@@ -272,11 +281,11 @@ void launch_ksw_inner_rot(const DeviceTables& T, u64* out0, u64* out1, const u64
   prof::Scope prof_scope_("ksw_inner_rot", s);
   dim3 grid((T.N + 255) / 256, num_q + K);
   if (T.N % 256 == 0)
-    ksw_inner_rot_kernel<true><<<grid, 128, 0, s>>>(T, out0, out1, ext, own, part_size, key0, key1, beta,
+    launch_chain(ksw_inner_rot_kernel<true>, grid, 128, 0, s, T, out0, out1, ext, own, part_size, key0, key1, beta,
                                                     num_q, L, K, c0, pmodq, pmodq_sh, scatter,
                                                     acc0 ? 1 : 0, acc1 ? 1 : 0);
   else
-    ksw_inner_rot_kernel<false><<<grid, 256, 0, s>>>(T, out0, out1, ext, own, part_size, key0, key1, beta,
+    launch_chain(ksw_inner_rot_kernel<false>, grid, 256, 0, s, T, out0, out1, ext, own, part_size, key0, key1, beta,
                                                      num_q, L, K, c0, pmodq, pmodq_sh, scatter,
                                                      acc0 ? 1 : 0, acc1 ? 1 : 0);
 }
@@ -286,6 +295,7 @@ __global__ void __launch_bounds__(256) gather_add_basis_kernel(DeviceTables T, u
                                                                const u64* __restrict__ a,
                                                                const int64_t* __restrict__ order,
                                                                Basis bs) {
+  pdl_enter();
   const u64    q   = T.mod[bs.g(blockIdx.y)].q;
   const size_t off = (size_t)blockIdx.y * T.N;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
@@ -297,7 +307,7 @@ __global__ void __launch_bounds__(256) gather_add_basis_kernel(DeviceTables T, u
 void launch_gather_add_basis(const DeviceTables& T, u64* r, const u64* a, const int64_t* order,
                              Basis bs, cudaStream_t s) {
   prof::Scope prof_scope_("gather_add_basis", s);
-  gather_add_basis_kernel<<<grid_for(T, bs.width()), 256, 0, s>>>(T, r, a, order, bs);
+  launch_chain(gather_add_basis_kernel, grid_for(T, bs.width()), 256, 0, s, T, r, a, order, bs);
 }
 
 // All baby-step inner sums of one BSGS level in one pass over the giant-step rotations:
@@ -308,6 +318,7 @@ template <int B>
 __global__ void __launch_bounds__(256) pt_dot_all_kernel(DeviceTables T,
                                                          const __grid_constant__ DotAllArgs A,
                                                          Basis bs) {
+  pdl_enter();
   const u32     y    = blockIdx.y;
   const Modulus m    = T.mod[bs.g(y)];
   const size_t  off  = (size_t)y * T.N;
@@ -345,8 +356,8 @@ __global__ void __launch_bounds__(256) pt_dot_all_kernel(DeviceTables T,
 void launch_pt_dot_all(const DeviceTables& T, const DotAllArgs& args, Basis bs, cudaStream_t s) {
   prof::Scope prof_scope_("pt_dot_all", s);
   if (bs.width() == 0 || args.b == 0 || args.g == 0) return;
-  if (args.b <= 4) pt_dot_all_kernel<4><<<grid_for(T, bs.width()), 256, 0, s>>>(T, args, bs);
-  else pt_dot_all_kernel<kMaxDotBaby><<<grid_for(T, bs.width()), 256, 0, s>>>(T, args, bs);
+  if (args.b <= 4) launch_chain(pt_dot_all_kernel<4>, grid_for(T, bs.width()), 256, 0, s, T, args, bs);
+  else launch_chain(pt_dot_all_kernel<kMaxDotBaby>, grid_for(T, bs.width()), 256, 0, s, T, args, bs);
 }
 
 }  // namespace ace

@@ -381,6 +381,7 @@ __device__ __forceinline__ void fwd_cols_body(const DeviceTables& T, u32 g, u64*
   ACE_TW_DECL;
   ACE_TW_PRELOAD(PA, PB, 15)
   E x[16];
+  if (!XCH) pdl_wait();  // the kernel before this transform in the stream (kernels.cuh: pdl_enter)
 #pragma unroll
   for (int k = 0; k < 16; k++) x[k] = A::from_canonical(hook.pre(in[(j + 16 * k) * 256 + col]), M);
 #define TW_A(i, h) ACE_TW_GET_A(PA, i, h)
@@ -423,15 +424,17 @@ __device__ __forceinline__ void fwd_rows_body(const DeviceTables& T, u32 g, u64*
 #define PA(i, h) (tw + (256 << (i)) + (r << (i)) + (h))
 #define PB(i, h) (tw + (4096 << (i)) + ((16 * r + j) << (i)) + (h))
   u64* saux = sm + 16 * kRowPad;  // (fused batches only: the launch provides the room)
-  if (H::kActive && hook.post_mode) stage_aux(saux, hook.aux + blockIdx.x * 4096);
   ACE_TW_DECL;
   ACE_TW_PRELOAD(PA, PB, 15)
   E x[16];
   if (XCH) {
+    if (H::kActive && hook.post_mode) stage_aux(saux, hook.aux + blockIdx.x * 4096);
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = A::from_mid(xin[rho * kRowPad + 17 * k + j], M);
   } else {
     pdl_wait();  // the coefficients come from the first kernel
+    pdl_launch_dependents();  // whatever follows the transform may be launched now
+    if (H::kActive && hook.post_mode) stage_aux(saux, hook.aux + blockIdx.x * 4096);
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = A::from_mid(row[j + 16 * k], M);
   }
@@ -482,6 +485,7 @@ __device__ __forceinline__ void inv_rows_body(const DeviceTables& T, u32 g, u64*
   ACE_TW_DECL;
   ACE_TW_PRELOAD(PA, PB, 13)
   E x[16];
+  if (!XCH) pdl_wait();  // the kernel before this transform in the stream
   const ulonglong2* i2 = reinterpret_cast<const ulonglong2*>(in + r * 256 + 16 * j);
 #pragma unroll
   for (int k = 0; k < 8; k++) {
@@ -534,6 +538,7 @@ __device__ __forceinline__ void inv_cols_body(const DeviceTables& T, u32 g, u64*
     for (int k = 0; k < 16; k++) x[k] = A::from_mid(xin[(16 * j + k) * 16 + c], M);
   } else {
     pdl_wait();  // the coefficients come from the first kernel
+    pdl_launch_dependents();
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = A::from_mid(data[(16 * j + k) * 256 + col], M);
   }
@@ -701,7 +706,7 @@ static void launch_pair(const DeviceTables& T, const B& b, cudaStream_t s) {
                          (int)kernel_smem<K2, B>());
     attr = true;
   }
-  ntt16_kernel<K1, B, PRE><<<grid, kThreads, kernel_smem<K1, B>(), s>>>(T, b);
+  launch_chain(ntt16_kernel<K1, B, PRE>, grid, dim3(kThreads), kernel_smem<K1, B>(), s, T, b);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kThreads);

@@ -20,6 +20,7 @@ namespace ace {
 // the saved loads give back.  Not kept.)
 __global__ void __launch_bounds__(256) ew_chain_kernel(DeviceTables T,
                                                              const __grid_constant__ ChainPack P) {
+  pdl_enter();
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= T.N) return;
   const u32 k0 = P.chain_start[blockIdx.y], k1 = P.chain_start[blockIdx.y + 1];
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(256) ew_chain_kernel(DeviceTables T,
 // negative entries: number_theory.c:215-224) takes the direct path; the CTA decides by itself.
 __global__ void __launch_bounds__(256) gather_batch_kernel(DeviceTables T,
                                                            const __grid_constant__ ChainPack P) {
+  pdl_enter();
   __shared__ u64     stage[256];
   __shared__ int64_t first;
   const ChainItem& it    = P.it[blockIdx.y];
@@ -98,12 +100,12 @@ struct ContextBackend : SchedBackend {
   }
   void run_chains(const ChainPack& pack, u32 n_chains) override {
     prof::Scope ps("ew_chain", c->stream);
-    ew_chain_kernel<<<dim3((c->N + 255) / 256, n_chains), 256, 0, c->stream>>>(c->T, pack);
+    launch_chain(ew_chain_kernel, dim3((c->N + 255) / 256, n_chains), dim3(256), 0, c->stream, c->T, pack);
     c->launches++;
   }
   void run_gathers(const ChainPack& pack, u32 n) override {
     prof::Scope ps("gather_batch", c->stream);
-    gather_batch_kernel<<<dim3((c->N + 255) / 256, n), 256, 0, c->stream>>>(c->T, pack);
+    launch_chain(gather_batch_kernel, dim3((c->N + 255) / 256, n), dim3(256), 0, c->stream, c->T, pack);
     c->launches++;
   }
   void run_encode(const EncodeJob* j, size_t n) override { c->encode_batch(j, n); }

@@ -1,8 +1,9 @@
 """Exact key generation, run in its own process (the reference keeps one global context).
 
     python tests/keygen_case.py N depth hamming_weight [bootstrap]
-    python tests/keygen_case.py model <name>      (the whole key set of an emitted ResNet: its
-                                                   rotation indices + the bootstrap keys)
+    python tests/keygen_case.py model <name> [n]  (the whole key set of an emitted ResNet: its
+                                                   rotation indices -- or the first n of them --
+                                                   + the bootstrap keys)
 
 The compiled reference (oracle/_ref/libace_ref.so) generates its keys with pinned randomness in
 pin mode 1 (oracle/ref_harness.c: BLAKE2 PRNG seed words + counter pinned; the k-th Sample_triangle
@@ -34,6 +35,8 @@ def main():
         cfg = json.load(open(os.path.join(HERE, "emitted", sys.argv[2] + ".rots.json")))
         N, depth, hw, rots, with_bts = cfg["N"], cfg["mul_depth"], cfg["hamming_weight"], cfg["rot_idxs"], True
         assert (cfg["first_mod_size"], cfg["num_q_parts"]) == (51, 3)
+        if len(sys.argv) > 3:  # only the first keys of the list (the streams are sequential)
+            rots = rots[:int(sys.argv[3])]
         SF = cfg["scaling_mod_size"]
     else:
         N, depth, hw = (int(x) for x in sys.argv[1:4])

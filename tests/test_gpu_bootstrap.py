@@ -23,8 +23,13 @@ CASES = [
     # ResNet-110's scale (q0 = 2^51, Delta = 2^48: resnet110_cifar10_train.onnx.inc Get_context_params)
     (1024, 17, 192, 512, 2, 3, 1, 51, 48),
     (2048, 18, 192, 256, 2, 3, 1, 51, 48),
-    (65536, 33, 192, 32768, 3, 17, 1, 51, 48),  # ResNet-110's parameter set and a call of its
 ]
+# ResNet-110's parameter set and one of its calls on their own: ~100 s, most of it the reference's
+# bootstrap on the host.  Runs with ACE_MODEL_PARITY=1 (last run: profiles/r2_pytest_gpu_full_v2.log);
+# by default this setting is covered by test_gpu_model.py::test_resnet110_bit_exact, whose output
+# ciphertext went through 109 such bootstraps and must equal the reference's bit for bit.
+if os.environ.get("ACE_MODEL_PARITY") == "1":
+    CASES.append((65536, 33, 192, 32768, 3, 17, 1, 51, 48))
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "N%d_d%d_hw%d_s%d_even%d" % (c[0], c[1], c[2], c[3], c[6]) + ("_sf%d" % c[8] if len(c) > 8 else ""))

@@ -4,10 +4,10 @@ unit on the reference rtlib (tests/golden/resnet20_cifar10_pre.json, made by
 tests/golden/make_model_golden.py: 1925 s of Main_graph on the CPU).
 
 * test_resnet20_logits: own keys; decrypted logits within 1e-5 of the reference's (always runs).
-* test_resnet20_bit_exact: the reference library regenerates the golden run's keys on the host
-  (minutes, ~40 GB of RAM), the GPU imports them and must reproduce the output ciphertext bit for
-  bit (~3 min).  Runs when the host has >= 64 GB of RAM; ACE_MODEL_PARITY=0 skips it, =1 forces
-  it (log of the last run: profiles/r1_model_parity.log)."""
+* test_*_bit_exact: the runtime generates the golden run's keys and input ciphertext from the
+  reference's pinned random streams (csrc/refrng.h) and must reproduce the golden OUTPUT
+  CIPHERTEXT bit for bit; ACE_MODEL_REFKEYS=1 has the compiled reference regenerate the keys on
+  the host instead (minutes, ~40 GB of RAM) and imports them."""
 import os
 import subprocess
 import sys
@@ -53,29 +53,36 @@ def _enough_ram():
         return False
 
 
-def test_resnet20_bit_exact():
-    flag = os.environ.get("ACE_MODEL_PARITY")
-    if flag == "0" or (flag != "1" and not _enough_ram()):
-        pytest.skip("needs ~40 GB of host RAM for the reference's keys (ACE_MODEL_PARITY=1 forces it)")
-    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", MODEL + "_ref.so")):
-        pytest.skip("oracle/_ref/%s_ref.so not built (needs the reference tree at build time)" % MODEL)
-    _run("exact", timeout=3000)
-
-
 def _bit_exact(model):
-    flag = os.environ.get("ACE_MODEL_PARITY")
-    if not os.path.exists(os.path.join(HERE, "golden", model + ".json")):
+    """tests/model_case.py <model> exact.  When the golden file records where the reference's
+    triangle samples entered its rand() stream (tri_positions, tests/golden/make_tri_positions.py)
+    the runtime generates the golden run's keys and input ciphertext ITSELF (seconds; the
+    reference is not run).  Otherwise, or with ACE_MODEL_REFKEYS=1, the compiled reference
+    regenerates them on the host (minutes, ~45 GB of RAM) and the runtime imports them."""
+    import json
+    gpath = os.path.join(HERE, "golden", model + ".json")
+    if not os.path.exists(gpath):
         pytest.skip("no golden run for " + model)
-    if flag == "0" or (flag != "1" and not _enough_ram()):
-        pytest.skip("needs ~45 GB of host RAM for the reference's keys (ACE_MODEL_PARITY=1 forces it)")
-    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", model + "_ref.so")) or \
-            not os.path.exists(os.path.join(ROOT, "ace_compiler_b200", "models", "lib%s.so" % model)):
-        pytest.skip("model units not built (need the reference tree at build time)")
+    if not os.path.exists(os.path.join(ROOT, "ace_compiler_b200", "models", "lib%s.so" % model)):
+        pytest.skip("model unit not built (needs the reference tree at build time)")
+    own = "tri_positions" in json.load(open(gpath)) and os.environ.get("ACE_MODEL_REFKEYS") != "1"
+    if not own:
+        flag = os.environ.get("ACE_MODEL_PARITY")
+        if flag == "0" or (flag != "1" and not _enough_ram()):
+            pytest.skip("needs ~45 GB of host RAM for the reference's keys (ACE_MODEL_PARITY=1 forces it)")
+        if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", model + "_ref.so")):
+            pytest.skip("oracle/_ref/%s_ref.so not built (needs the reference tree at build time)" % model)
     r = subprocess.run([sys.executable, os.path.join(HERE, "model_case.py"), model, "exact"],
                        capture_output=True, text=True, timeout=3000)
     sys.stdout.write(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + "\n" + r.stderr[-4000:]
     assert "MODEL PARITY OK" in r.stdout
+
+
+def test_resnet20_bit_exact():
+    """BASELINE.json config 1: the output ciphertext of the whole emitted ResNet-20 equals the
+    golden run's (SHA-256 of its limbs; 1 925 s of Main_graph on the unmodified reference)"""
+    _bit_exact(MODEL)
 
 
 def test_resnet110_bit_exact():
