@@ -18,31 +18,49 @@ namespace ace {
 // and dropping stores that a later item of the chain overwrites was measured: 8 % SLOWER, 281 vs
 // 260 ms per two ResNet-20 images; the extra dependences cost more memory-level parallelism than
 // the saved loads give back.  Not kept.)
+// V = 2: two adjacent coefficients per thread, 16-byte accesses (N a multiple of 512 -- every
+// emitted ResNet); V = 1: any N.
+template <int V> struct ChainVec;
+template <> struct ChainVec<1> {
+  typedef u64 type;
+  static __device__ __forceinline__ u64 splat(u64 x) { return x; }
+};
+template <> struct ChainVec<2> {
+  typedef ulonglong2 type;
+  static __device__ __forceinline__ ulonglong2 splat(u64 x) { return make_ulonglong2(x, x); }
+};
+template <class F> __device__ __forceinline__ u64 chain_map(u64 x, u64 y, F f) { return f(x, y); }
+template <class F> __device__ __forceinline__ ulonglong2 chain_map(ulonglong2 x, ulonglong2 y, F f) {
+  return make_ulonglong2(f(x.x, y.x), f(x.y, y.y));
+}
+template <int V>
 __global__ void __launch_bounds__(256) ew_chain_kernel(DeviceTables T,
                                                              const __grid_constant__ ChainPack P) {
+  typedef typename ChainVec<V>::type W;
   pdl_enter();
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= T.N) return;
+  if (i * V >= T.N) return;
   const u32 k0 = P.chain_start[blockIdx.y], k1 = P.chain_start[blockIdx.y + 1];
   for (u32 k = k0; k < k1; k++) {
     const ChainItem& it = P.it[k];
     const u32 op = it.op;
-    if (op == OP_ZERO) { it.r[i] = 0; continue; }
-    if (op == OP_COPY) { it.r[i] = it.a[i]; continue; }
-    if (op == OP_FILL) { it.r[i] = (u64)(uintptr_t)it.a; continue; }
+    W* const r = reinterpret_cast<W*>(it.r);
+    if (op == OP_ZERO) { r[i] = ChainVec<V>::splat(0); continue; }
+    if (op == OP_COPY) { r[i] = reinterpret_cast<const W*>(it.a)[i]; continue; }
+    if (op == OP_FILL) { r[i] = ChainVec<V>::splat((u64)(uintptr_t)it.a); continue; }
     const Modulus m = T.mod[it.g];
-    const u64 x = it.a[i], y = it.b[i];
-    u64 z;
-    if (op == OP_ADD) z = add_mod(x, y, m.q);
-    else if (op == OP_SUB) z = sub_mod(x, y, m.q);
+    const W x = reinterpret_cast<const W*>(it.a)[i], y = reinterpret_cast<const W*>(it.b)[i];
+    W z;
+    if (op == OP_ADD) z = chain_map(x, y, [&](u64 p, u64 q) { return add_mod(p, q, m.q); });
+    else if (op == OP_SUB) z = chain_map(x, y, [&](u64 p, u64 q) { return sub_mod(p, q, m.q); });
     else {
-      z = mul_mod(x, y, m);
+      z = chain_map(x, y, [&](u64 p, u64 q) { return mul_mod(p, q, m); });
       if (op == OP_MAC) {
-        if (it.t) it.t[i] = z;
-        if (it.c) z = add_mod(it.c[i], z, m.q);
+        if (it.t) reinterpret_cast<W*>(it.t)[i] = z;
+        if (it.c) z = chain_map(reinterpret_cast<const W*>(it.c)[i], z, [&](u64 p, u64 q) { return add_mod(p, q, m.q); });
       }
     }
-    it.r[i] = z;
+    r[i] = z;
   }
 }
 
@@ -100,7 +118,10 @@ struct ContextBackend : SchedBackend {
   }
   void run_chains(const ChainPack& pack, u32 n_chains) override {
     prof::Scope ps("ew_chain", c->stream);
-    launch_chain(ew_chain_kernel, dim3((c->N + 255) / 256, n_chains), dim3(256), 0, c->stream, c->T, pack);
+    if (c->N % 512 == 0)
+      launch_chain(ew_chain_kernel<2>, dim3(c->N / 512, n_chains), dim3(256), 0, c->stream, c->T, pack);
+    else
+      launch_chain(ew_chain_kernel<1>, dim3((c->N + 255) / 256, n_chains), dim3(256), 0, c->stream, c->T, pack);
     c->launches++;
   }
   void run_gathers(const ChainPack& pack, u32 n) override {
