@@ -53,6 +53,8 @@ SIGNATURES = {
     "ace_key_switch": (C.c_int, [vp, vp, vp, vp, u32, C.c_int, i32]),
     "ace_ct_rotate": (C.c_int, [vp, vp, vp, vp, vp, u32, i32]),
     "ace_ct_mul_relin": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, u32]),
+    "ace_ct_rotate_hoisted": (C.c_int, [vp, vp, vp, vp, vp, u32, vp, sz]),
+    "ace_ct_mul_plain_acc": (C.c_int, [vp, vp, vp, vp, vp, vp, u32, C.c_int]),
     "ace_ct_rescale": (C.c_int, [vp, vp, vp, vp, vp, u32]),
     "ace_keygen": (C.c_int, [vp, C.c_uint64, vp, sz]),
     "ace_sk_import": (C.c_int, [vp, vp]),
@@ -267,6 +269,28 @@ class Context:
         d0, d1, r0, r1 = self.put(c0), self.put(c1), self.empty(nq), self.empty(nq)
         self._ck(self.lib.ace_ct_rotate(self.h, r0.ptr, r1.ptr, d0.ptr, d1.ptr, nq, rot))
         return r0.get(), r1.get()
+
+    def ct_rotate_hoisted(self, c0, c1, rots):
+        """n rotations of one ciphertext sharing one ModUp; returns [(r0, r1)] per rotation"""
+        nq = c0.shape[0]
+        d0, d1 = self.put(c0), self.put(c1)
+        outs = [(self.empty(nq), self.empty(nq)) for _ in rots]
+        p0 = (C.c_void_p * len(rots))(*[o[0].ptr for o in outs])
+        p1 = (C.c_void_p * len(rots))(*[o[1].ptr for o in outs])
+        r = (C.c_int32 * len(rots))(*rots)
+        self._ck(self.lib.ace_ct_rotate_hoisted(self.h, p0, p1, d0.ptr, d1.ptr, nq, r, len(rots)))
+        return [(a.get(), b.get()) for a, b in outs]
+
+    def ct_mul_plain_acc(self, acc, c0, c1, pt):
+        """acc (+)= ct (.) pt; acc = None starts a sum.  Returns (acc0, acc1) host arrays."""
+        nq = c0.shape[0]
+        d0, d1, dp = self.put(c0), self.put(c1), self.put(pt)
+        if acc is None:
+            a0, a1, first = self.empty(nq), self.empty(nq), 1
+        else:
+            a0, a1, first = self.put(acc[0]), self.put(acc[1]), 0
+        self._ck(self.lib.ace_ct_mul_plain_acc(self.h, a0.ptr, a1.ptr, d0.ptr, d1.ptr, dp.ptr, nq, first))
+        return a0.get(), a1.get()
 
     def ct_mul_relin(self, a0, a1, b0, b1):
         nq = a0.shape[0]

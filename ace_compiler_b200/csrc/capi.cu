@@ -188,6 +188,17 @@ int ace_ct_rotate(ace_ctx* ctx, int64_t* r0, int64_t* r1, const int64_t* c0, con
                   uint32_t num_q, int32_t rot) {
   ACE_TRY(check_level(ctx->c, num_q); ctx->c->ct_rotate(U(r0), U(r1), U(c0), U(c1), num_q, rot))
 }
+int ace_ct_rotate_hoisted(ace_ctx* ctx, int64_t* const* r0, int64_t* const* r1, const int64_t* c0,
+                          const int64_t* c1, uint32_t num_q, const int32_t* rots, size_t n) {
+  ACE_TRY(check_level(ctx->c, num_q);
+          ctx->c->ct_rotate_hoisted(reinterpret_cast<u64* const*>(r0), reinterpret_cast<u64* const*>(r1), U(c0),
+                                    U(c1), num_q, rots, n))
+}
+int ace_ct_mul_plain_acc(ace_ctx* ctx, int64_t* acc0, int64_t* acc1, const int64_t* c0, const int64_t* c1,
+                         const int64_t* pt, uint32_t num_q, int first) {
+  ACE_TRY(check_level(ctx->c, num_q);
+          ctx->c->ct_mul_plain_acc(U(acc0), U(acc1), U(c0), U(c1), U(pt), num_q, first != 0))
+}
 int ace_ct_mul_relin(ace_ctx* ctx, int64_t* r0, int64_t* r1, const int64_t* a0,
                      const int64_t* a1, const int64_t* b0, const int64_t* b1, uint32_t num_q) {
   ACE_TRY(check_level(ctx->c, num_q);

@@ -787,6 +787,61 @@ void Context::ct_rotate(u64* r0, u64* r1, const u64* c0, const u64* c1, u32 num_
   free_limbs(s);
 }
 
+// n rotations of ONE ciphertext: Decomp_modup of c1 once, then per rotation the key inner
+// product, ModDown (+ c0) and the automorphism -- what the reference's bootstrap does by hand
+// (Switch_key_precompute reused by every Fast_rotate, ckks_bootstrap_context.c:1284-1299) and what
+// the 9 input rotations of an emitted convolution could share (ut_ksw_opt.cxx:663-770).  Every
+// output is bit-identical to ct_rotate() of the same index: the ModUp does not depend on the key.
+void Context::ct_rotate_hoisted(u64* const* r0, u64* const* r1, const u64* c0, const u64* c1, u32 num_q,
+                                const int32_t* rots, size_t n) {
+  for (size_t i = 0; i < n; i++)
+    if (!has_rot_key(auto_index(rots[i]))) throw std::runtime_error("rotation key not loaded");
+  const u32 beta = (u32)num_decomp(num_q), W = num_q + (u32)K;
+  u64* ext = alloc_limbs((size_t)beta * W, false);
+  modup_all(ext, c1, num_q);
+  // the ModDowns of a group of rotations run as ONE batch (one inverse transform over all their
+  // P limbs, one base conversion, one forward transform, one tail): 2.5 -> 2.2 ms for nine
+  // rotations at l = 34 against one ModDown pair per rotation (nine separate ct_rotate: 4.2 ms)
+  constexpr size_t kGroup = 12;
+  const size_t g_max = n < kGroup ? n : kGroup;
+  u64* acc = alloc_limbs(g_max * 2 * (size_t)W, false);
+  u64* s   = alloc_limbs(g_max * 2 * (size_t)num_q, false);
+  std::vector<ModdownJob> jobs;
+  for (size_t at = 0; at < n; at += kGroup) {
+    const size_t m = n - at < kGroup ? n - at : kGroup;
+    jobs.clear();
+    for (size_t i = 0; i < m; i++) {
+      u64* a0 = acc + i * 2 * (size_t)W * N;
+      u64* s0 = s + i * 2 * (size_t)num_q * N;
+      ksw_acc(a0, a0 + (size_t)W * N, ext, c1, num_q, rot_key(auto_index(rots[at + i])));
+      jobs.push_back(ModdownJob{s0, a0, num_q});
+      jobs.push_back(ModdownJob{s0 + (size_t)num_q * N, a0 + (size_t)W * N, num_q});
+    }
+    moddown_batch(jobs.data(), jobs.size());
+    for (size_t i = 0; i < m; i++) {
+      u64* s0 = s + i * 2 * (size_t)num_q * N;
+      const int64_t* order = auto_order(auto_index(rots[at + i]));
+      launch_ew(T, EW_ADD, s0, s0, c0, 0, num_q, stream);
+      launch_gather(T, r0[at + i], s0, order, 0, num_q, stream);
+      launch_gather(T, r1[at + i], s0 + (size_t)num_q * N, order, 0, num_q, stream);
+      tr(TR_LIMB_ADD, 0, num_q);
+      tr(TR_LIMB_ROT, 0, 2 * num_q);
+      launches += 3;
+    }
+  }
+  free_limbs(ext); free_limbs(acc); free_limbs(s);
+}
+
+// acc (+)= ct (.) pt, both polynomials, all limbs in one launch (Mul_plain + Add_ciph of the
+// emitted convolution loops: 2 Hw_modmul + 2 Hw_modadd per limb)
+void Context::ct_mul_plain_acc(u64* acc0, u64* acc1, const u64* c0, const u64* c1, const u64* pt, u32 num_q,
+                               bool first) {
+  launch_ct_mul_plain_acc(T, acc0, acc1, first ? nullptr : acc0, first ? nullptr : acc1, c0, c1, pt, num_q, stream);
+  tr(TR_LIMB_MUL, 0, 2 * num_q);
+  if (!first) tr(TR_LIMB_ADD, 0, 2 * num_q);
+  launches++;
+}
+
 // tensor product + emitted Relinearize(): r0 = a0 b0 + ks0(a1 b1), r1 = a0 b1 + a1 b0 + ks1
 void Context::ct_mul_relin(u64* r0, u64* r1, const u64* a0, const u64* a1, const u64* b0,
                            const u64* b1, u32 num_q) {

@@ -168,6 +168,10 @@ class Context {
   void mod_down_pair(u64* out0, u64* out1, const u64* a0, const u64* a1, u32 num_q,
                      const u64* add0, const u64* add1 = nullptr);
   void ct_rotate(u64* r0, u64* r1, const u64* c0, const u64* c1, u32 num_q, int32_t rot_idx);
+  void ct_rotate_hoisted(u64* const* r0, u64* const* r1, const u64* c0, const u64* c1, u32 num_q,
+                         const int32_t* rots, size_t n);
+  void ct_mul_plain_acc(u64* acc0, u64* acc1, const u64* c0, const u64* c1, const u64* pt, u32 num_q,
+                        bool first);
   void ct_mul_relin(u64* r0, u64* r1, const u64* a0, const u64* a1, const u64* b0,
                     const u64* b1, u32 num_q);
 

@@ -265,6 +265,8 @@ void launch_pt_dot(const DeviceTables& T, u64* out0, u64* out1, const DotArgs& a
 
 // acc0[y] += c0[y] * sc[y] on the Q limbs only, then nothing else: the "add_first" term of
 // Fast_rotate_ext (ckks_evaluator.c:566-573); r may alias acc.
+void launch_ct_mul_plain_acc(const DeviceTables& T, u64* acc0, u64* acc1, const u64* in0, const u64* in1,
+                             const u64* c0, const u64* c1, const u64* pt, u32 n_limbs, cudaStream_t s);
 void launch_mul_scalar_add(const DeviceTables& T, u64* r, const u64* acc, const u64* c,
                            const u64* sc, const u64* sc_sh, u32 n_limbs, cudaStream_t s);
 

@@ -175,6 +175,32 @@ void launch_mul_scalar_add(const DeviceTables& T, u64* r, const u64* acc, const 
   launch_chain(mul_scalar_add_kernel, grid_for(T, n_limbs), 256, 0, s, T, r, acc, c, sc, sc_sh);
 }
 
+// acc += ct (.) pt over all limbs of both polynomials: the plaintext limb is read once for c0 and
+// c1 (emitted code: 2 Hw_modmul + 2 Hw_modadd per limb and term of a convolution).  acc may be
+// the first operand of a fresh sum (acc_in == nullptr: acc = ct (.) pt).
+__global__ void __launch_bounds__(256) ct_mul_plain_acc_kernel(DeviceTables T, u64* acc0, u64* acc1,
+                                                               const u64* acc_in0, const u64* acc_in1,
+                                                               const u64* __restrict__ c0,
+                                                               const u64* __restrict__ c1,
+                                                               const u64* __restrict__ pt) {
+  pdl_enter();
+  const Modulus m   = T.mod[blockIdx.y];
+  const size_t  off = (size_t)blockIdx.y * T.N;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
+    const u64 p = pt[off + i];
+    u64 z0 = mul_mod(c0[off + i], p, m), z1 = mul_mod(c1[off + i], p, m);
+    if (acc_in0) { z0 = add_mod(acc_in0[off + i], z0, m.q); z1 = add_mod(acc_in1[off + i], z1, m.q); }
+    acc0[off + i] = z0;
+    acc1[off + i] = z1;
+  }
+}
+void launch_ct_mul_plain_acc(const DeviceTables& T, u64* acc0, u64* acc1, const u64* in0, const u64* in1,
+                             const u64* c0, const u64* c1, const u64* pt, u32 n_limbs, cudaStream_t s) {
+  prof::Scope prof_scope_("ct_mul_plain_acc", s);
+  if (n_limbs == 0) return;
+  launch_chain(ct_mul_plain_acc_kernel, grid_for(T, n_limbs), 256, 0, s, T, acc0, acc1, in0, in1, c0, c1, pt);
+}
+
 // Key inner product with the epilogue of a "fast" rotation in the extended basis
 // (Fast_rotate_ext, ckks_evaluator.c:537-577 = Fast_switch_key_ext + P*c0 + automorphism):
 //   v0[o] = sum_j ext_j[o] key0_j[g(o)]  (+ c0[o] * (P mod q_o) on the Q limbs)

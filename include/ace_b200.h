@@ -89,6 +89,17 @@ const int64_t* ace_swk_poly(ace_ctx* ctx, int is_rot, int32_t rot_idx, uint32_t 
 int ace_key_switch(ace_ctx* ctx, int64_t* out0, int64_t* out1, const int64_t* d, uint32_t num_q, int is_rot, int32_t rot_idx);
 int ace_ct_rotate(ace_ctx* ctx, int64_t* r0, int64_t* r1, const int64_t* c0, const int64_t* c1, uint32_t num_q, int32_t rot_idx);
 int ace_ct_mul_relin(ace_ctx* ctx, int64_t* r0, int64_t* r1, const int64_t* a0, const int64_t* a1, const int64_t* b0, const int64_t* b1, uint32_t num_q);
+/*      ace_ct_rotate_hoisted: n rotations of one ciphertext with ONE Decomp_modup (Switch_key_precompute
+ *      reused by every rotation, ckks_bootstrap_context.c:1284-1299; the fusion measured in
+ *      unittest/ut_ksw_opt.cxx:663-770); r0[i] / r1[i] are bit-identical to ace_ct_rotate(rot_idxs[i]).
+ *      ace_ct_mul_plain_acc: acc (+)= ct (.) pt over num_q limbs of both polynomials (first != 0:
+ *      acc = ct (.) pt) -- Mul_plain + Add_ciph of the emitted convolution loops in one launch.
+ *      These two are what a POLY emitter retargeted to ciphertext granularity would call
+ *      (lib_provider.h:18-21). */
+int ace_ct_rotate_hoisted(ace_ctx* ctx, int64_t* const* r0, int64_t* const* r1, const int64_t* c0, const int64_t* c1,
+                          uint32_t num_q, const int32_t* rot_idxs, size_t n);
+int ace_ct_mul_plain_acc(ace_ctx* ctx, int64_t* acc0, int64_t* acc1, const int64_t* c0, const int64_t* c1,
+                         const int64_t* pt, uint32_t num_q, int first);
 int ace_ct_rescale(ace_ctx* ctx, int64_t* r0, int64_t* r1, const int64_t* c0, const int64_t* c1, uint32_t num_q);
 
 /* ---- client side: keys, encryption, CKKS encode/decode.

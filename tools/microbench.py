@@ -63,6 +63,15 @@ def main():
         res["L=%d ct_rotate" % lv] = timeit(lambda: lib.ace_ct_rotate(h, o0, o1, a0, a1, lv, 1))
         res["L=%d ct_mul_relin" % lv] = timeit(lambda: lib.ace_ct_mul_relin(h, o0, o1, a0, a1, b0, b1, lv))
         res["L=%d ct_rescale" % lv] = timeit(lambda: lib.ace_ct_rescale(h, o0, o1, a0, a1, lv))
+        # 9 rotations of one ciphertext (the input rotations of a 3x3 convolution): one call with a
+        # shared ModUp against nine calls (the same key every time: only the timing matters here)
+        outs = [ctx.empty(2 * lv) for _ in range(9)]
+        p0 = (C.c_void_p * 9)(*[x.ptr for x in outs])
+        p1 = (C.c_void_p * 9)(*[x.ptr + lv * NB for x in outs])
+        r9 = (C.c_int32 * 9)(*([1] * 9))
+        res["L=%d 9 x ct_rotate" % lv] = timeit(lambda: [lib.ace_ct_rotate(h, p0[k], p1[k], a0, a1, lv, 1) for k in range(9)], reps=5)
+        res["L=%d ct_rotate_hoisted x9" % lv] = timeit(lambda: lib.ace_ct_rotate_hoisted(h, p0, p1, a0, a1, lv, r9, 9), reps=5)
+        res["L=%d ct_mul_plain_acc" % lv] = timeit(lambda: lib.ace_ct_mul_plain_acc(h, o0, o1, a0, a1, b0, lv, 0))
     for k, v in res.items():
         print("%-32s %10.1f us" % (k, v))
     ctx.close()
