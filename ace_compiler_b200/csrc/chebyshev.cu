@@ -9,6 +9,7 @@
 #include <cstdlib>
 
 #include "evaluator.h"
+#include "host_math.h"
 
 namespace ace {
 
@@ -116,6 +117,52 @@ static void cheb_long_div(vd& q, vd& r, const vd& f, const vd& g) {
 // out = rescale(sum_i weights[i] * list[i]) over the first `size` ciphertexts
 void Evaluator::eval_linear_wsum(Ct& out, std::vector<Ct>& list, size_t size,
                                  const double* weights) {
+  // One kernel per 12 terms instead of Mul_const + Add_ciph (+ a copy) per term: the same canonical
+  // residues (modular sums do not depend on their order), a fifth of the traffic, and a bootstrap
+  // loses ~200 of its ~960 launches.  ACE_B200_NO_WSUM=1: term by term, as the reference.
+  static const bool fused = getenv("ACE_B200_NO_WSUM") == nullptr;
+  bool usable = fused && c->L + 0 <= (size_t)kMaxWsumLimbs;
+  for (size_t i = 0; i < size && usable; i++)
+    if (weights[i] != 0. && (list[i].np || &list[i] == &out)) usable = false;
+  if (usable) {
+    const double delta = (double)((u64)1 << c->params.scaling_mod_size);
+    u32  level = 0;
+    bool any = false;
+    for (size_t i = 0; i < size; i++)
+      if (weights[i] != 0.) { level = any ? (list[i].nq < level ? list[i].nq : level) : list[i].nq; any = true; }
+    if (!any) throw std::runtime_error("polynomial has no non-zero coefficient");
+    static thread_local WsumArgs args;
+    args.n = 0; args.acc = 0;
+    bool first_term = true;
+    u32  run_level = 0;
+    for (size_t i = 0; i < size; i++) {
+      if (weights[i] == 0.) continue;
+      Ct& a = list[i];
+      if (first_term) {  // what copy(out, Mul_const(list[i])) leaves in out's header
+        reserve(out, a.nq, 0);
+        out.sf = a.sf * pow(delta, 1); out.sfd = a.sfd + 1; out.slots = a.slots;
+        run_level = a.nq;
+        first_term = false;
+      } else {
+        run_level = a.nq < run_level ? a.nq : run_level;
+        c->tr(Context::TR_LIMB_ADD, 0, 2 * run_level);
+      }
+      c->tr(Context::TR_LIMB_MUL, 0, 2 * a.nq);
+      const std::vector<u64> res = c->value_residues(weights[i], a.nq, 1);
+      const u32 t = args.n++;
+      args.c0[t] = a.c0; args.c1[t] = a.c1;
+      for (u32 y = 0; y < level; y++) { args.w[t][y] = res[y]; args.wsh[t][y] = hm::shoup(res[y], c->mod[y]); }
+      if (args.n == (u32)kMaxWsum) {
+        launch_ct_wsum(c->T, out.c0, out.c1, args, level, c->stream);
+        c->launches++;
+        args.n = 0; args.acc = 1;
+      }
+    }
+    if (args.n) { launch_ct_wsum(c->T, out.c0, out.c1, args, level, c->stream); c->launches++; }
+    out.nq = level;
+    rescale(out, out);
+    return;
+  }
   bool first = true;
   Ct tmp;
   for (size_t i = 0; i < size; i++) {

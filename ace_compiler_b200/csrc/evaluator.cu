@@ -75,10 +75,9 @@ void Evaluator::add(Ct& res, Ct& a, Ct& b) {
   u32 level;
   binary_meta(this, res, a, b, level);
   Basis bs{level, a.np, (u32)c->L};
-  launch_ew_basis(c->T, EW_ADD, res.c0, a.c0, b.c0, bs, c->stream);
-  launch_ew_basis(c->T, EW_ADD, res.c1, a.c1, b.c1, bs, c->stream);
+  launch_ew_basis2(c->T, EW_ADD, res.c0, res.c1, a.c0, a.c1, b.c0, b.c1, bs, c->stream);
   c->tr(Context::TR_LIMB_ADD, 0, 2 * bs.width());
-  c->launches += 2;
+  c->launches += 1;
   res.nq = level;
 }
 
@@ -87,10 +86,9 @@ void Evaluator::sub(Ct& res, Ct& a, Ct& b) {
   binary_meta(this, res, a, b, level);
   if (a.np) throw std::runtime_error("sub: extended ciphertexts are not supported");
   Basis bs{level, 0, (u32)c->L};
-  launch_ew_basis(c->T, EW_SUB, res.c0, a.c0, b.c0, bs, c->stream);
-  launch_ew_basis(c->T, EW_SUB, res.c1, a.c1, b.c1, bs, c->stream);
+  launch_ew_basis2(c->T, EW_SUB, res.c0, res.c1, a.c0, a.c1, b.c0, b.c1, bs, c->stream);
   c->tr(Context::TR_LIMB_ADD, 0, 2 * bs.width());
-  c->launches += 2;
+  c->launches += 1;
   res.nq = level;
 }
 
@@ -130,10 +128,9 @@ void Evaluator::mul_const(Ct& res, Ct& a, double v) {
   u32 sfd = a.sfd + 1, slots = a.slots, nq = a.nq;
   if (&res != &a) reserve(res, nq, 0);
   Basis bs{nq, 0, (u32)c->L};
-  launch_mul_scalar_pack(c->T, res.c0, a.c0, sp, bs, c->stream);
-  launch_mul_scalar_pack(c->T, res.c1, a.c1, sp, bs, c->stream);
+  launch_mul_scalar_pack2(c->T, res.c0, res.c1, a.c0, a.c1, sp, bs, c->stream);
   c->tr(Context::TR_LIMB_MUL, 0, 2 * bs.width());
-  c->launches += 2;
+  c->launches += 1;
   res.sf = sf; res.sfd = sfd; res.slots = slots;
 }
 
@@ -149,10 +146,9 @@ void Evaluator::mul_integer(Ct& res, Ct& a, u32 power) {
     reserve(res, a.nq, a.np);
     res.sf = a.sf; res.sfd = a.sfd; res.slots = a.slots;
   }
-  launch_mul_scalar_pack(c->T, res.c0, a.c0, sp, bs, c->stream);
-  launch_mul_scalar_pack(c->T, res.c1, a.c1, sp, bs, c->stream);
+  launch_mul_scalar_pack2(c->T, res.c0, res.c1, a.c0, a.c1, sp, bs, c->stream);
   c->tr(Context::TR_LIMB_MUL, 0, 2 * bs.width());
-  c->launches += 2;
+  c->launches += 1;
 }
 
 // Mul_by_monomial: multiply by X^power; the monomial is built in coefficient form

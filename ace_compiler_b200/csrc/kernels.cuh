@@ -221,6 +221,8 @@ struct Basis {
 void launch_ew_basis(const DeviceTables& T, EwOp op, u64* r, const u64* a, const u64* b,
                      Basis bs, cudaStream_t s);
 // r[y][i] = a[y][order[i]] over all limbs (Automorphism_transform, polynomial.c:299-340)
+void launch_ew_basis2(const DeviceTables& T, EwOp op, u64* r0, u64* r1, const u64* a0, const u64* a1,
+                      const u64* b0, const u64* b1, Basis bs, cudaStream_t s);  // both polynomials, one launch
 void launch_gather_basis(const DeviceTables& T, u64* r, const u64* a, const int64_t* order,
                          Basis bs, cudaStream_t s);
 // Per-limb scalars passed by value (no staging copy, no sync): v[y] < q_y, sh[y] its Shoup
@@ -238,6 +240,8 @@ void launch_mul_scalar_pack(const DeviceTables& T, u64* r, const u64* a, const S
                             Basis bs, cudaStream_t s);
 // ModRaise (Transform_values_from_level0, ckks_bootstrap_context.c:1527-1550):
 // out[0] = in, out[y] = Switch_modulus(in, q_0, q_y) for 0 < y < n_limbs; coefficient form
+void launch_mul_scalar_pack2(const DeviceTables& T, u64* r0, u64* r1, const u64* a0, const u64* a1,
+                             const ScalarPack& sc, Basis bs, cudaStream_t s);
 void launch_mod_raise(const DeviceTables& T, u64* out, const u64* in, u32 n_limbs,
                       cudaStream_t s);
 
@@ -265,6 +269,18 @@ void launch_pt_dot(const DeviceTables& T, u64* out0, u64* out1, const DotArgs& a
 
 // acc0[y] += c0[y] * sc[y] on the Q limbs only, then nothing else: the "add_first" term of
 // Fast_rotate_ext (ckks_evaluator.c:566-573); r may alias acc.
+// out = sum_t w_t (.) ct_t over both polynomials (Eval_linear_wsum, ckks_chebyshev.c:282-323: Mul_const
+// + Add_ciph per term): every term is read once, the sum is written once.  acc != 0: out is itself
+// the first term (weight 1).  Canonical residues: the order of the modular additions does not matter.
+constexpr int kMaxWsum = 12, kMaxWsumLimbs = 64;
+struct WsumArgs {
+  u32        n, acc;
+  const u64* c0[kMaxWsum];
+  const u64* c1[kMaxWsum];
+  u64        w[kMaxWsum][kMaxWsumLimbs];
+  u64        wsh[kMaxWsum][kMaxWsumLimbs];
+};
+void launch_ct_wsum(const DeviceTables& T, u64* out0, u64* out1, const WsumArgs& args, u32 n_limbs, cudaStream_t s);
 void launch_ct_mul_plain_acc(const DeviceTables& T, u64* acc0, u64* acc1, const u64* in0, const u64* in1,
                              const u64* c0, const u64* c1, const u64* pt, u32 n_limbs, cudaStream_t s);
 void launch_mul_scalar_add(const DeviceTables& T, u64* r, const u64* acc, const u64* c,

@@ -38,6 +38,37 @@ void launch_ew_basis(const DeviceTables& T, EwOp op, u64* r, const u64* a, const
   }
 }
 
+// both polynomials of a ciphertext in one launch (blockIdx.z = polynomial): r_z = a_z op b_z
+template <int OP>
+__global__ void __launch_bounds__(256) ew_basis2_kernel(DeviceTables T, u64* r0, u64* r1, const u64* a0,
+                                                        const u64* a1, const u64* b0, const u64* b1, Basis bs) {
+  pdl_enter();
+  u64* __restrict__       r = blockIdx.z ? r1 : r0;
+  const u64* __restrict__ a = blockIdx.z ? a1 : a0;
+  const u64* __restrict__ b = blockIdx.z ? b1 : b0;
+  const Modulus m   = T.mod[bs.g(blockIdx.y)];
+  const size_t  off = (size_t)blockIdx.y * T.N;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
+    u64 x = a[off + i], y = b[off + i], z;
+    if (OP == EW_ADD) z = add_mod(x, y, m.q);
+    if (OP == EW_SUB) z = sub_mod(x, y, m.q);
+    if (OP == EW_MUL) z = mul_mod(x, y, m);
+    r[off + i] = z;
+  }
+}
+void launch_ew_basis2(const DeviceTables& T, EwOp op, u64* r0, u64* r1, const u64* a0, const u64* a1,
+                      const u64* b0, const u64* b1, Basis bs, cudaStream_t s) {
+  prof::Scope prof_scope_("ew_basis", s);
+  if (bs.width() == 0) return;
+  dim3 grid = grid_for(T, bs.width());
+  grid.z = 2;
+  switch (op) {
+    case EW_ADD: launch_chain(ew_basis2_kernel<EW_ADD>, grid, 256, 0, s, T, r0, r1, a0, a1, b0, b1, bs); break;
+    case EW_SUB: launch_chain(ew_basis2_kernel<EW_SUB>, grid, 256, 0, s, T, r0, r1, a0, a1, b0, b1, bs); break;
+    case EW_MUL: launch_chain(ew_basis2_kernel<EW_MUL>, grid, 256, 0, s, T, r0, r1, a0, a1, b0, b1, bs); break;
+  }
+}
+
 __global__ void __launch_bounds__(256) gather_basis_kernel(DeviceTables T, u64* __restrict__ r,
                                                            const u64* __restrict__ a,
                                                            const int64_t* __restrict__ order,
@@ -93,6 +124,27 @@ void launch_mul_scalar_pack(const DeviceTables& T, u64* r, const u64* a, const S
   prof::Scope prof_scope_("mul_scalar_pack", s);
   if (bs.width() == 0) return;
   launch_chain(mul_scalar_pack_kernel, grid_for(T, bs.width()), 256, 0, s, T, r, a, sc, bs);
+}
+
+__global__ void __launch_bounds__(256) mul_scalar_pack2_kernel(DeviceTables T, u64* r0, u64* r1, const u64* a0,
+                                                               const u64* a1, const __grid_constant__ ScalarPack sc,
+                                                               Basis bs) {
+  pdl_enter();
+  u64* __restrict__       r = blockIdx.z ? r1 : r0;
+  const u64* __restrict__ a = blockIdx.z ? a1 : a0;
+  const u64    q   = T.mod[bs.g(blockIdx.y)].q;
+  const u64    w = sc.v[blockIdx.y], wsh = sc.sh[blockIdx.y];
+  const size_t off = (size_t)blockIdx.y * T.N;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x)
+    r[off + i] = mul_shoup(a[off + i], w, wsh, q);
+}
+void launch_mul_scalar_pack2(const DeviceTables& T, u64* r0, u64* r1, const u64* a0, const u64* a1,
+                             const ScalarPack& sc, Basis bs, cudaStream_t s) {
+  prof::Scope prof_scope_("mul_scalar_pack", s);
+  if (bs.width() == 0) return;
+  dim3 grid = grid_for(T, bs.width());
+  grid.z = 2;
+  launch_chain(mul_scalar_pack2_kernel, grid, 256, 0, s, T, r0, r1, a0, a1, sc, bs);
 }
 
 __global__ void __launch_bounds__(256) mod_raise_kernel(DeviceTables T, u64* __restrict__ out,
@@ -173,6 +225,30 @@ void launch_mul_scalar_add(const DeviceTables& T, u64* r, const u64* acc, const 
   prof::Scope prof_scope_("mul_scalar_add", s);
   if (n_limbs == 0) return;
   launch_chain(mul_scalar_add_kernel, grid_for(T, n_limbs), 256, 0, s, T, r, acc, c, sc, sc_sh);
+}
+
+__global__ void __launch_bounds__(256) ct_wsum_kernel(DeviceTables T, u64* out0, u64* out1,
+                                                      const __grid_constant__ WsumArgs A) {
+  pdl_enter();
+  const u32    y   = blockIdx.y;
+  const u64    q   = T.mod[y].q;
+  const size_t off = (size_t)y * T.N;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
+    u64 s0 = A.acc ? out0[off + i] : 0, s1 = A.acc ? out1[off + i] : 0;
+#pragma unroll 4
+    for (u32 t = 0; t < A.n; t++) {
+      const u64 w = A.w[t][y], wsh = A.wsh[t][y];
+      s0 = add_mod(s0, mul_shoup(A.c0[t][off + i], w, wsh, q), q);
+      s1 = add_mod(s1, mul_shoup(A.c1[t][off + i], w, wsh, q), q);
+    }
+    out0[off + i] = s0;
+    out1[off + i] = s1;
+  }
+}
+void launch_ct_wsum(const DeviceTables& T, u64* out0, u64* out1, const WsumArgs& args, u32 n_limbs, cudaStream_t s) {
+  prof::Scope prof_scope_("ct_wsum", s);
+  if (n_limbs == 0 || args.n == 0) return;
+  launch_chain(ct_wsum_kernel, grid_for(T, n_limbs), 256, 0, s, T, out0, out1, args);
 }
 
 // acc += ct (.) pt over all limbs of both polynomials: the plaintext limb is read once for c0 and
