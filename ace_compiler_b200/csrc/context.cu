@@ -747,11 +747,12 @@ void Context::mod_down_pair(u64* out0, u64* out1, const u64* a0, const u64* a1, 
   cb.base = conv; cb.src = nullptr; cb.n = np * num_q;
   for (u32 i = 0; i < np * num_q; i++) { cb.slot[i] = (u16)i; cb.g[i] = (u16)(i % num_q); }
   launch_ntt(T, cb, stream);
-  launch_moddown_tail(T, out0, a0, conv, add0, pinv_mod_q_, pinv_mod_q_sh_, num_q, stream);
   if (a1)
-    launch_moddown_tail(T, out1, a1, conv + (size_t)num_q * N, add1, pinv_mod_q_,
-                        pinv_mod_q_sh_, num_q, stream);
-  launches += 1 + np + ((logN > 12) ? 2 : 1);
+    launch_moddown_tail2(T, out0, out1, a0, a1, conv, conv + (size_t)num_q * N, add0, add1, pinv_mod_q_,
+                         pinv_mod_q_sh_, num_q, stream);
+  else
+    launch_moddown_tail(T, out0, a0, conv, add0, pinv_mod_q_, pinv_mod_q_sh_, num_q, stream);
+  launches += 1 + 1 + ((logN > 12) ? 2 : 1);
   free_limbs(pc); free_limbs(conv);
 }
 

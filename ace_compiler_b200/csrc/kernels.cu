@@ -791,6 +791,38 @@ void launch_moddown_tail(const DeviceTables& T, u64* out, const u64* old, const 
                                                           pinv_sh);
 }
 
+// the tails of both polynomials of a key switch in one launch (blockIdx.z = polynomial)
+__global__ void __launch_bounds__(256) moddown_tail2_kernel(DeviceTables T, u64* out0, u64* out1, const u64* old0,
+                                                            const u64* old1, const u64* conv0, const u64* conv1,
+                                                            const u64* add0, const u64* add1,
+                                                            const u64* __restrict__ pinv,
+                                                            const u64* __restrict__ pinv_sh) {
+  pdl_enter();
+  u64* __restrict__       out  = blockIdx.z ? out1 : out0;
+  const u64* __restrict__ old  = blockIdx.z ? old1 : old0;
+  const u64* __restrict__ conv = blockIdx.z ? conv1 : conv0;
+  const u64* __restrict__ add  = blockIdx.z ? add1 : add0;
+  const u32    l   = blockIdx.y;
+  const u64    q   = T.mod[l].q;
+  const u64    w = pinv[l], wsh = pinv_sh[l];
+  const size_t off = (size_t)l * T.N;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < T.N; i += gridDim.x * blockDim.x) {
+    u64 v = mul_shoup(sub_mod(old[off + i], conv[off + i], q), w, wsh, q);
+    if (add != nullptr) v = add_mod(v, add[off + i], q);
+    out[off + i] = v;
+  }
+}
+void launch_moddown_tail2(const DeviceTables& T, u64* out0, u64* out1, const u64* old0, const u64* old1,
+                          const u64* conv0, const u64* conv1, const u64* add0, const u64* add1, const u64* pinv,
+                          const u64* pinv_sh, u32 n_limbs, cudaStream_t s) {
+  prof::Scope prof_scope_("moddown_tail", s);
+  if (n_limbs == 0) return;
+  dim3 grid = ew_grid(T, n_limbs);
+  grid.z = 2;
+  launch_chain(moddown_tail2_kernel, grid, 256, 0, s, T, out0, out1, old0, old1, conv0, conv1, add0, add1, pinv,
+               pinv_sh);
+}
+
 __global__ void __launch_bounds__(256) rescale_pre_kernel(DeviceTables T, u64* __restrict__ tmp,
                                                           const u64* __restrict__ last, u32 l,
                                                           const u64* __restrict__ negqlinv,

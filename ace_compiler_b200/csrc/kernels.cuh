@@ -170,6 +170,9 @@ void launch_moddown_tail(const DeviceTables& T, u64* out, const u64* old, const 
 
 // d0 = a0 b0, d1 = a0 b1 + a1 b0, d2 = a1 b1 over n_limbs Q limbs (tensor product of two
 // ciphertexts, ckks_evaluator.c:133-165) in one pass
+void launch_moddown_tail2(const DeviceTables& T, u64* out0, u64* out1, const u64* old0, const u64* old1,
+                          const u64* conv0, const u64* conv1, const u64* add0, const u64* add1, const u64* pinv,
+                          const u64* pinv_sh, u32 n_limbs, cudaStream_t s);
 void launch_tensor(const DeviceTables& T, u64* d0, u64* d1, u64* d2, const u64* a0,
                    const u64* a1, const u64* b0, const u64* b1, u32 n_limbs, cudaStream_t s);
 

@@ -37,6 +37,9 @@ def main():
     t_i = timeit(lambda: lib.ace_intt(h, d.ptr, 0, G))
     t_q = timeit(lambda: lib.ace_ntt(h, d.ptr, 0, ctx.L))
     t_p = timeit(lambda: lib.ace_ntt(h, d.ptr + ctx.L * N * 8, ctx.L, ctx.K))
+    t_ip = timeit(lambda: lib.ace_intt(h, d.ptr + ctx.L * N * 8, ctx.L, ctx.K))
+    t_ip2 = timeit(lambda: lib.ace_intt(h, d.ptr + (ctx.L - 11) * N * 8, ctx.L - 11, 22))
+    print("intt P x%d: %.1f us   intt 11 Q + 11 P: %.1f us" % (ctx.K, t_ip, t_ip2))
     small = []
     for n in (1, 2, 4, 8, 9, 10, 16, 18, 19, 24, 27, 28, 30, 33):
         small.append("x%d %.1f/%.1f" % (n, timeit(lambda: lib.ace_ntt(h, d.ptr, 0, n)), timeit(lambda: lib.ace_intt(h, d.ptr, 0, n))))
