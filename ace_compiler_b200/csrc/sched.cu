@@ -118,7 +118,10 @@ struct ContextBackend : SchedBackend {
   }
   void run_chains(const ChainPack& pack, u32 n_chains) override {
     prof::Scope ps("ew_chain", c->stream);
-    if (c->N % 512 == 0)
+    // a few long chains (the 576-term sums of the last convolutions run on 3 limbs: three chains of
+    // 1 161 items per wave, ACE_SCHED_LONGCHAINS=1) leave most of the GPU idle: one coefficient
+    // per thread then, twice the threads
+    if (c->N % 512 == 0 && n_chains > 8)
       launch_chain(ew_chain_kernel<2>, dim3(c->N / 512, n_chains), dim3(256), 0, c->stream, c->T, pack);
     else
       launch_chain(ew_chain_kernel<1>, dim3((c->N + 255) / 256, n_chains), dim3(256), 0, c->stream, c->T, pack);
@@ -638,8 +641,29 @@ void Scheduler::run_chains(std::vector<u32>& idx) {
     n_chain_launches++;
     items = chains = 0;
   };
+  static const bool dump_long = getenv("ACE_SCHED_LONGCHAINS") != nullptr;  // debugging aid
   for (u32 ch = 0; ch < n_chains; ch++) {
     u32 len = cnt[ch + 1] - cnt[ch], at = cnt[ch];
+    if (dump_long && len > (u32)kChainCap) {
+      u32 kinds[16] = {0}, tlive = 0;
+      std::vector<const u64*> rs, ts, as;
+      for (u32 q = 0; q < len; q++) {
+        const Op& o = ops_[idx[order[at + q]]];
+        kinds[o.kind & 15]++;
+        rs.push_back(o.r);
+        if (o.kind == OP_MAC && o.t_live) { tlive++; ts.push_back(o.t); }
+      }
+      std::sort(rs.begin(), rs.end()); rs.erase(std::unique(rs.begin(), rs.end()), rs.end());
+      std::sort(ts.begin(), ts.end()); ts.erase(std::unique(ts.begin(), ts.end()), ts.end());
+      fprintf(stderr, "[sched] chain of %u items (of %zu in the wave, %u chains): distinct r %zu, live t %u (distinct %zu); kinds",
+              len, n, n_chains, rs.size(), tlive, ts.size());
+      for (int k = 0; k < 16; k++) if (kinds[k]) fprintf(stderr, " %d:%u", k, kinds[k]);
+      fprintf(stderr, "\n");
+      for (u32 q = 0; q < 6 && q < len; q++) {
+        const Op& o = ops_[idx[order[at + q]]];
+        fprintf(stderr, "    kind %d g %u r=%p a=%p b=%p c=%p t=%p tl=%d\n", (int)o.kind, o.g, (void*)o.r, (void*)o.a, (void*)o.b, (void*)o.c, (void*)o.t, (int)o.t_live);
+      }
+    }
     while (len > 0) {
       if (items == (u32)kChainCap || (items > 0 && items + len > (u32)kChainCap && len <= (u32)kChainCap))
         launch();
