@@ -374,14 +374,31 @@ void Scheduler::ew(SchedOp op, u64* r, const u64* a, const u64* b, u32 g) {
     if (op == OP_ADD) { copy(r, za ? b : a, 1); return; }
     if (op == OP_SUB && zb) { copy(r, a, 1); return; }
   }
-  // ---- Hw_modmul(tmp, x, y) directly followed by Hw_modadd(r, acc, tmp): one multiply-add
-  if (op == OP_ADD && !ops_.empty()) {
-    Op& m = ops_.back();
+  // ---- Hw_modmul(tmp, x, y) followed by Hw_modadd(r, acc, tmp): one multiply-add.  Directly
+  // followed (the key inner products of Rotate / Relinearize: mul, add, mul, add), or with ONE
+  // unrelated multiplication in between (the emitted convolutions: mul c0, mul c1, add c0, add
+  // c1 -- GEN20:1494-1500): the op in between must not touch tmp, acc or r, so the addition
+  // commutes with it and can join the multiplication where that stands.
+  static const int max_back = getenv("ACE_B200_NO_FUSE2") ? 1 : 2;
+  for (int back = 1; op == OP_ADD && back <= max_back && ops_.size() >= (size_t)back; back++) {
+    const int32_t mi = (int32_t)ops_.size() - back;
+    Op& m = ops_[mi];
     if (m.kind == OP_MUL && m.g == (uint16_t)g && m.r != r && ((b == m.r) != (a == m.r))) {
       const u64* acc = (b == m.r) ? a : b;
       u64*       tmp = m.r;
+      if (back == 2) {
+        const Op& x = ops_.back();
+        const u64* touched[3] = {tmp, acc, r};
+        bool clash = x.kind != OP_MUL;
+        for (const u64* p : touched) clash |= x.r == p;
+        clash |= x.a == tmp || x.a == r || x.b == tmp || x.b == r;
+        // the multiply-add may move to a LATER wave than x (it waits for acc): x must not
+        // overwrite what it still has to read
+        clash |= x.r == m.a || x.r == m.b;
+        if (clash) break;
+      }
       Limb& lt = limb(tmp);
-      if (lt.w_op == (int32_t)ops_.size() - 1 && !lt.read_since) {
+      if (lt.w_op == mi && !lt.read_since) {
         Limb& lacc = limb(acc);
         const bool acc_zero = lacc.is_zero;
         u32 wave = m.wave;
@@ -394,7 +411,7 @@ void Scheduler::ew(SchedOp op, u64* r, const u64* a, const u64* b, u32 g) {
         wave = std::max(wave, dep_write(lr, false));
         m.kind = OP_MAC; m.c = acc_zero ? nullptr : acc; m.t = tmp; m.t_live = 1; m.r = r;
         m.wave = wave;
-        const int32_t idx = (int32_t)ops_.size() - 1;
+        const int32_t idx = mi;
         note_write(lr, wave, false, idx, false);
         Limb& lt2 = limb(tmp);
         lt2.w_wave = wave; lt2.w_is_t = 1; lt2.w_op = idx;

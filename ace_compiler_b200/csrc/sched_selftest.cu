@@ -253,6 +253,21 @@ std::vector<uint64_t> run_program(uint64_t seed, u32 n_ops, u32 sync_permille, b
       SchedOp o = (SchedOp)(OP_ADD + rng.below(3));
       TR("%u ew%d %s = %s , %s\n", op, (int)o, where(limb(br, l)), where(limb(ba, l)), where(limb(bb, l)));
       S.ew(o, limb(br, l), limb(ba, l), limb(bb, l), l);
+    } else if (kind >= 50 && kind < 55) {
+      // the emitted convolutions (GEN20:1494-1500): mul t0 = a0*p; mul t1 = a1*p; add acc0 += t0;
+      // add acc1 += t1 -- the first addition joins a multiplication that is NOT the last op.  Blocks
+      // are drawn at random, so tmp / acc / operands alias now and then: those must not be fused
+      int bt0 = pick(1), bt1 = pick(1), ba0 = pick(1), ba1 = pick(1), bp = pick(1), bc0 = pick(1), bc1 = pick(1);
+      u32 lim = (u32)blk[bt0].n;
+      for (int bx : {bt1, ba0, ba1, bp, bc0, bc1}) lim = std::min(lim, (u32)blk[bx].n);
+      const u32 l = rng.below(lim);
+      TR("%u conv t0=%s t1=%s a0=%s a1=%s p=%s acc0=%s acc1=%s\n", op, where(limb(bt0, l)), where(limb(bt1, l)),
+         where(limb(ba0, l)), where(limb(ba1, l)), where(limb(bp, l)), where(limb(bc0, l)), where(limb(bc1, l)));
+      S.ew(OP_MUL, limb(bt0, l), limb(ba0, l), limb(bp, l), l);
+      S.ew(OP_MUL, limb(bt1, l), limb(ba1, l), limb(bp, l), l);
+      if (rng.below(2)) S.ew(OP_ADD, limb(bc0, l), limb(bc0, l), limb(bt0, l), l);
+      else S.ew(OP_ADD, limb(bc0, l), limb(bt0, l), limb(bc0, l), l);
+      S.ew(OP_ADD, limb(bc1, l), limb(bc1, l), limb(bt1, l), l);
     } else if (kind < 55) {  // Hw_modmul(tmp, a, b); Hw_modadd(acc, acc, tmp)  (emitted pattern)
       int bt = pick(1), ba = pick(1), bb = pick(1), bc = pick(1);
       u32 l = rng.below((u32)std::min(std::min(blk[bt].n, blk[ba].n), std::min(blk[bb].n, blk[bc].n)));
