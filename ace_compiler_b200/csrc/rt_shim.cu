@@ -1357,6 +1357,24 @@ API void Pt_mgr_fini(void) {
   g_lut = nullptr;
   g_nent = 0;
 }
+// Pt_from_msg_validate (pt_mgr.c:193-205; emitted with the compiler's run-time validation option,
+// ir2c_ctx.h:96-100): the constant the program carries must equal the file's entry, then as
+// Pt_from_msg.  float32 message files only, as in the reference.
+API void Pt_from_msg(void* pt, uint32_t index, size_t len, uint32_t scale, uint32_t level);
+API void Pt_from_msg_validate(void* pt, float* buf, uint32_t index, size_t len, uint32_t scale, uint32_t level) {
+  if (g_pt_fd >= 0) die("bad entry type");
+  if (!g_lut || index >= g_nent) die("index out of entry range");
+  const LutEntry& e = g_lut[index];
+  if (g_etype != DE_MSG_F32 || e.size < len * sizeof(float)) die("entry size too small");
+  const float* data = reinterpret_cast<const float*>(g_wfile.data() + e.ent_ofst);
+  for (size_t i = 0; i < len; i++)
+    if (!(fabs(buf[i] - data[i]) < 0.000001)) {
+      fprintf(stderr, "Pt_from_msg_validate failed. index=%u, i=%zu: %f != %f.\n", index, i, buf[i], data[i]);
+      die("Pt_from_msg_validate failed");
+    }
+  Pt_from_msg(pt, index, len, scale, level);
+}
+
 // Pt_from_msg (pt_mgr.c:182-191): look the message up and encode it at run time.  The message
 // is read from the HBM copy of the weight file: no host->device copy, no synchronisation.
 API void Pt_from_msg(void* pt, uint32_t index, size_t len, uint32_t scale, uint32_t level) {

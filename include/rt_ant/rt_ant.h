@@ -260,6 +260,8 @@ void Free_plain_poly(PLAIN plain);
 bool Pt_mgr_init(const char* fname);
 void Pt_mgr_fini(void);
 void Pt_from_msg(void* pt, uint32_t index, size_t len, uint32_t scale, uint32_t level);
+void Pt_from_msg_validate(void* pt, float* buf, uint32_t index, size_t len, uint32_t scale,
+                          uint32_t level); /* include/common/pt_mgr.h:44-46 */
 /* pre-encoded weights (DE_PLAINTEXT data files; include/common/pt_mgr.h:28-38): Pt_get returns a
  * PLAINTEXT whose limbs are in HBM, valid until its slot (index % PT_ENTRY_COUNT) is used again */
 void  Pt_prefetch(uint32_t index);
